@@ -1,0 +1,204 @@
+"""numpy-in / numpy-out adapters over the UNMODIFIED reference numba kernel generators.
+
+TEST INFRASTRUCTURE ONLY; needs /root/reference (build container).  Each adapter passes the same
+static kwargs the reference primitive would pass and has the same
+signature as its counterpart in oracle/__init__.py, so tests can compare them call-for-call.
+"""
+import numpy as np
+
+from . import ref_shim as R
+from . import conn_length
+
+SDS = R.SDS
+available = R.available
+
+
+def _first(o):
+    return o[0] if isinstance(o, (list, tuple)) else o
+
+
+def _spk(v):
+    v = np.ascontiguousarray(v)
+    return v
+
+
+# -- RNG ----------------------------------------------------------------------------------------
+def rng():
+    return R.ref_module("_numba_random")
+
+
+# -- compaction / bitpack -----------------------------------------------------------------------
+def binary_1d_array_index(spikes):
+    m = R.ref_module("_event.compact")
+    s = _spk(spikes)
+    n = s.shape[0]
+    k = m._binary_1d_array_index_numba_kernel(
+        spikes_info=SDS(s.shape, s.dtype), outs=[SDS((n,), np.int32), SDS((1,), np.int32)])
+    ids, na = k(s)
+    return ids, na
+
+
+def binary_2d_array_index(spikes):
+    m = R.ref_module("_event.compact")
+    s = _spk(spikes)
+    n, b = s.shape
+    k = m._binary_2d_array_index_numba_kernel(
+        spikes_info=SDS(s.shape, s.dtype),
+        outs=[SDS((n, (b + 31) // 32), np.uint32), SDS((n,), np.int32), SDS((1,), np.int32)])
+    return tuple(k(s))
+
+
+def binary_2d_compact_only(spikes):
+    m = R.ref_module("_event.compact")
+    s = _spk(spikes)
+    n, b = s.shape
+    k = m._binary_2d_compact_only_numba_kernel(
+        spikes_info=SDS(s.shape, s.dtype), outs=[SDS((n,), np.int32), SDS((1,), np.int32)])
+    return tuple(k(s))
+
+
+def csr_to_csc_index(indptr, indices, shape):
+    m = R.ref_module("_misc")
+    return m._csr_to_csc_index_numpy(np.asarray(indptr), np.asarray(indices), shape=shape)
+
+
+# -- CSR ------------------------------------------------------------------------------------------
+def binary_csrmv(data, indices, indptr, v, *, shape, transpose=False):
+    m = R.ref_module("_csr.binary")
+    data = np.atleast_1d(data)
+    v = _spk(v)
+    out_n = shape[1] if transpose else shape[0]
+    k = m._csrmv_numba_kernel(weight_info=SDS(data.shape, data.dtype),
+                              vector_info=SDS(v.shape, v.dtype), transpose=transpose,
+                              outs=[SDS((out_n,), data.dtype)])
+    return _first(k(data, indices, indptr, v, None, None, None)[0])
+
+
+def binary_csrmm(data, indices, indptr, B, *, shape, transpose=False):
+    m = R.ref_module("_csr.binary")
+    data = np.atleast_1d(data)
+    B = _spk(B)
+    out_n = shape[1] if transpose else shape[0]
+    k = m._csrmm_numba_kernel(weight_info=SDS(data.shape, data.dtype),
+                              vector_info=SDS(B.shape, B.dtype), transpose=transpose,
+                              outs=[SDS((out_n, B.shape[1]), data.dtype)])
+    return _first(k(data, indices, indptr, B, None, None, None)[0])
+
+
+def binary_csrmv_indexed(data, indices, indptr, perm, v, *, shape, transpose=False):
+    m = R.ref_module("_csr.binary_indexed")
+    data = np.atleast_1d(data)
+    v = _spk(v)
+    out_n = shape[1] if transpose else shape[0]
+    k = m._csrmv_indexed_numba_kernel(weight_info=SDS(data.shape, data.dtype),
+                                      vector_info=SDS(v.shape, v.dtype), transpose=transpose,
+                                      outs=[SDS((out_n,), data.dtype)])
+    return _first(k(data, indices, indptr, perm, v, None, None, None)[0])
+
+
+def binary_csrmm_indexed(data, indices, indptr, perm, B, *, shape, transpose=False):
+    m = R.ref_module("_csr.binary_indexed")
+    data = np.atleast_1d(data)
+    B = _spk(B)
+    out_n = shape[1] if transpose else shape[0]
+    k = m._csrmm_indexed_numba_kernel(weight_info=SDS(data.shape, data.dtype),
+                                      vector_info=SDS(B.shape, B.dtype), transpose=transpose,
+                                      outs=[SDS((out_n, B.shape[1]), data.dtype)])
+    return _first(k(data, indices, indptr, perm, B, None, None, None)[0])
+
+
+# -- FCN ------------------------------------------------------------------------------------------
+def binary_fcnmv(weights, indices, spikes, *, shape, transpose=False):
+    m = R.ref_module("_fcn.binary")
+    weights = np.atleast_1d(weights)
+    s = _spk(spikes)
+    out_n = shape[1] if transpose else shape[0]
+    k = m._ell_binary_matvec_numba_kernel(weight_info=SDS(weights.shape, weights.dtype),
+                                          spike_info=SDS(s.shape, s.dtype), transpose=transpose,
+                                          outs=[SDS((out_n,), weights.dtype)])
+    return _first(k(weights, indices, s))
+
+
+def binary_fcnmm(weights, indices, matrix, *, shape, transpose=False):
+    m = R.ref_module("_fcn.binary")
+    weights = np.atleast_1d(weights)
+    s = _spk(matrix)
+    out_n = shape[1] if transpose else shape[0]
+    k = m._binary_fcnmm_numba_kernel(weight_info=SDS(weights.shape, weights.dtype),
+                                     matrix_info=SDS(s.shape, s.dtype), transpose=transpose,
+                                     outs=[SDS((out_n, s.shape[1]), weights.dtype)])
+    return _first(k(weights, indices, s))
+
+
+# -- JITC -----------------------------------------------------------------------------------------
+def _jit(modname, gen, is_mm, params, prob, x, seed, shape, transpose, corder, dtype):
+    m = R.ref_module(modname)
+    x = _spk(x)
+    out_n = shape[1] if transpose else shape[0]
+    oshape = (out_n, x.shape[1]) if is_mm else (out_n,)
+    info_kw = {"B_info" if is_mm else "vector_info": SDS(x.shape, x.dtype)}
+    k = getattr(m, gen)(corder=corder, shape=tuple(shape), outs=[SDS(oshape, dtype)],
+                        transpose=transpose, **info_kw)
+    clen = np.asarray([conn_length(prob)], np.int32)
+    seed = np.asarray([seed], np.int32)
+    ps = [np.asarray([p], dtype) for p in params]
+    if modname.startswith("_jit_scalar"):
+        return _first(k(*ps, clen, x, seed, None))
+    return _first(k(*ps, clen, x, seed))
+
+
+def binary_jitsmv(weight, prob, vector, seed, *, shape, transpose=False, corder=True,
+                  dtype=np.float32):
+    return _jit("_jit_scalar.binary", "_jitsmv_numba_kernel", False, [weight], prob, vector, seed,
+                shape, transpose, corder, dtype)
+
+
+def binary_jitsmm(weight, prob, B, seed, *, shape, transpose=False, corder=True, dtype=np.float32):
+    return _jit("_jit_scalar.binary", "_jitsmm_numba_kernel", True, [weight], prob, B, seed,
+                shape, transpose, corder, dtype)
+
+
+def binary_jitnmv(w_loc, w_scale, prob, vector, seed, *, shape, transpose=False, corder=True,
+                  dtype=np.float32):
+    return _jit("_jit_normal.binary", "_jitc_mv_normal_numba_kernel_generator", False,
+                [w_loc, w_scale], prob, vector, seed, shape, transpose, corder, dtype)
+
+
+def binary_jitnmm(w_loc, w_scale, prob, B, seed, *, shape, transpose=False, corder=True,
+                  dtype=np.float32):
+    return _jit("_jit_normal.binary", "_jitc_mm_normal_numba_kernel_generator", True,
+                [w_loc, w_scale], prob, B, seed, shape, transpose, corder, dtype)
+
+
+def binary_jitumv(w_low, w_high, prob, vector, seed, *, shape, transpose=False, corder=True,
+                  dtype=np.float32):
+    return _jit("_jit_uniform.binary", "_jitumv_numba_kernel_generator", False,
+                [w_low, w_high], prob, vector, seed, shape, transpose, corder, dtype)
+
+
+def binary_jitumm(w_low, w_high, prob, B, seed, *, shape, transpose=False, corder=True,
+                  dtype=np.float32):
+    return _jit("_jit_uniform.binary", "_jitumm_numba_kernel_generator", True,
+                [w_low, w_high], prob, B, seed, shape, transpose, corder, dtype)
+
+
+# -- dense ----------------------------------------------------------------------------------------
+def binary_densemv(weights, spikes, *, transpose):
+    m = R.ref_module("_dense.binary")
+    W = np.ascontiguousarray(weights)
+    s = _spk(spikes)
+    out_n = W.shape[1] if transpose else W.shape[0]
+    k = m._binary_densemv_numba_kernel(spk_info=SDS(s.shape, s.dtype), transpose=transpose,
+                                       outs=[SDS((out_n,), W.dtype)])
+    return _first(k(W, s))
+
+
+def binary_densemm(weights, spikes, *, transpose):
+    m = R.ref_module("_dense.binary")
+    W = np.ascontiguousarray(weights)
+    s = _spk(spikes)
+    out_m = W.shape[1] if transpose else W.shape[0]
+    k = m._binary_densemm_numba_kernel(spk_info=SDS(s.shape, s.dtype),
+                                       weight_info=SDS(W.shape, W.dtype), transpose=transpose,
+                                       outs=[SDS((out_m, s.shape[1]), W.dtype)])
+    return _first(k(W, s))

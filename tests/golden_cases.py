@@ -1,0 +1,65 @@
+"""Re-creates the inputs of tests/golden/ops.npz (same seeds as make_golden.py) and yields
+(tag, callable(impl) -> result, golden, atol) so both the oracle and the CUDA path are checked
+against the reference's own outputs through one table."""
+import os
+
+import numpy as np
+
+from tests import cases
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def load(name):
+    return np.load(os.path.join(GOLD, name + ".npz"))
+
+
+def op_cases():
+    """Yield (tag, fn(api) -> ndarray, atol) for every entry of ops.npz that is a float result."""
+    for homo in (False, True):
+        c = cases.csr_case(4, 300, 200, 9, 0.1, homo=homo, ragged=True)
+        m, k = c["shape"]
+        for tr in (False, True):
+            for fs in (False, True):
+                tag = f"csr_h{int(homo)}_t{int(tr)}_f{int(fs)}"
+                v = cases.spikes(5, m if tr else k, 0.15, fs)
+                B = cases.spikes(6, m if tr else k, 0.1, fs, batch=13)
+                yield (tag + "_mv", (lambda api, c=c, v=v, tr=tr: api.binary_csrmv(
+                    c["data"], c["indices"], c["indptr"], v, shape=c["shape"], transpose=tr)), 1e-6)
+                yield (tag + "_mm", (lambda api, c=c, B=B, tr=tr: api.binary_csrmm(
+                    c["data"], c["indices"], c["indptr"], B, shape=c["shape"], transpose=tr)), 1e-6)
+    for homo in (False, True):
+        c = cases.fcn_case(9, 250, 180, 11, homo=homo)
+        for tr in (False, True):
+            tag = f"fcn_h{int(homo)}_t{int(tr)}"
+            v = cases.spikes(10, 250 if tr else 180, 0.15)
+            B = cases.spikes(11, 250 if tr else 180, 0.1, batch=9)
+            yield (tag + "_mv", (lambda api, c=c, v=v, tr=tr: api.binary_fcnmv(
+                c["weights"], c["indices"], v, shape=(250, 180), transpose=tr)), 1e-6)
+            yield (tag + "_mm", (lambda api, c=c, B=B, tr=tr: api.binary_fcnmm(
+                c["weights"], c["indices"], B, shape=(250, 180), transpose=tr)), 1e-6)
+    shape, prob, seed = (230, 310), 0.05, 1234
+    for fam, params in [("s", (1.5,)), ("n", (1.0, 0.1)), ("u", (-0.5, 1.0))]:
+        # normal: the golden values come from the reference's fastmath numba build, which
+        # deviates from its own strict light_rng_normal01 by up to 3e-4 per edge
+        # (see tests/test_oracle_vs_reference.py::test_jitc).
+        atol = 3e-4 if fam == "n" else 2e-6
+        for tr in (False, True):
+            for co in (False, True):
+                tag = f"jit{fam}_t{int(tr)}_c{int(co)}"
+                vec_len = shape[0] if tr else shape[1]
+                v = cases.spikes(12, vec_len, 0.2)
+                B = cases.spikes(13, vec_len, 0.2, batch=6)
+                yield (tag + "_mv", (lambda api, fam=fam, params=params, v=v, tr=tr, co=co: getattr(
+                    api, f"binary_jit{fam}mv")(*params, prob, v, seed, shape=shape, transpose=tr,
+                                               corder=co)), atol)
+                yield (tag + "_mm", (lambda api, fam=fam, params=params, B=B, tr=tr, co=co: getattr(
+                    api, f"binary_jit{fam}mm")(*params, prob, B, seed, shape=shape, transpose=tr,
+                                               corder=co)), atol)
+    W = np.random.default_rng(14).standard_normal((90, 130)).astype(np.float32)
+    for tr in (False, True):
+        k = W.shape[0] if tr else W.shape[1]
+        v = cases.spikes(15, k, 0.2)
+        B = cases.spikes(16, k, 0.2, batch=7)
+        yield (f"dense_t{int(tr)}_mv", (lambda api, v=v, tr=tr: api.binary_densemv(W, v, transpose=tr)), 1e-5)
+        yield (f"dense_t{int(tr)}_mm", (lambda api, B=B, tr=tr: api.binary_densemm(W, B, transpose=tr)), 1e-5)
