@@ -1,0 +1,256 @@
+"""Just-in-time connectivity event operators and matrix classes.
+
+Mirrors ref: brainevent/_jit_scalar/binary.py (:44, :171), _jit_normal/binary.py (:44, :177),
+_jit_uniform/binary.py (:44, :177) and the R/C classes in _jit_*/main.py.  The connectivity is
+regenerated in-kernel from (seed, row, chunk, lane); `corder` picks gather (True) vs scatter
+(False) exactly as in the reference (_jit_scalar/binary.py:438-439), `transpose` only fixes the
+output shape, and chunk_size = ceil(shape[1]/4) of the *passed* shape (_misc.py:74-122).
+"""
+import math
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._csr import _EVENT_TYPES
+from ._event import BinaryArray
+from ._op import XLACustomKernel, maybe_decimal, split_mantissa_unit
+from ._runtime import as_tensor, event_args, ptr, stream_ptr, workspace, wt_code
+
+MV_STRIDE, MM_STRIDE = 32, 4   # ref: _misc.py:37-38
+_KIND = {"scalar": _lib.JIT_SCALAR, "normal": _lib.JIT_NORMAL, "uniform": _lib.JIT_UNIFORM}
+
+
+def _normalize_chunk_size(n_cols, chunk_size=None, target_chunks=4):
+    """ref: _misc.py:74-122"""
+    if chunk_size is None:
+        target_chunks = int(target_chunks)
+        if target_chunks <= 0:
+            raise ValueError("target_chunks must be positive")
+        chunk_size = max(1, (int(n_cols) + target_chunks - 1) // target_chunks)
+    chunk_size = int(chunk_size)
+    if chunk_size <= 0:
+        raise ValueError("chunk_size must be positive")
+    return chunk_size
+
+
+def _initialize_seed(seed=None, device="cuda"):
+    """int32[1] on the device (ref: _data.py:1181-1210)."""
+    if seed is None:
+        seed = np.random.randint(0, int(1e8))
+    if isinstance(seed, torch.Tensor):
+        return seed.reshape(-1)[:1].to(device=device, dtype=torch.int32)
+    return torch.tensor([int(np.asarray(seed).reshape(-1)[0])], dtype=torch.int64, device=device).to(torch.int32)
+
+
+def _initialize_conn_length(conn_prob, device="cuda"):
+    """clen = ceil(2 / prob) as int32[1] (ref: _data.py:1212-1245)."""
+    clen = int(np.asarray(np.ceil(2.0 / float(conn_prob)), dtype=np.int32))
+    return torch.tensor([clen], dtype=torch.int32, device=device)
+
+
+def _jit_kernel(outs=None, shape=None, transpose=False, corder=True, kind="scalar", matmat=False,
+                row_window=None, col_window=None, **kw):
+    def kernel(p0, p1, clen, seed, ev):
+        out_len = shape[1] if transpose else shape[0]
+        vec_len = shape[0] if transpose else shape[1]
+        chunk = _normalize_chunk_size(shape[1])
+        dev = p0.device
+        L = _lib.lib()
+        if matmat:
+            n = ev.batch
+            out = torch.empty((out_len, n), dtype=p0.dtype, device=dev)
+            ws = workspace(dev, ev.n, n)
+            rc = L.be_b200_binary_jitmm(_KIND[kind], ptr(p0), ptr(p1), wt_code(p0.dtype), ptr(clen), ptr(seed),
+                                        ptr(ev.spikes), ptr(ev.aux), ev.kind, vec_len, out_len, n, chunk,
+                                        int(corder), ptr(out), ptr(ws), ws.numel(), stream_ptr(dev))
+            _lib.check(rc, "binary_jitmm")
+        else:
+            r0, rn = row_window if row_window is not None else (0, -1)
+            c0, c1 = col_window if col_window is not None else (0, -1)
+            n_local = (rn if (corder and rn >= 0) else out_len) if corder else ((c1 - c0) if c1 >= 0 else out_len)
+            out = torch.empty(n_local, dtype=p0.dtype, device=dev)
+            ws = workspace(dev, ev.n, 1)
+            rc = L.be_b200_binary_jitmv(_KIND[kind], ptr(p0), ptr(p1), wt_code(p0.dtype), ptr(clen), ptr(seed),
+                                        ptr(ev.spikes), ptr(ev.aux), ev.kind, vec_len, out_len, chunk,
+                                        int(corder), r0, rn, c0, c1, ptr(out), ptr(ws), ws.numel(),
+                                        stream_ptr(dev))
+            _lib.check(rc, "binary_jitmv")
+        return [out]
+    return kernel
+
+
+def _make_prim(name, kind, matmat):
+    p = XLACustomKernel(name)
+    p.def_kernel("b200", "gpu", lambda **kw: _jit_kernel(kind=kind, matmat=matmat, **kw), asdefault=True)
+    p.def_tags("jit_" + kind, "binary")
+    return p
+
+
+binary_jitsmv_p = _make_prim("binary_jitsmv", "scalar", False)
+binary_jitsmm_p = _make_prim("binary_jitsmm", "scalar", True)
+binary_jitnmv_p = _make_prim("binary_jitnmv", "normal", False)
+binary_jitnmm_p = _make_prim("binary_jitnmm", "normal", True)
+binary_jitumv_p = _make_prim("binary_jitumv", "uniform", False)
+binary_jitumm_p = _make_prim("binary_jitumm", "uniform", True)
+
+
+def _param(x, device, dtype):
+    t = as_tensor(x, device=device)
+    if not t.dtype.is_floating_point:
+        t = t.to(dtype or torch.float32)
+    elif dtype is not None and t.dtype != dtype:
+        t = t.to(dtype)
+    return t.reshape(-1)[:1].contiguous()
+
+
+def _jit_p_call(prim, params, clen, x, seed, shape, transpose, corder, backend, matmat, **extra):
+    ev = event_args(x)
+    dev = ev.device
+    assert len(shape) == 2, "The matrix shape should be a tuple of two integers."
+    shape = (int(shape[0]), int(shape[1]))
+    p0 = _param(params[0], dev, None)
+    p1 = _param(params[1], dev, p0.dtype) if len(params) > 1 else None
+    clen = as_tensor(clen, device=dev, dtype=torch.int32).reshape(-1)
+    seed = as_tensor(seed, device=dev, dtype=torch.int32).reshape(-1)
+    assert clen.shape == (1,), f"The clen shape should be (1,), but got {tuple(clen.shape)}."
+    assert seed.shape == (1,), f"The seed shape should be (1,), but got {tuple(seed.shape)}."
+    assert (ev.batch is not None) == matmat, "event rank does not match the operator"
+    if transpose:
+        assert shape[0] == ev.n, f"The matrix shape and vector length do not match. {ev.n} @ {shape}"
+    else:
+        assert shape[1] == ev.n, f"The matrix shape and vector length do not match. {shape} @ {ev.n}"
+    return prim(p0, p1, clen, seed, ev, outs=None, shape=shape, transpose=bool(transpose),
+                corder=bool(corder), backend=backend, **extra)
+
+
+def _public(prim, n_params, matmat, doc):
+    def op(*args, shape, transpose=False, corder=True, backend=None, **extra):
+        params, (prob, x, seed) = args[:n_params], args[n_params:]
+        units = []
+        vals = []
+        for p in params:
+            v, un = split_mantissa_unit(p)
+            vals.append(v)
+            units.append(un)
+        x, unx = split_mantissa_unit(x)
+        dev = event_args(x).device
+        seed = _initialize_seed(seed, dev)
+        clen = _initialize_conn_length(prob, dev)
+        res = _jit_p_call(prim, vals, clen, x, seed, shape, transpose, corder, backend, matmat, **extra)[0]
+        return maybe_decimal(res, units[0], unx)
+    op.__doc__ = doc
+    return op
+
+
+binary_jitsmv = _public(binary_jitsmv_p, 1, False, "binary_jitsmv(weight, prob, vector, seed, *, shape, transpose, corder); ref: _jit_scalar/binary.py:44")
+binary_jitsmm = _public(binary_jitsmm_p, 1, True, "binary_jitsmm(weight, prob, B, seed, *, shape, transpose, corder); ref: _jit_scalar/binary.py:171")
+binary_jitnmv = _public(binary_jitnmv_p, 2, False, "binary_jitnmv(w_loc, w_scale, prob, vector, seed, ...); ref: _jit_normal/binary.py:44")
+binary_jitnmm = _public(binary_jitnmm_p, 2, True, "binary_jitnmm(w_loc, w_scale, prob, B, seed, ...); ref: _jit_normal/binary.py:177")
+binary_jitumv = _public(binary_jitumv_p, 2, False, "binary_jitumv(w_low, w_high, prob, vector, seed, ...); ref: _jit_uniform/binary.py:44")
+binary_jitumm = _public(binary_jitumm_p, 2, True, "binary_jitumm(w_low, w_high, prob, B, seed, ...); ref: _jit_uniform/binary.py:177")
+
+
+def jitc_row_connections(prob, seed, rows, k, chunk_size, stride=MV_STRIDE, device="cuda", cap=None):
+    """Connectivity dump for parity: (counts int32[n_rows], cols int32[n_rows, cap]) of generated
+    rows `rows` = (begin, n) in walk order.  ref: _jit_scalar/csr.py (count/fill)."""
+    begin, n_rows = rows
+    clen = _initialize_conn_length(prob, device)
+    seed_t = _initialize_seed(seed, device)
+    if cap is None:
+        cap = int(2.5 * k * float(prob)) + 64
+    counts = torch.zeros(n_rows, dtype=torch.int32, device=device)
+    cols = torch.full((n_rows, cap), -1, dtype=torch.int32, device=device)
+    _lib.check(_lib.lib().be_b200_jitc_row_connections(ptr(clen), ptr(seed_t), begin, n_rows, k, chunk_size,
+                                                       stride, ptr(counts), ptr(cols), cap,
+                                                       stream_ptr(torch.device(device))), "jitc_row_connections")
+    return counts, cols
+
+
+# ---------------------------------------------------------------------------------------------
+# matrix classes
+# ---------------------------------------------------------------------------------------------
+class JITCMatrix:
+    """Base of the just-in-time connectivity matrices (ref: _data.py JITCMatrix)."""
+    _mv = _mm = None
+
+    def __init__(self, params, prob, seed, *, shape, corder=False, backend=None):
+        self.params = tuple(params)
+        self.prob = float(prob)
+        self.seed = seed
+        self.shape = (int(shape[0]), int(shape[1]))
+        self.corder = bool(corder)
+        self.backend = backend
+
+    def _call(self, other, shape, transpose, corder):
+        mv, mm = type(self)._mv, type(self)._mm
+        if not isinstance(other, _EVENT_TYPES):
+            raise NotImplementedError("brainevent_b200 implements the event-driven path only: wrap the "
+                                      "operand in BinaryArray / BitPackedBinary / CompactBinary")
+        if other.ndim == 1:
+            return mv(*self.params, self.prob, other, self.seed, shape=shape, transpose=transpose,
+                      corder=corder, backend=self.backend)
+        if other.ndim == 2:
+            return mm, other
+        raise NotImplementedError(f"matmul with object of shape {other.shape}")
+
+
+class _JITC_R(JITCMatrix):
+    """Row-oriented: the generated matrix has the logical shape (ref: _jit_scalar/main.py:885-1066)."""
+
+    def __matmul__(self, other):
+        r = self._call(other, self.shape, False, self.corder)
+        if isinstance(r, tuple):
+            mm, other = r
+            return mm(*self.params, self.prob, other, self.seed, shape=self.shape, transpose=False,
+                      corder=self.corder, backend=self.backend)
+        return r
+
+    def __rmatmul__(self, other):
+        r = self._call(other, self.shape, True, not self.corder)
+        if isinstance(r, tuple):
+            mm, other = r
+            if not isinstance(other, BinaryArray):
+                raise NotImplementedError("2-D packed events must be packed along the batch axis")
+            return mm(*self.params, self.prob, other.value.t(), self.seed, shape=self.shape, transpose=True,
+                      corder=not self.corder, backend=self.backend).t()
+        return r
+
+
+class _JITC_C(JITCMatrix):
+    """Column-oriented: the generator is invoked with shape[::-1] (ref: _jit_scalar/main.py:1392-1593),
+    so R and C of the same logical shape draw different matrices."""
+
+    def __matmul__(self, other):
+        r = self._call(other, self.shape[::-1], True, self.corder)
+        if isinstance(r, tuple):
+            mm, other = r
+            return mm(*self.params, self.prob, other, self.seed, shape=self.shape[::-1], transpose=True,
+                      corder=self.corder, backend=self.backend)
+        return r
+
+    def __rmatmul__(self, other):
+        r = self._call(other, self.shape[::-1], False, not self.corder)
+        if isinstance(r, tuple):
+            mm, other = r
+            if not isinstance(other, BinaryArray):
+                raise NotImplementedError("2-D packed events must be packed along the batch axis")
+            return mm(*self.params, self.prob, other.value.t(), self.seed, shape=self.shape[::-1],
+                      transpose=False, corder=not self.corder, backend=self.backend).t()
+        return r
+
+
+def _cls(name, base, mv, mm, n_params, doc):
+    def __init__(self, data, *, shape, corder=False, backend=None):
+        *params, prob, seed = data
+        assert len(params) == n_params, f"{name} expects ({', '.join(['w'] * n_params)}, prob, seed)"
+        base.__init__(self, params, prob, seed, shape=shape, corder=corder, backend=backend)
+    return type(name, (base,), {"__init__": __init__, "_mv": staticmethod(mv), "_mm": staticmethod(mm), "__doc__": doc})
+
+
+JITCScalarR = _cls("JITCScalarR", _JITC_R, binary_jitsmv, binary_jitsmm, 1, "JITCScalarR((weight, prob, seed), shape=...)")
+JITCScalarC = _cls("JITCScalarC", _JITC_C, binary_jitsmv, binary_jitsmm, 1, "JITCScalarC((weight, prob, seed), shape=...)")
+JITCNormalR = _cls("JITCNormalR", _JITC_R, binary_jitnmv, binary_jitnmm, 2, "JITCNormalR((loc, scale, prob, seed), shape=...)")
+JITCNormalC = _cls("JITCNormalC", _JITC_C, binary_jitnmv, binary_jitnmm, 2, "JITCNormalC((loc, scale, prob, seed), shape=...)")
+JITCUniformR = _cls("JITCUniformR", _JITC_R, binary_jitumv, binary_jitumm, 2, "JITCUniformR((low, high, prob, seed), shape=...)")
+JITCUniformC = _cls("JITCUniformC", _JITC_C, binary_jitumv, binary_jitumm, 2, "JITCUniformC((low, high, prob, seed), shape=...)")

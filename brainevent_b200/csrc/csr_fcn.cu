@@ -1,0 +1,531 @@
+// csr_fcn.cu -- event-driven propagation through stored connectivity (CSR/CSC and fixed-number/ELL).
+//
+// Replaces ref: _csr/binary_csrmv.cu (NT gather), _csr/binary_csrmv_hybrid.cu (T scatter),
+// _csr/binary_csrmm{,_hybrid}.cu, _csr/binary_indexed_csrm{v,m}{,_hybrid}.cu,
+// _fcn/binary_fcnmv.cu, _fcn/binary_fcnmm.cu.
+//
+// Design (B200-first, not a port):
+//  * scatter ("transpose"): driven by the ordered active-row list from events.cu, so only active
+//    rows are touched; a group of lanes streams a row's indices/weights with 128-bit
+//    L1-bypassing loads and issues fire-and-forget RED.ADD to the L2-resident output.  Rows
+//    longer than kHeavyRow are deferred and processed by the whole CTA.
+//  * gather ("no transpose"): deterministic, no atomics; every output row tests its sources
+//    against the bit-packed spike vector (8x smaller than a byte mask, L1/L2 resident) and loads
+//    a 16-byte weight quad only when one of its four sources fired.
+//  * mm: the connectivity row is read ONCE per call and applied to every batch column
+//    (the reference loops over columns on the host); outputs are [rows, batch] with
+//    batch innermost so one synapse touches one contiguous segment.
+#include "common.cuh"
+
+#include <algorithm>
+#include <type_traits>
+
+namespace be {
+
+constexpr int kHeavyRow = 8192;   // rows longer than this are processed by the whole CTA
+constexpr int kHeavyCap = 32;     // deferred heavy rows per CTA before falling back to the warp
+
+// ------------------------------------------------------------------------------------------
+// row accessors
+// ------------------------------------------------------------------------------------------
+template <typename PT>
+struct CsrRows {
+    const PT* indptr;
+    __device__ __forceinline__ void get(int64_t r, int64_t& s, int64_t& e) const {
+        s = (int64_t)__ldg(indptr + r);
+        e = (int64_t)__ldg(indptr + r + 1);
+    }
+};
+struct FcnRows {
+    int64_t n_conn;
+    __device__ __forceinline__ void get(int64_t r, int64_t& s, int64_t& e) const {
+        s = r * n_conn;
+        e = s + n_conn;
+    }
+};
+
+template <typename T, bool HOMO, int PERM>
+__device__ __forceinline__ typename Acc<T>::type weight_at(const T* __restrict__ w,
+                                                           const void* __restrict__ perm,
+                                                           int64_t j, typename Acc<T>::type w0) {
+    if (HOMO) return w0;
+    if (PERM == 1) return to_acc<T>(__ldg(w + __ldg((const int32_t*)perm + j)));
+    if (PERM == 2) return to_acc<T>(__ldg(w + __ldg((const int64_t*)perm + j)));
+    return to_acc<T>(__ldg(w + j));
+}
+
+// ------------------------------------------------------------------------------------------
+// scatter, matvec:  out[indices[j]] += w[j]  for j in rows of active sources
+// ------------------------------------------------------------------------------------------
+template <typename T, bool HOMO, int PERM, bool VEC, int G>
+__device__ __forceinline__ void scatter_segment(int64_t s, int64_t e, int gl,
+                                                const int32_t* __restrict__ indices,
+                                                const T* __restrict__ weights,
+                                                const void* __restrict__ perm,
+                                                typename Acc<T>::type w0, T* __restrict__ out) {
+    using A = typename Acc<T>::type;
+    if (!VEC) {
+        for (int64_t j = s + gl; j < e; j += G)
+            red_add(out + __ldg(indices + j), weight_at<T, HOMO, PERM>(weights, perm, j, w0));
+        return;
+    }
+    int64_t a = (s + 3) & ~(int64_t)3;
+    if (a > e) a = e;
+    if (gl < a - s) red_add(out + __ldg(indices + s + gl), weight_at<T, HOMO, PERM>(weights, perm, s + gl, w0));
+    int64_t aend = a + ((e - a) & ~(int64_t)3);
+#pragma unroll 2
+    for (int64_t j = a + (int64_t)gl * 4; j < aend; j += (int64_t)G * 4) {
+        int4 ix = ldg_stream((const int4*)(indices + j));
+        A wv[4];
+        if (HOMO) { wv[0] = wv[1] = wv[2] = wv[3] = w0; }
+        else if (PERM == 0) { Vec4<T> v = load4(weights + j); wv[0] = v.v[0]; wv[1] = v.v[1]; wv[2] = v.v[2]; wv[3] = v.v[3]; }
+        else {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) wv[q] = weight_at<T, HOMO, PERM>(weights, perm, j + q, w0);
+        }
+        red_add(out + ix.x, wv[0]);
+        red_add(out + ix.y, wv[1]);
+        red_add(out + ix.z, wv[2]);
+        red_add(out + ix.w, wv[3]);
+    }
+    if (gl < e - aend) red_add(out + __ldg(indices + aend + gl), weight_at<T, HOMO, PERM>(weights, perm, aend + gl, w0));
+}
+
+template <typename T, bool HOMO, int PERM, bool VEC, int LPR, typename Rows>
+__global__ void __launch_bounds__(256) scatter_mv_kernel(Rows rows, const int32_t* __restrict__ indices,
+                                                         const T* __restrict__ weights,
+                                                         const void* __restrict__ perm,
+                                                         const int32_t* __restrict__ ids,
+                                                         const int* __restrict__ n_active_ptr,
+                                                         T* __restrict__ out) {
+    using A = typename Acc<T>::type;
+    __shared__ int s_heavy[kHeavyCap];
+    __shared__ int s_nheavy;
+    if (threadIdx.x == 0) s_nheavy = 0;
+    __syncthreads();
+    const int n_active = *n_active_ptr;
+    const A w0 = HOMO ? to_acc<T>(__ldg(weights)) : A(0);
+    constexpr int GROUPS = 256 / LPR;
+    const int g = threadIdx.x / LPR, gl = threadIdx.x % LPR;
+    for (int64_t a = (int64_t)blockIdx.x * GROUPS + g; a < n_active; a += (int64_t)gridDim.x * GROUPS) {
+        const int r = __ldg(ids + a);
+        int64_t s, e;
+        rows.get(r, s, e);
+        if (e - s > kHeavyRow) {
+            int slot = -1;
+            if (gl == 0) slot = atomicAdd(&s_nheavy, 1);
+            const int leader = ((threadIdx.x & 31) / LPR) * LPR;
+            const unsigned gmask = (LPR >= 32) ? 0xffffffffu : (((1u << LPR) - 1u) << leader);
+            slot = __shfl_sync(gmask, slot, leader);
+            if (slot < kHeavyCap) { if (gl == 0) s_heavy[slot] = r; continue; }
+        }
+        scatter_segment<T, HOMO, PERM, VEC, LPR>(s, e, gl, indices, weights, perm, w0, out);
+    }
+    __syncthreads();
+    const int nh = min(s_nheavy, kHeavyCap);
+    for (int h = 0; h < nh; ++h) {
+        int64_t s, e;
+        rows.get(s_heavy[h], s, e);
+        scatter_segment<T, HOMO, PERM, VEC, 256>(s, e, threadIdx.x, indices, weights, perm, w0, out);
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// gather, matvec:  out[i] = sum_j w[j] * bit(indices[j])   (all rows, deterministic)
+// ------------------------------------------------------------------------------------------
+template <typename T, bool HOMO, int PERM, bool VEC, int LPR, typename Rows>
+__global__ void __launch_bounds__(256) gather_mv_kernel(Rows rows, const int32_t* __restrict__ indices,
+                                                        const T* __restrict__ weights,
+                                                        const void* __restrict__ perm,
+                                                        const uint32_t* __restrict__ packed,
+                                                        int64_t n_rows, T* __restrict__ out) {
+    using A = typename Acc<T>::type;
+    const A w0 = HOMO ? to_acc<T>(__ldg(weights)) : A(0);
+    constexpr int GROUPS = 256 / LPR;
+    const int g = threadIdx.x / LPR, gl = threadIdx.x % LPR;
+    const int64_t row_iters = ceil_div(n_rows, (int64_t)gridDim.x * GROUPS);
+    for (int64_t it = 0; it < row_iters; ++it) {
+        const int64_t r = (it * gridDim.x + blockIdx.x) * GROUPS + g;
+        A acc = A(0);
+        int cnt = 0;
+        if (r < n_rows) {
+            int64_t s, e;
+            rows.get(r, s, e);
+            int64_t a = s, aend = s;
+            if (VEC) {
+                a = (s + 3) & ~(int64_t)3;
+                if (a > e) a = e;
+                aend = a + ((e - a) & ~(int64_t)3);
+                if (gl < a - s && bit_test(packed, __ldg(indices + s + gl))) {
+                    if (HOMO) ++cnt; else acc += weight_at<T, HOMO, PERM>(weights, perm, s + gl, w0);
+                }
+#pragma unroll 2
+                for (int64_t j = a + (int64_t)gl * 4; j < aend; j += (int64_t)LPR * 4) {
+                    int4 ix = ldg_stream((const int4*)(indices + j));
+                    bool b0 = bit_test(packed, ix.x), b1 = bit_test(packed, ix.y),
+                         b2 = bit_test(packed, ix.z), b3 = bit_test(packed, ix.w);
+                    if (HOMO) cnt += (int)b0 + (int)b1 + (int)b2 + (int)b3;
+                    else if (b0 | b1 | b2 | b3) {
+                        if (PERM == 0) {
+                            Vec4<T> v = load4(weights + j);
+                            acc += (b0 ? v.v[0] : A(0)) + (b1 ? v.v[1] : A(0)) + (b2 ? v.v[2] : A(0)) + (b3 ? v.v[3] : A(0));
+                        } else {
+                            if (b0) acc += weight_at<T, HOMO, PERM>(weights, perm, j, w0);
+                            if (b1) acc += weight_at<T, HOMO, PERM>(weights, perm, j + 1, w0);
+                            if (b2) acc += weight_at<T, HOMO, PERM>(weights, perm, j + 2, w0);
+                            if (b3) acc += weight_at<T, HOMO, PERM>(weights, perm, j + 3, w0);
+                        }
+                    }
+                }
+                if (gl < e - aend && bit_test(packed, __ldg(indices + aend + gl))) {
+                    if (HOMO) ++cnt; else acc += weight_at<T, HOMO, PERM>(weights, perm, aend + gl, w0);
+                }
+            } else {
+                for (int64_t j = s + gl; j < e; j += LPR)
+                    if (bit_test(packed, __ldg(indices + j))) {
+                        if (HOMO) ++cnt; else acc += weight_at<T, HOMO, PERM>(weights, perm, j, w0);
+                    }
+            }
+        }
+        if (HOMO) {
+#pragma unroll
+            for (int o = LPR / 2; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+            acc = w0 * (A)cnt;
+        } else {
+#pragma unroll
+            for (int o = LPR / 2; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+        }
+        if (gl == 0 && r < n_rows) out[r] = from_acc<T>(acc);
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// scatter, matmat: out[indices[j], c] += w[j] for every active column c of an active row.
+// One warp per active row; the row's connectivity is read once.  Sparse column masks use
+// lanes = synapses (32 REDs per instruction); dense masks use lanes = columns (contiguous REDs).
+// ------------------------------------------------------------------------------------------
+constexpr int kMaxWpr = 8;  // register-resident mask words (batch <= 256); wider batches loop
+
+template <typename T, bool HOMO, int PERM, typename Rows>
+__global__ void __launch_bounds__(256) scatter_mm_kernel(Rows rows, const int32_t* __restrict__ indices,
+                                                         const T* __restrict__ weights,
+                                                         const void* __restrict__ perm,
+                                                         const int32_t* __restrict__ ids,
+                                                         const int* __restrict__ n_active_ptr,
+                                                         const uint32_t* __restrict__ packed, int wpr,
+                                                         int64_t n, T* __restrict__ out) {
+    using A = typename Acc<T>::type;
+    const int n_active = *n_active_ptr;
+    const A w0 = HOMO ? to_acc<T>(__ldg(weights)) : A(0);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int64_t a = (int64_t)blockIdx.x * 8 + warp; a < n_active; a += (int64_t)gridDim.x * 8) {
+        const int r = __ldg(ids + a);
+        int64_t s, e;
+        rows.get(r, s, e);
+        const uint32_t* mrow = packed + (int64_t)r * wpr;
+        for (int w_base = 0; w_base < wpr; w_base += kMaxWpr) {
+            uint32_t mask[kMaxWpr];
+            int pc = 0;
+#pragma unroll
+            for (int q = 0; q < kMaxWpr; ++q) {
+                mask[q] = (w_base + q < wpr) ? __ldg(mrow + w_base + q) : 0u;
+                pc += __popc(mask[q]);
+            }
+            if (pc == 0) continue;
+            if (pc <= 8) {
+                // lanes = synapses
+                for (int64_t j = s + lane; j < e; j += 32) {
+                    const int64_t o = (int64_t)__ldg(indices + j) * n + (int64_t)w_base * 32;
+                    const A wv = weight_at<T, HOMO, PERM>(weights, perm, j, w0);
+#pragma unroll
+                    for (int q = 0; q < kMaxWpr; ++q) {
+                        uint32_t m = mask[q];
+                        while (m) {
+                            int c = __ffs(m) - 1;
+                            m &= m - 1;
+                            red_add(out + o + q * 32 + c, wv);
+                        }
+                    }
+                }
+            } else {
+                // lanes = columns: broadcast one synapse at a time
+                for (int64_t j0 = s; j0 < e; j0 += 32) {
+                    const int64_t j = j0 + lane;
+                    int64_t my_o = 0;
+                    A my_w = A(0);
+                    if (j < e) {
+                        my_o = (int64_t)__ldg(indices + j) * n + (int64_t)w_base * 32;
+                        my_w = weight_at<T, HOMO, PERM>(weights, perm, j, w0);
+                    }
+                    const int cnt = (int)min((int64_t)32, e - j0);
+                    for (int t = 0; t < cnt; ++t) {
+                        const int64_t o = __shfl_sync(0xffffffffu, my_o, t);
+                        const A wv = __shfl_sync(0xffffffffu, my_w, t);
+#pragma unroll
+                        for (int q = 0; q < kMaxWpr; ++q)
+                            if ((mask[q] >> lane) & 1u) red_add(out + o + q * 32 + lane, wv);
+                    }
+                }
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// gather, matmat: out[i, c] = sum_j w[j] * bit(B[indices[j], c]); lanes = columns,
+// CPL columns per lane (batch tile of 32*CPL columns per pass).
+// ------------------------------------------------------------------------------------------
+template <typename T, bool HOMO, int PERM, int CPL, typename Rows>
+__global__ void __launch_bounds__(256) gather_mm_kernel(Rows rows, const int32_t* __restrict__ indices,
+                                                        const T* __restrict__ weights,
+                                                        const void* __restrict__ perm,
+                                                        const uint32_t* __restrict__ packed, int wpr,
+                                                        int64_t n_rows, int64_t n, T* __restrict__ out) {
+    using A = typename Acc<T>::type;
+    const A w0 = HOMO ? to_acc<T>(__ldg(weights)) : A(0);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int n_pass = (wpr + CPL - 1) / CPL;
+    for (int64_t r = (int64_t)blockIdx.x * 8 + warp; r < n_rows; r += (int64_t)gridDim.x * 8) {
+        int64_t s, e;
+        rows.get(r, s, e);
+        for (int pass = 0; pass < n_pass; ++pass) {
+            const int wb = pass * CPL;
+            A acc[CPL];
+#pragma unroll
+            for (int q = 0; q < CPL; ++q) acc[q] = A(0);
+            for (int64_t j0 = s; j0 < e; j0 += 32) {
+                const int64_t j = j0 + lane;
+                uint32_t mw[CPL];
+                A my_w = A(0);
+                bool nz = false;
+#pragma unroll
+                for (int q = 0; q < CPL; ++q) mw[q] = 0u;
+                if (j < e) {
+                    const uint32_t* brow = packed + (int64_t)__ldg(indices + j) * wpr + wb;
+#pragma unroll
+                    for (int q = 0; q < CPL; ++q) {
+                        mw[q] = (wb + q < wpr) ? __ldg(brow + q) : 0u;
+                        nz |= (mw[q] != 0u);
+                    }
+                    if (nz) my_w = weight_at<T, HOMO, PERM>(weights, perm, j, w0);
+                }
+                uint32_t live = __ballot_sync(0xffffffffu, nz);
+                while (live) {
+                    const int t = __ffs(live) - 1;
+                    live &= live - 1;
+                    const A wv = __shfl_sync(0xffffffffu, my_w, t);
+#pragma unroll
+                    for (int q = 0; q < CPL; ++q) {
+                        const uint32_t m = __shfl_sync(0xffffffffu, mw[q], t);
+                        if ((m >> lane) & 1u) acc[q] += wv;
+                    }
+                }
+            }
+#pragma unroll
+            for (int q = 0; q < CPL; ++q) {
+                const int64_t c = (int64_t)(wb + q) * 32 + lane;
+                if (c < n) out[r * n + c] = from_acc<T>(acc[q]);
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// launch helpers
+// ------------------------------------------------------------------------------------------
+static inline bool al16(const void* p) { return ((uintptr_t)p & 15u) == 0; }
+
+struct ConnArgs {
+    const void* weights;
+    int w_dtype, homo;
+    const int32_t* indices;
+    const void* perm;
+    int perm_kind;  // 0 none, 1 int32, 2 int64
+    double avg_row;  // mean synapses per row (launch-shape heuristic only)
+};
+
+template <typename T, bool HOMO, int PERM, typename Rows>
+static int launch_scatter_mv(const Rows& rows, const ConnArgs& c, const Events& ev, int64_t n_src,
+                             T* out, cudaStream_t s) {
+    const bool vec = al16(c.indices) && (c.homo || al16(c.weights));
+    const bool narrow = c.avg_row < 40.0;
+    const int groups = narrow ? 32 : 8;
+    int blocks = (int)std::min<int64_t>(ceil_div(std::max<int64_t>(n_src, 1), groups), kNumSM * 8);
+#define BE_SC(VEC, LPR)                                                                      \
+    scatter_mv_kernel<T, HOMO, PERM, VEC, LPR, Rows><<<blocks, 256, 0, s>>>(                 \
+        rows, c.indices, (const T*)c.weights, c.perm, ev.active_ids, ev.n_active, out)
+    if (vec) { if (narrow) BE_SC(true, 8); else BE_SC(true, 32); }
+    else { if (narrow) BE_SC(false, 8); else BE_SC(false, 32); }
+#undef BE_SC
+    BE_LAUNCH_CHECK("scatter_mv_kernel");
+    return BE_B200_OK;
+}
+
+template <typename T, bool HOMO, int PERM, typename Rows>
+static int launch_gather_mv(const Rows& rows, const ConnArgs& c, const Events& ev, int64_t n_rows,
+                            T* out, cudaStream_t s) {
+    if (n_rows == 0) return BE_B200_OK;
+    const bool vec = al16(c.indices) && (c.homo || al16(c.weights));
+    const int lpr = c.avg_row <= 12 ? 4 : (c.avg_row <= 48 ? 8 : (c.avg_row <= 160 ? 16 : 32));
+    int blocks = (int)std::min<int64_t>(ceil_div(n_rows, 256 / lpr), (int64_t)kNumSM * 16);
+#define BE_GA(VEC, LPR)                                                                      \
+    gather_mv_kernel<T, HOMO, PERM, VEC, LPR, Rows><<<blocks, 256, 0, s>>>(                  \
+        rows, c.indices, (const T*)c.weights, c.perm, ev.packed, n_rows, out)
+#define BE_GA2(VEC) switch (lpr) { case 4: BE_GA(VEC, 4); break; case 8: BE_GA(VEC, 8); break; \
+                                   case 16: BE_GA(VEC, 16); break; default: BE_GA(VEC, 32); }
+    if (vec) { BE_GA2(true) } else { BE_GA2(false) }
+#undef BE_GA2
+#undef BE_GA
+    BE_LAUNCH_CHECK("gather_mv_kernel");
+    return BE_B200_OK;
+}
+
+template <typename T, bool HOMO, int PERM, typename Rows>
+static int launch_scatter_mm(const Rows& rows, const ConnArgs& c, const Events& ev, int64_t n_src,
+                             int64_t n, T* out, cudaStream_t s) {
+    int blocks = (int)std::min<int64_t>(ceil_div(std::max<int64_t>(n_src, 1), 8), kNumSM * 8);
+    scatter_mm_kernel<T, HOMO, PERM, Rows><<<blocks, 256, 0, s>>>(
+        rows, c.indices, (const T*)c.weights, c.perm, ev.active_ids, ev.n_active, ev.packed,
+        ev.words_per_row, n, out);
+    BE_LAUNCH_CHECK("scatter_mm_kernel");
+    return BE_B200_OK;
+}
+
+template <typename T, bool HOMO, int PERM, typename Rows>
+static int launch_gather_mm(const Rows& rows, const ConnArgs& c, const Events& ev, int64_t n_rows,
+                            int64_t n, T* out, cudaStream_t s) {
+    if (n_rows == 0) return BE_B200_OK;
+    int blocks = (int)std::min<int64_t>(ceil_div(n_rows, 8), (int64_t)kNumSM * 16);
+    const int wpr = ev.words_per_row;
+#define BE_GM(CPL)                                                                           \
+    gather_mm_kernel<T, HOMO, PERM, CPL, Rows><<<blocks, 256, 0, s>>>(                       \
+        rows, c.indices, (const T*)c.weights, c.perm, ev.packed, wpr, n_rows, n, out)
+    if (wpr == 1) BE_GM(1); else if (wpr == 2) BE_GM(2); else BE_GM(4);
+#undef BE_GM
+    BE_LAUNCH_CHECK("gather_mm_kernel");
+    return BE_B200_OK;
+}
+
+// One entry for all four shapes.  n == 0 means matvec.
+template <typename T, typename Rows>
+static int run_conn(const Rows& rows, const ConnArgs& c, const void* spikes, const void* aux,
+                    int spk_kind, int64_t n_src, int64_t n_rows, int64_t n_out, int64_t n_batch,
+                    bool scatter, void* out_v, void* workspace, size_t workspace_bytes,
+                    cudaStream_t s) {
+    T* out = (T*)out_v;
+    Events ev;
+    int rc;
+    const bool mm = n_batch > 0;
+    if (mm) rc = prepare_events_2d(spikes, aux, spk_kind, n_src, n_batch, scatter, workspace, workspace_bytes, s, &ev);
+    else rc = prepare_events_1d(spikes, aux, spk_kind, n_src, scatter, !scatter, workspace, workspace_bytes, s, &ev);
+    if (rc) return rc;
+    const int64_t out_elems = n_out * (mm ? n_batch : 1);
+    if (scatter && out_elems > 0) BE_CUDA(cudaMemsetAsync(out, 0, (size_t)out_elems * sizeof(T), s));
+    if (out_elems == 0) return BE_B200_OK;
+    if (n_src == 0) {
+        if (!scatter) BE_CUDA(cudaMemsetAsync(out, 0, (size_t)out_elems * sizeof(T), s));
+        return BE_B200_OK;
+    }
+#define BE_RUN(HOMO, PERM)                                                                              \
+    do {                                                                                                \
+        if (scatter) return mm ? launch_scatter_mm<T, HOMO, PERM, Rows>(rows, c, ev, n_src, n_batch, out, s) \
+                               : launch_scatter_mv<T, HOMO, PERM, Rows>(rows, c, ev, n_src, out, s);         \
+        return mm ? launch_gather_mm<T, HOMO, PERM, Rows>(rows, c, ev, n_rows, n_batch, out, s)              \
+                  : launch_gather_mv<T, HOMO, PERM, Rows>(rows, c, ev, n_rows, out, s);                      \
+    } while (0)
+    if (c.homo) BE_RUN(true, 0);
+    if constexpr (!std::is_same<Rows, FcnRows>::value) {
+        if (c.perm_kind == 1) BE_RUN(false, 1);
+        if (c.perm_kind == 2) BE_RUN(false, 2);
+    }
+    BE_RUN(false, 0);
+#undef BE_RUN
+}
+
+}  // namespace be
+
+using namespace be;
+
+static int csr_entry(const void* weights, int w_dtype, int homo, const int32_t* indices,
+                     const void* indptr, int indptr_is64, const void* perm, int perm_is64,
+                     const void* spikes, const void* aux, int spk_kind, int64_t m, int64_t k,
+                     int64_t nse, int64_t n, int transpose, void* out, void* workspace,
+                     size_t workspace_bytes, void* stream) {
+    cudaStream_t s = (cudaStream_t)stream;
+    BE_REQUIRE(m >= 0 && k >= 0 && m < (1ll << 31) && k < (1ll << 31), "csr: shape out of range");
+    BE_REQUIRE(weights && indptr && out, "csr: NULL pointer");
+    BE_REQUIRE(indices || nse == 0, "csr: indices is NULL");
+    ConnArgs c{weights, w_dtype, homo, indices, homo ? nullptr : perm,
+               (homo || !perm) ? 0 : (perm_is64 ? 2 : 1), m > 0 ? (double)nse / (double)m : 0.0};
+    const int64_t n_src = transpose ? m : k, n_out = transpose ? k : m;
+    BE_DISPATCH_WT(w_dtype, T, {
+        if (indptr_is64) {
+            CsrRows<int64_t> rows{(const int64_t*)indptr};
+            return run_conn<T>(rows, c, spikes, aux, spk_kind, n_src, m, n_out, n, transpose != 0, out, workspace, workspace_bytes, s);
+        } else {
+            CsrRows<int32_t> rows{(const int32_t*)indptr};
+            return run_conn<T>(rows, c, spikes, aux, spk_kind, n_src, m, n_out, n, transpose != 0, out, workspace, workspace_bytes, s);
+        }
+    });
+    return BE_B200_OK;
+}
+
+extern "C" int be_b200_binary_csrmv(const void* weights, int w_dtype, int homo,
+                                    const int32_t* indices, const void* indptr, int indptr_is64,
+                                    const void* perm, int perm_is64, const void* spikes,
+                                    const void* aux, int spk_kind, int64_t m, int64_t k,
+                                    int64_t nse, int transpose, void* out, void* workspace,
+                                    size_t workspace_bytes, void* stream) {
+    return csr_entry(weights, w_dtype, homo, indices, indptr, indptr_is64, perm, perm_is64, spikes,
+                     aux, spk_kind, m, k, nse, 0, transpose, out, workspace, workspace_bytes, stream);
+}
+
+extern "C" int be_b200_binary_csrmm(const void* weights, int w_dtype, int homo,
+                                    const int32_t* indices, const void* indptr, int indptr_is64,
+                                    const void* perm, int perm_is64, const void* spikes,
+                                    const void* aux, int spk_kind, int64_t m, int64_t k,
+                                    int64_t nse, int64_t n, int transpose, void* out,
+                                    void* workspace, size_t workspace_bytes, void* stream) {
+    BE_REQUIRE(n >= 1, "csrmm: batch must be >= 1");
+    return csr_entry(weights, w_dtype, homo, indices, indptr, indptr_is64, perm, perm_is64, spikes,
+                     aux, spk_kind, m, k, nse, n, transpose, out, workspace, workspace_bytes, stream);
+}
+
+static int fcn_entry(const void* weights, int w_dtype, int homo, const int32_t* indices,
+                     int64_t n_rows, int64_t n_conn, const void* spikes, const void* aux,
+                     int spk_kind, int64_t n_src, int64_t n_out, int64_t n, int transpose,
+                     void* out, void* workspace, size_t workspace_bytes, void* stream) {
+    cudaStream_t s = (cudaStream_t)stream;
+    BE_REQUIRE(n_rows >= 0 && n_conn >= 0 && n_src >= 0 && n_out >= 0, "fcn: negative size");
+    BE_REQUIRE(n_rows < (1ll << 31) && n_src < (1ll << 31) && n_out < (1ll << 31), "fcn: size out of range");
+    BE_REQUIRE(weights && out, "fcn: NULL pointer");
+    BE_REQUIRE(indices || n_rows * n_conn == 0, "fcn: indices is NULL");
+    if (transpose) BE_REQUIRE(n_src == n_rows, "fcn scatter: events length %lld != n_rows %lld", (long long)n_src, (long long)n_rows);
+    else BE_REQUIRE(n_out == n_rows, "fcn gather: out length %lld != n_rows %lld", (long long)n_out, (long long)n_rows);
+    ConnArgs c{weights, w_dtype, homo, indices, nullptr, 0, (double)n_conn};
+    FcnRows rows{n_conn};
+    BE_DISPATCH_WT(w_dtype, T, {
+        return run_conn<T>(rows, c, spikes, aux, spk_kind, n_src, n_rows, n_out, n, transpose != 0, out, workspace, workspace_bytes, s);
+    });
+    return BE_B200_OK;
+}
+
+extern "C" int be_b200_binary_fcnmv(const void* weights, int w_dtype, int homo,
+                                    const int32_t* indices, int64_t n_rows, int64_t n_conn,
+                                    const void* spikes, const void* aux, int spk_kind,
+                                    int64_t n_src, int64_t n_out, int transpose, void* out,
+                                    void* workspace, size_t workspace_bytes, void* stream) {
+    return fcn_entry(weights, w_dtype, homo, indices, n_rows, n_conn, spikes, aux, spk_kind, n_src,
+                     n_out, 0, transpose, out, workspace, workspace_bytes, stream);
+}
+
+extern "C" int be_b200_binary_fcnmm(const void* weights, int w_dtype, int homo,
+                                    const int32_t* indices, int64_t n_rows, int64_t n_conn,
+                                    const void* spikes, const void* aux, int spk_kind,
+                                    int64_t n_src, int64_t n_out, int64_t n, int transpose,
+                                    void* out, void* workspace, size_t workspace_bytes,
+                                    void* stream) {
+    BE_REQUIRE(n >= 1, "fcnmm: batch must be >= 1");
+    return fcn_entry(weights, w_dtype, homo, indices, n_rows, n_conn, spikes, aux, spk_kind, n_src,
+                     n_out, n, transpose, out, workspace, workspace_bytes, stream);
+}

@@ -1,0 +1,491 @@
+// jitc.cu -- just-in-time connectivity: the matrix is regenerated inside the kernel from
+// (seed, row, chunk, lane) with a bit-exact copy of the reference's light-RNG walk.
+//
+// Replaces ref: _jit_scalar/binary_jitsmv.cu, binary_jitsmm.cu; _jit_normal/binary_jitn{mv,mm}.cu;
+// _jit_uniform/binary_jitu{mv,mm}.cu.  RNG spec: _numba_random.py:385-502.
+//
+// Differences from the reference CUDA (same results, different machine mapping):
+//  * scatter ("trans") is driven by the compacted active-row list: one warp per (active row,
+//    chunk) task instead of a warp for every row that exits early when its spike bit is clear.
+//  * gather ("notrans") keeps one warp per output row across ALL chunks and writes out[row] once:
+//    no memset, no atomics, deterministic; the packed-spike word index / bit shift are hoisted
+//    out of the walk (they are invariant per (chunk, lane)).
+//  * mm draws each connection ONCE and applies it to every batch column (lanes = columns); the
+//    reference re-runs the whole walk per column (SURVEY F8 ii).
+//  * the per-edge Normal weight uses explicitly rounded (non-fused) f32 arithmetic so that it is
+//    bit-identical to the reference's strict `light_rng_normal01`; Acklam's central rational is
+//    ill-conditioned near |u-0.5| ~ 0.47 and FMA contraction alone moves it by ~1e-4.
+#include "common.cuh"
+
+#include <algorithm>
+
+namespace be {
+
+// ------------------------------------------------------------------------------------------
+// light-RNG (all uint32 wrap-around arithmetic)
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t mix32(uint32_t x) {
+    x ^= x >> 16; x *= 0x7feb352dU; x ^= x >> 15; x *= 0x846ca68bU; x ^= x >> 16;
+    return x;
+}
+// xorshift32 (13,17,5) is a bijection on non-zero states, so the reference's `x == 0` guard can
+// only fire for a zero input, which init() already excludes; it is kept for exactness of intent.
+__device__ __forceinline__ uint32_t rng_next(uint32_t x) {
+    x ^= x << 13; x ^= x >> 17; x ^= x << 5;
+    return x;
+}
+__device__ __forceinline__ uint32_t rng_init(uint32_t seed, uint32_t row, uint32_t chunk, uint32_t lane) {
+    uint32_t x = seed ^ 0xd1b54a35U;
+    x ^= row * 0x85ebca6bU; x ^= chunk * 0xc2b2ae35U; x ^= lane * 0x27d4eb2dU;
+    x = mix32(x);
+    return x == 0U ? 0x6d2b79f5U : x;
+}
+__device__ __forceinline__ uint32_t rng_initial_q(uint32_t& s, uint32_t cl) {
+    const uint32_t n = cl - 1U;
+    while (true) {
+        s = rng_next(s); const uint32_t q = __umulhi(s, n);
+        s = rng_next(s); const uint32_t g = __umulhi(s, n);
+        if (g < n - q) return q;
+    }
+}
+__device__ __forceinline__ float hash_uniform01(uint32_t seed, uint32_t row, uint32_t col) {
+    uint32_t h = seed ^ 0xa0761d65U;
+    h ^= row * 0xe7037ed1U; h ^= col * 0x8ebc6af1U;
+    h = mix32(h);
+    return __fmul_rn((float)(h & 0x00ffffffU), 1.0f / 16777216.0f);
+}
+// Horner steps with explicit rounding (no FMA contraction): bit-identical to strict IEEE f32.
+__device__ __forceinline__ float hs(float acc, float x, float c) { return __fadd_rn(__fmul_rn(acc, x), c); }
+__device__ __forceinline__ float hash_normal01(uint32_t seed, uint32_t row, uint32_t col) {
+    float u = hash_uniform01(seed, row, col);
+    u = fmaxf(fminf(u, 1.0f - 1e-10f), 1e-10f);
+    const float a1 = -39.696830f, a2 = 220.94609f, a3 = -275.92851f, a4 = 138.35775f,
+                a5 = -30.664799f, a6 = 2.5066283f;
+    const float b1 = -54.476099f, b2 = 161.58584f, b3 = -155.69898f, b4 = 66.801312f,
+                b5 = -13.280681f;
+    const float c1 = -0.007784894f, c2 = -0.32239646f, c3 = -2.4007583f, c4 = -2.5497325f,
+                c5 = 4.3746641f, c6 = 2.9381640f;
+    const float d1 = 0.007784696f, d2 = 0.32246713f, d3 = 2.4451342f, d4 = 3.7544087f;
+    if (u < 0.02425f || u > 0.97575f) {
+        const bool lower = u < 0.02425f;
+        const float t = lower ? u : __fsub_rn(1.0f, u);
+        const float v = __fsqrt_rn(__fmul_rn(-2.0f, logf(t)));
+        const float num = hs(hs(hs(hs(hs(c1, v, c2), v, c3), v, c4), v, c5), v, c6);
+        const float den = hs(hs(hs(hs(d1, v, d2), v, d3), v, d4), v, 1.0f);
+        const float z = __fdiv_rn(num, den);
+        return lower ? -z : z;
+    }
+    const float v = __fsub_rn(u, 0.5f);
+    const float r = __fmul_rn(v, v);
+    const float num = __fmul_rn(hs(hs(hs(hs(hs(a1, r, a2), r, a3), r, a4), r, a5), r, a6), v);
+    const float den = hs(hs(hs(hs(hs(b1, r, b2), r, b3), r, b4), r, b5), r, 1.0f);
+    return __fdiv_rn(num, den);
+}
+
+template <int KIND, typename A>
+__device__ __forceinline__ A jit_weight(A p0, A p1, uint32_t seed, uint32_t row, uint32_t col) {
+    if (KIND == BE_B200_JIT_SCALAR) return p0;
+    if (KIND == BE_B200_JIT_NORMAL) return p0 + (A)hash_normal01(seed, row, col) * p1;
+    return p0 + (A)hash_uniform01(seed, row, col) * p1;  // p1 holds (w_high - w_low)
+}
+// rounding note: the oracle computes w_loc + n01*w_scale in the weight dtype; for f32 the
+// compiler may fuse the multiply-add here, which is within 1 ulp of the unfused value.
+
+struct JitParams {
+    const void* p0;
+    const void* p1;
+    const int32_t* clen;
+    const int32_t* seed;
+};
+template <typename T, int KIND>
+__device__ __forceinline__ void load_params(const JitParams& jp, typename Acc<T>::type& p0,
+                                            typename Acc<T>::type& p1, uint32_t& cl, uint32_t& seed) {
+    using A = typename Acc<T>::type;
+    p0 = to_acc<T>(__ldg((const T*)jp.p0));
+    p1 = A(0);
+    if (KIND == BE_B200_JIT_NORMAL) p1 = to_acc<T>(__ldg((const T*)jp.p1));
+    if (KIND == BE_B200_JIT_UNIFORM) p1 = to_acc<T>(__ldg((const T*)jp.p1)) - p0;
+    cl = (uint32_t)__ldg(jp.clen);
+    if (cl < 2U) cl = 2U;
+    seed = (uint32_t)__ldg(jp.seed);
+}
+
+// number of walk positions of `lane` inside a chunk of `width` columns with residue stride S
+template <int S>
+__device__ __forceinline__ uint32_t lane_qmax(uint32_t width, uint32_t lane) {
+    return width > lane ? (width - lane + (S - 1)) / S : 0U;
+}
+
+// ------------------------------------------------------------------------------------------
+// mv gather (corder=True): out[row] = sum_{j in C(row)} w(row,j) * bit(j)
+// one warp per output row, lane = residue class, loops over chunks; single plain store.
+// ------------------------------------------------------------------------------------------
+template <typename T, int KIND>
+__global__ void __launch_bounds__(256) jit_mv_gather_kernel(JitParams jp, const uint32_t* __restrict__ packed,
+                                                            int64_t vec_len, int64_t chunk_size,
+                                                            int64_t row_offset, int64_t row_count,
+                                                            T* __restrict__ out) {
+    using A = typename Acc<T>::type;
+    A p0, p1; uint32_t cl, seed;
+    load_params<T, KIND>(jp, p0, p1, cl, seed);
+    const uint32_t lane = threadIdx.x & 31;
+    const int n_chunks = (int)ceil_div(vec_len, chunk_size);
+    for (int64_t lr = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5); lr < row_count; lr += (int64_t)gridDim.x * 8) {
+        const uint32_t row = (uint32_t)(row_offset + lr);
+        A acc = A(0);
+        uint32_t cnt = 0;
+        for (int c = 0; c < n_chunks; ++c) {
+            const int64_t cs = (int64_t)c * chunk_size;
+            const uint32_t width = (uint32_t)min(chunk_size, vec_len - cs);
+            const uint32_t qmax = lane_qmax<32>(width, lane);
+            uint32_t s = rng_init(seed, row, (uint32_t)c, lane);
+            uint32_t q = rng_initial_q(s, cl);
+            // column j = cs + lane + 32 q  ->  word (cs+lane)/32 + q, bit (cs+lane)%32: invariant shift
+            const int64_t b0 = cs + lane;
+            const uint32_t* wp = packed + (b0 >> 5);
+            const uint32_t sh = (uint32_t)(b0 & 31);
+            while (q < qmax) {
+                const uint32_t bit = (__ldg(wp + q) >> sh) & 1u;
+                if (KIND == BE_B200_JIT_SCALAR) cnt += bit;
+                else if (bit) acc += jit_weight<KIND, A>(p0, p1, seed, row, (uint32_t)(b0 + 32 * (int64_t)q));
+                s = rng_next(s);
+                q += 1U + __umulhi(s, cl - 1U);
+            }
+        }
+        if (KIND == BE_B200_JIT_SCALAR) {
+            cnt = __reduce_add_sync(0xffffffffu, cnt);
+            acc = (A)cnt * p0;
+        } else {
+            acc = warp_sum(acc);
+        }
+        if (lane == 0) out[lr] = from_acc<T>(acc);
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// mv scatter (corder=False): for every active row, out[j] += w(row,j) for j in C(row)
+// one warp per (active row, chunk) task.  [col_begin, col_end) is the owned output window.
+// ------------------------------------------------------------------------------------------
+template <typename T, int KIND>
+__global__ void __launch_bounds__(256) jit_mv_scatter_kernel(JitParams jp, const int32_t* __restrict__ ids,
+                                                             const int* __restrict__ n_active_ptr,
+                                                             int64_t out_len, int64_t chunk_size,
+                                                             int64_t row_offset, int64_t row_count,
+                                                             int64_t col_begin, int64_t col_end,
+                                                             T* __restrict__ out) {
+    using A = typename Acc<T>::type;
+    A p0, p1; uint32_t cl, seed;
+    load_params<T, KIND>(jp, p0, p1, cl, seed);
+    const uint32_t lane = threadIdx.x & 31;
+    const int n_chunks = (int)ceil_div(out_len, chunk_size);
+    const int64_t n_tasks = (int64_t)(*n_active_ptr) * n_chunks;
+    for (int64_t t = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5); t < n_tasks; t += (int64_t)gridDim.x * 8) {
+        const int64_t a = t / n_chunks;
+        const int c = (int)(t - a * n_chunks);
+        const int64_t r = __ldg(ids + a);
+        if (r < row_offset || r >= row_offset + row_count) continue;
+        const int64_t cs = (int64_t)c * chunk_size;
+        const int64_t ce = min(cs + chunk_size, out_len);
+        if (ce <= col_begin || cs >= col_end) continue;   // chunk outside the owned window
+        const uint32_t width = (uint32_t)(min(ce, col_end) - cs);   // stop at the window's end
+        const uint32_t qmax = lane_qmax<32>(width, lane);
+        const uint32_t row = (uint32_t)r;
+        uint32_t s = rng_init(seed, row, (uint32_t)c, lane);
+        uint32_t q = rng_initial_q(s, cl);
+        const int64_t b0 = cs + lane;
+        while (q < qmax) {
+            const int64_t j = b0 + 32 * (int64_t)q;
+            if (j >= col_begin) red_add(out + (j - col_begin), jit_weight<KIND, A>(p0, p1, seed, row, (uint32_t)j));
+            s = rng_next(s);
+            q += 1U + __umulhi(s, cl - 1U);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// mm (stride 4).  Lanes 0..3 of a warp walk the four residue streams of one (row, chunk); every
+// connection they find is broadcast and applied by all 32 lanes (= batch columns, CPL per lane).
+// ------------------------------------------------------------------------------------------
+template <typename T, int KIND, int CPL>
+__global__ void __launch_bounds__(256) jit_mm_gather_kernel(JitParams jp, const uint32_t* __restrict__ packed,
+                                                            int wpr, int64_t vec_len, int64_t out_len,
+                                                            int64_t n, int64_t chunk_size,
+                                                            T* __restrict__ out) {
+    using A = typename Acc<T>::type;
+    A p0, p1; uint32_t cl, seed;
+    load_params<T, KIND>(jp, p0, p1, cl, seed);
+    const uint32_t lane = threadIdx.x & 31;
+    const int n_chunks = (int)ceil_div(vec_len, chunk_size);
+    const int n_pass = (wpr + CPL - 1) / CPL;
+    for (int64_t rr = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5); rr < out_len; rr += (int64_t)gridDim.x * 8) {
+        const uint32_t row = (uint32_t)rr;
+        for (int pass = 0; pass < n_pass; ++pass) {
+            const int wb = pass * CPL;
+            A acc[CPL];
+#pragma unroll
+            for (int k = 0; k < CPL; ++k) acc[k] = A(0);
+            for (int c = 0; c < n_chunks; ++c) {
+                const int64_t cs = (int64_t)c * chunk_size;
+                const uint32_t width = (uint32_t)min(chunk_size, vec_len - cs);
+                uint32_t s = 0, q = 0, qmax = 0;
+                if (lane < 4) {
+                    qmax = lane_qmax<4>(width, lane);
+                    s = rng_init(seed, row, (uint32_t)c, lane);
+                    q = rng_initial_q(s, cl);
+                }
+                uint32_t live = __ballot_sync(0xffffffffu, q < qmax);
+                while (live) {
+                    // each live walker lane holds one connection this round
+                    int64_t my_j = 0;
+                    A my_w = A(0);
+                    uint32_t mw[CPL];
+#pragma unroll
+                    for (int k = 0; k < CPL; ++k) mw[k] = 0u;
+                    if (q < qmax) {
+                        my_j = cs + lane + 4 * (int64_t)q;
+                        const uint32_t* brow = packed + my_j * wpr + wb;
+#pragma unroll
+                        for (int k = 0; k < CPL; ++k) mw[k] = (wb + k < wpr) ? __ldg(brow + k) : 0u;
+                        my_w = jit_weight<KIND, A>(p0, p1, seed, row, (uint32_t)my_j);
+                        s = rng_next(s);
+                        q += 1U + __umulhi(s, cl - 1U);
+                    }
+                    uint32_t m = live;
+                    while (m) {
+                        const int t = __ffs(m) - 1;
+                        m &= m - 1;
+                        const A wv = __shfl_sync(0xffffffffu, my_w, t);
+#pragma unroll
+                        for (int k = 0; k < CPL; ++k) {
+                            const uint32_t bits = __shfl_sync(0xffffffffu, mw[k], t);
+                            if ((bits >> lane) & 1u) acc[k] += wv;
+                        }
+                    }
+                    live = __ballot_sync(0xffffffffu, q < qmax);
+                }
+            }
+#pragma unroll
+            for (int k = 0; k < CPL; ++k) {
+                const int64_t col = (int64_t)(wb + k) * 32 + lane;
+                if (col < n) out[rr * n + col] = from_acc<T>(acc[k]);
+            }
+        }
+    }
+}
+
+template <typename T, int KIND>
+__global__ void __launch_bounds__(256) jit_mm_scatter_kernel(JitParams jp, const int32_t* __restrict__ ids,
+                                                             const int* __restrict__ n_active_ptr,
+                                                             const uint32_t* __restrict__ packed, int wpr,
+                                                             int64_t out_len, int64_t n,
+                                                             int64_t chunk_size, T* __restrict__ out) {
+    using A = typename Acc<T>::type;
+    A p0, p1; uint32_t cl, seed;
+    load_params<T, KIND>(jp, p0, p1, cl, seed);
+    const uint32_t lane = threadIdx.x & 31;
+    const int n_chunks = (int)ceil_div(out_len, chunk_size);
+    const int64_t n_tasks = (int64_t)(*n_active_ptr) * n_chunks;
+    for (int64_t t = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5); t < n_tasks; t += (int64_t)gridDim.x * 8) {
+        const int64_t a = t / n_chunks;
+        const int c = (int)(t - a * n_chunks);
+        const int64_t r = __ldg(ids + a);
+        const uint32_t row = (uint32_t)r;
+        const int64_t cs = (int64_t)c * chunk_size;
+        const uint32_t width = (uint32_t)min(chunk_size, out_len - cs);
+        uint32_t s = 0, q = 0, qmax = 0;
+        if (lane < 4) {
+            qmax = lane_qmax<4>(width, lane);
+            s = rng_init(seed, row, (uint32_t)c, lane);
+            q = rng_initial_q(s, cl);
+        }
+        const uint32_t* mrow = packed + r * wpr;
+        uint32_t live = __ballot_sync(0xffffffffu, q < qmax);
+        while (live) {
+            int64_t my_j = 0;
+            A my_w = A(0);
+            if (q < qmax) {
+                my_j = cs + lane + 4 * (int64_t)q;
+                my_w = jit_weight<KIND, A>(p0, p1, seed, row, (uint32_t)my_j);
+                s = rng_next(s);
+                q += 1U + __umulhi(s, cl - 1U);
+            }
+            uint32_t m = live;
+            while (m) {
+                const int tt = __ffs(m) - 1;
+                m &= m - 1;
+                const A wv = __shfl_sync(0xffffffffu, my_w, tt);
+                const int64_t j = __shfl_sync(0xffffffffu, my_j, tt);
+                for (int k = 0; k < wpr; ++k) {
+                    const uint32_t bits = __ldg(mrow + k);
+                    const int64_t col = (int64_t)k * 32 + lane;
+                    if ((bits >> lane) & 1u) red_add(out + j * n + col, wv);
+                }
+            }
+            live = __ballot_sync(0xffffffffu, q < qmax);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// connectivity dump (parity instrument): per generated row, count and the first `cap` columns
+// in the reference's walk order (chunk-major, then lane, then ascending within the lane).
+// ------------------------------------------------------------------------------------------
+template <int S>
+__global__ void jit_conn_dump_kernel(const int32_t* __restrict__ clen_p, const int32_t* __restrict__ seed_p,
+                                     int64_t row_begin, int64_t n_rows, int64_t k, int64_t chunk_size,
+                                     int32_t* __restrict__ counts, int32_t* __restrict__ cols, int64_t cap) {
+    const int64_t lr = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (lr >= n_rows) return;
+    uint32_t cl = (uint32_t)__ldg(clen_p);
+    if (cl < 2U) cl = 2U;
+    const uint32_t seed = (uint32_t)__ldg(seed_p);
+    const uint32_t row = (uint32_t)(row_begin + lr);
+    const int n_chunks = (int)ceil_div(k, chunk_size);
+    int64_t cnt = 0;
+    for (int c = 0; c < n_chunks; ++c) {
+        const int64_t cs = (int64_t)c * chunk_size;
+        const uint32_t width = (uint32_t)min(chunk_size, k - cs);
+        for (uint32_t lane = 0; lane < (uint32_t)S; ++lane) {
+            const uint32_t qmax = lane_qmax<S>(width, lane);
+            uint32_t s = rng_init(seed, row, (uint32_t)c, lane);
+            uint32_t q = rng_initial_q(s, cl);
+            while (q < qmax) {
+                if (cols != nullptr && cnt < cap) cols[lr * cap + cnt] = (int32_t)(cs + lane + (int64_t)S * q);
+                ++cnt;
+                s = rng_next(s);
+                q += 1U + __umulhi(s, cl - 1U);
+            }
+        }
+    }
+    counts[lr] = (int32_t)cnt;
+}
+
+// ------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------
+template <typename T, int KIND>
+static int run_jit_mv(const JitParams& jp, const Events& ev, int64_t vec_len, int64_t out_len,
+                      int64_t chunk_size, bool corder, int64_t row_offset, int64_t row_count,
+                      int64_t col_begin, int64_t col_end, T* out, cudaStream_t s) {
+    if (corder) {
+        if (row_count == 0) return BE_B200_OK;
+        int blocks = (int)std::min<int64_t>(ceil_div(row_count, 8), (int64_t)kNumSM * 32);
+        jit_mv_gather_kernel<T, KIND><<<blocks, 256, 0, s>>>(jp, ev.packed, vec_len, chunk_size,
+                                                            row_offset, row_count, out);
+        BE_LAUNCH_CHECK("jit_mv_gather_kernel");
+    } else {
+        const int64_t own = col_end - col_begin;
+        if (own <= 0) return BE_B200_OK;
+        BE_CUDA(cudaMemsetAsync(out, 0, (size_t)own * sizeof(T), s));
+        if (vec_len == 0) return BE_B200_OK;
+        const int64_t n_chunks = ceil_div(out_len, chunk_size);
+        int blocks = (int)std::min<int64_t>(ceil_div(std::max<int64_t>(vec_len * n_chunks, 1), 8), (int64_t)kNumSM * 8);
+        jit_mv_scatter_kernel<T, KIND><<<blocks, 256, 0, s>>>(jp, ev.active_ids, ev.n_active, out_len,
+                                                             chunk_size, row_offset, row_count,
+                                                             col_begin, col_end, out);
+        BE_LAUNCH_CHECK("jit_mv_scatter_kernel");
+    }
+    return BE_B200_OK;
+}
+
+template <typename T, int KIND>
+static int run_jit_mm(const JitParams& jp, const Events& ev, int64_t vec_len, int64_t out_len,
+                      int64_t n, int64_t chunk_size, bool corder, T* out, cudaStream_t s) {
+    const int wpr = ev.words_per_row;
+    if (corder) {
+        int blocks = (int)std::min<int64_t>(ceil_div(out_len, 8), (int64_t)kNumSM * 32);
+#define BE_JG(CPL) jit_mm_gather_kernel<T, KIND, CPL><<<blocks, 256, 0, s>>>(jp, ev.packed, wpr, vec_len, out_len, n, chunk_size, out)
+        if (wpr == 1) BE_JG(1); else if (wpr == 2) BE_JG(2); else BE_JG(4);
+#undef BE_JG
+        BE_LAUNCH_CHECK("jit_mm_gather_kernel");
+    } else {
+        BE_CUDA(cudaMemsetAsync(out, 0, (size_t)(out_len * n) * sizeof(T), s));
+        if (vec_len == 0) return BE_B200_OK;
+        const int64_t n_chunks = ceil_div(out_len, chunk_size);
+        int blocks = (int)std::min<int64_t>(ceil_div(std::max<int64_t>(vec_len * n_chunks, 1), 8), (int64_t)kNumSM * 8);
+        jit_mm_scatter_kernel<T, KIND><<<blocks, 256, 0, s>>>(jp, ev.active_ids, ev.n_active, ev.packed,
+                                                             wpr, out_len, n, chunk_size, out);
+        BE_LAUNCH_CHECK("jit_mm_scatter_kernel");
+    }
+    return BE_B200_OK;
+}
+
+#define BE_DISPATCH_KIND(kind, K, ...)                                             \
+    switch (kind) {                                                                \
+        case BE_B200_JIT_SCALAR: { constexpr int K = BE_B200_JIT_SCALAR; __VA_ARGS__; break; }   \
+        case BE_B200_JIT_NORMAL: { constexpr int K = BE_B200_JIT_NORMAL; __VA_ARGS__; break; }   \
+        case BE_B200_JIT_UNIFORM: { constexpr int K = BE_B200_JIT_UNIFORM; __VA_ARGS__; break; } \
+        default: ::be::set_error("unknown JITC kind %d", (int)(kind)); return BE_B200_EINVAL;    \
+    }
+
+}  // namespace be
+
+using namespace be;
+
+extern "C" int be_b200_binary_jitmv(int kind, const void* p0, const void* p1, int w_dtype,
+                                    const int32_t* clen, const int32_t* seed, const void* spikes,
+                                    const void* aux, int spk_kind, int64_t vec_len, int64_t out_len,
+                                    int64_t chunk_size, int corder, int64_t row_offset,
+                                    int64_t row_count, int64_t col_begin, int64_t col_end, void* out,
+                                    void* workspace, size_t workspace_bytes, void* stream) {
+    cudaStream_t s = (cudaStream_t)stream;
+    BE_REQUIRE(p0 && clen && seed && out, "jitmv: NULL pointer");
+    BE_REQUIRE(kind == BE_B200_JIT_SCALAR || p1, "jitmv: p1 is NULL");
+    BE_REQUIRE(vec_len >= 0 && out_len >= 0 && vec_len < (1ll << 31) && out_len < (1ll << 31), "jitmv: shape out of range");
+    BE_REQUIRE(chunk_size >= 1, "jitmv: chunk_size must be positive");
+    const int64_t n_rows_total = corder ? out_len : vec_len;
+    if (row_count < 0) row_count = n_rows_total - row_offset;
+    if (col_end < 0) col_end = out_len;
+    BE_REQUIRE(row_offset >= 0 && row_offset + row_count <= n_rows_total, "jitmv: row window out of range");
+    BE_REQUIRE(col_begin >= 0 && col_begin <= col_end && col_end <= out_len, "jitmv: column window out of range");
+    BE_REQUIRE(!corder || (col_begin == 0 && col_end == out_len), "jitmv: column window only applies to corder=0");
+    Events ev;
+    int rc = prepare_events_1d(spikes, aux, spk_kind, vec_len, !corder, corder != 0, workspace, workspace_bytes, s, &ev);
+    if (rc) return rc;
+    JitParams jp{p0, p1, clen, seed};
+    BE_DISPATCH_WT(w_dtype, T, {
+        BE_DISPATCH_KIND(kind, K, {
+            return run_jit_mv<T, K>(jp, ev, vec_len, out_len, chunk_size, corder != 0, row_offset, row_count, col_begin, col_end, (T*)out, s);
+        });
+    });
+    return BE_B200_OK;
+}
+
+extern "C" int be_b200_binary_jitmm(int kind, const void* p0, const void* p1, int w_dtype,
+                                    const int32_t* clen, const int32_t* seed, const void* spikes,
+                                    const void* aux, int spk_kind, int64_t vec_len, int64_t out_len,
+                                    int64_t n, int64_t chunk_size, int corder, void* out,
+                                    void* workspace, size_t workspace_bytes, void* stream) {
+    cudaStream_t s = (cudaStream_t)stream;
+    BE_REQUIRE(p0 && clen && seed && out, "jitmm: NULL pointer");
+    BE_REQUIRE(kind == BE_B200_JIT_SCALAR || p1, "jitmm: p1 is NULL");
+    BE_REQUIRE(vec_len >= 0 && out_len >= 0 && vec_len < (1ll << 31) && out_len < (1ll << 31) && n >= 1, "jitmm: shape out of range");
+    BE_REQUIRE(chunk_size >= 1, "jitmm: chunk_size must be positive");
+    if (out_len == 0) return BE_B200_OK;
+    Events ev;
+    int rc = prepare_events_2d(spikes, aux, spk_kind, vec_len, n, !corder, workspace, workspace_bytes, s, &ev);
+    if (rc) return rc;
+    JitParams jp{p0, p1, clen, seed};
+    BE_DISPATCH_WT(w_dtype, T, {
+        BE_DISPATCH_KIND(kind, K, {
+            return run_jit_mm<T, K>(jp, ev, vec_len, out_len, n, chunk_size, corder != 0, (T*)out, s);
+        });
+    });
+    return BE_B200_OK;
+}
+
+extern "C" int be_b200_jitc_row_connections(const int32_t* clen, const int32_t* seed,
+                                            int64_t row_begin, int64_t n_rows, int64_t k,
+                                            int64_t chunk_size, int stride, int32_t* counts,
+                                            int32_t* cols, int64_t cap, void* stream) {
+    cudaStream_t s = (cudaStream_t)stream;
+    BE_REQUIRE(clen && seed && counts, "jitc_row_connections: NULL pointer");
+    BE_REQUIRE(stride == 32 || stride == 4, "jitc_row_connections: stride must be 32 (mv) or 4 (mm)");
+    BE_REQUIRE(chunk_size >= 1 && k >= 0 && n_rows >= 0, "jitc_row_connections: bad sizes");
+    if (n_rows == 0) return BE_B200_OK;
+    int blocks = (int)ceil_div(n_rows, 128);
+    if (stride == 32) jit_conn_dump_kernel<32><<<blocks, 128, 0, s>>>(clen, seed, row_begin, n_rows, k, chunk_size, counts, cols, cap);
+    else jit_conn_dump_kernel<4><<<blocks, 128, 0, s>>>(clen, seed, row_begin, n_rows, k, chunk_size, counts, cols, cap);
+    BE_LAUNCH_CHECK("jit_conn_dump_kernel");
+    return BE_B200_OK;
+}

@@ -1,0 +1,192 @@
+/*
+ * brainevent_b200.h -- C ABI of the B200-native event-driven synaptic propagation library.
+ *
+ * Drop-in boundary for ONE path of chaobrain/brainevent: BinaryArray / BitPackedBinary /
+ * CompactBinary events against CSR/CSC, FixedNumPerPre/PerPost, JITC{Scalar,Normal,Uniform} and
+ * dense matrices.  Every entry point is `extern "C"`, takes plain device pointers, sizes and a
+ * `cudaStream_t` (as void*), enqueues on that stream, never synchronises, keeps no global
+ * mutable state, and returns 0 on success or a BE_B200_E* code (message via
+ * be_b200_last_error()).  Outputs are treated as uninitialised on entry (the library zeroes what
+ * it accumulates into), like the reference's cuda_raw kernels (_fcn/binary_fcnmv.cu:203).
+ *
+ * Citations `ref:` are paths under /root/reference/brainevent/ of the interface replaced.
+ * The XLA-FFI handlers with the reference's own target names are declared in
+ * brainevent_b200_xla.h; they are thin decoders over the functions below.
+ */
+#ifndef BRAINEVENT_B200_H_
+#define BRAINEVENT_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define BE_B200_ABI_VERSION 1
+
+/* ---- error codes (ref: include/brainevent/check.h:35-47 throws; here: return codes) -------- */
+#define BE_B200_OK 0
+#define BE_B200_EINVAL 3       /* XLA_FFI_Error_Code INVALID_ARGUMENT */
+#define BE_B200_EUNIMPL 12     /* UNIMPLEMENTED */
+#define BE_B200_EINTERNAL 13   /* INTERNAL (CUDA launch failure) */
+
+/* ---- weight / output dtypes (ref: include/brainevent/tensor.h:42-59) ----------------------- */
+#define BE_B200_F32 0
+#define BE_B200_F64 1
+#define BE_B200_F16 2
+#define BE_B200_BF16 3
+
+/* ---- event (spike) encodings ---------------------------------------------------------------
+ * BOOL    : uint8/int8 per element, active when non-zero      (ref: BinaryArray bool, cuda_common.h:120-165)
+ * F32     : float per element, active when > 0                (ref: BinaryArray float)
+ * PACKED  : uint32 words, bit b of word w = element 32w+b     (ref: _event/bitpack_binary.py:32-76)
+ *           1-D: ceil(n/32) words.  2-D [n, batch]: packed along batch, ceil(batch/32) words/row.
+ * COMPACT : `spikes` = packed words as above, `aux` = int32 active_ids[n] followed by
+ *           int32 n_active at aux[n]  (ref: _event/compact_binary.py:99-107)
+ */
+#define BE_B200_SPK_BOOL 0
+#define BE_B200_SPK_F32 1
+#define BE_B200_SPK_PACKED 2
+#define BE_B200_SPK_COMPACT 3
+
+/* ---- JITC weight families (ref: _jit_scalar/, _jit_normal/, _jit_uniform/) ------------------ */
+#define BE_B200_JIT_SCALAR 0   /* w = p0 */
+#define BE_B200_JIT_NORMAL 1   /* w = p0 + N01(seed,row,col) * p1 */
+#define BE_B200_JIT_UNIFORM 2  /* w = p0 + U01(seed,row,col) * (p1 - p0) */
+
+const char* be_b200_last_error(void);
+int be_b200_abi_version(void);
+/* Device capability check: returns 0 when the current device is sm_100 (B200). */
+int be_b200_check_device(void);
+
+/* Scratch space.  Every operator takes a caller-owned device workspace (the reference aliases
+ * task_begin/task_end/status buffers the same way, ref: _csr/binary.py:55-124).  `n_src` is the
+ * number of source (event) rows, `n_batch` the event batch width (1 for matvec). */
+size_t be_b200_workspace_bytes(int64_t n_src, int64_t n_batch);
+
+/* ---- event encoders (ref: _event/compact.py:258,406,589; _event/compact.cu:70-430;
+ *                          _jit_scalar/binary_jitsmv.cu:107-125 pack_bool) ---------------------- */
+/* packed[ceil(n/32)] <- bits of spikes[n].  nonzero_pred=1 uses `!= 0` for floats (compaction
+ * convention, ref: _event/compact.py:327), 0 uses `> 0` (operator convention). */
+int be_b200_bitpack_1d(const void* spikes, int spk_kind, int64_t n, int nonzero_pred,
+                       uint32_t* packed, void* stream);
+/* Ordered stream compaction: active_ids[n] ascending with zero tail, n_active[1], and (when
+ * packed != NULL) the bit-packed words in the same pass.  ref: binary_1d_array_index_p. */
+int be_b200_compact_1d(const void* spikes, int spk_kind, int64_t n, int nonzero_pred,
+                       int32_t* active_ids, int32_t* n_active, uint32_t* packed,
+                       void* workspace, size_t workspace_bytes, void* stream);
+/* 2-D [n, batch] row-major: packed[n, ceil(batch/32)] (may be NULL: compact-only primitive),
+ * rows with any active column in ascending order.  ref: binary_2d_array_index_p /
+ * binary_2d_compact_only_p. */
+int be_b200_compact_2d(const void* spikes, int spk_kind, int64_t n, int64_t batch,
+                       int nonzero_pred, uint32_t* packed, int32_t* active_ids,
+                       int32_t* n_active, void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---- CSR / CSC (ref: _csr/binary.py:128 binary_csrmv, :264 binary_csrmm;
+ *                      _csr/binary_indexed.py:70,615 *_indexed) --------------------------------
+ * CSR structure with m rows, k columns, nse stored synapses.  weights: [nse] or [1] (homo=1).  indptr int32 or int64
+ * (indptr_is64).  perm (nullable): indexed variant reads weights[perm[j]] (perm_is64 selects
+ * int64).  transpose=1: events[m] -> out[k] (atomic scatter over active rows);
+ * transpose=0: events[k] -> out[m] (deterministic gather over all rows).
+ * mm: events [m or k, n] row-major, out [k or m, n] row-major (batch innermost). */
+int be_b200_binary_csrmv(const void* weights, int w_dtype, int homo, const int32_t* indices,
+                         const void* indptr, int indptr_is64, const void* perm, int perm_is64,
+                         const void* spikes, const void* aux, int spk_kind, int64_t m, int64_t k,
+                         int64_t nse, int transpose, void* out, void* workspace,
+                         size_t workspace_bytes, void* stream);
+int be_b200_binary_csrmm(const void* weights, int w_dtype, int homo, const int32_t* indices,
+                         const void* indptr, int indptr_is64, const void* perm, int perm_is64,
+                         const void* spikes, const void* aux, int spk_kind, int64_t m, int64_t k,
+                         int64_t nse, int64_t n, int transpose, void* out, void* workspace,
+                         size_t workspace_bytes, void* stream);
+
+/* ---- fixed-number connectivity / ELL (ref: _fcn/binary.py:43 binary_fcnmv, :512 binary_fcnmm;
+ *      _fcn/binary_fcnmv.cu:188-252) -----------------------------------------------------------
+ * indices int32 [n_rows, n_conn]; weights [n_rows, n_conn] or [1].  transpose=1: events[n_rows]
+ * -> out[n_out] scatter; transpose=0: events[n_src] -> out[n_rows] gather (n_out == n_rows). */
+int be_b200_binary_fcnmv(const void* weights, int w_dtype, int homo, const int32_t* indices,
+                         int64_t n_rows, int64_t n_conn, const void* spikes, const void* aux,
+                         int spk_kind, int64_t n_src, int64_t n_out, int transpose, void* out,
+                         void* workspace, size_t workspace_bytes, void* stream);
+int be_b200_binary_fcnmm(const void* weights, int w_dtype, int homo, const int32_t* indices,
+                         int64_t n_rows, int64_t n_conn, const void* spikes, const void* aux,
+                         int spk_kind, int64_t n_src, int64_t n_out, int64_t n, int transpose,
+                         void* out, void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---- JITC (ref: _jit_scalar/binary.py:44,171; _jit_normal/binary.py:44,177;
+ *      _jit_uniform/binary.py:44,177; CUDA _jit_scalar/binary_jitsmv.cu:127-214) ---------------
+ * p0, p1, clen, seed are DEVICE pointers to one element each (XLA buffers in the reference):
+ * p0/p1 in w_dtype, clen/seed int32.  corder=1 ("notrans"): one generated row per output,
+ * gathers events over the walk dimension vec_len.  corder=0 ("trans"): one generated row per
+ * event, scatters over out_len.  chunk_size = max(1, ceil(shape[1]/4)) of the *logical* shape
+ * (ref: _misc.py:74-122); the caller passes it, exactly like the reference's FFI attribute.
+ * row_offset / row_count restrict the generated rows (gather: output rows; scatter: event rows)
+ * and col_begin/col_end restrict the walked columns written (scatter) -- used by the post-sharded
+ * multi-GPU path; pass 0, -1, 0, -1 for the whole matrix.
+ * mm: events [vec_len, n] row-major, out [out_len, n]; stride-4 walk (a different matrix than
+ * mv, ref: _misc.py:33-38). */
+int be_b200_binary_jitmv(int kind, const void* p0, const void* p1, int w_dtype,
+                         const int32_t* clen, const int32_t* seed, const void* spikes,
+                         const void* aux, int spk_kind, int64_t vec_len, int64_t out_len,
+                         int64_t chunk_size, int corder, int64_t row_offset, int64_t row_count,
+                         int64_t col_begin, int64_t col_end, void* out, void* workspace,
+                         size_t workspace_bytes, void* stream);
+int be_b200_binary_jitmm(int kind, const void* p0, const void* p1, int w_dtype,
+                         const int32_t* clen, const int32_t* seed, const void* spikes,
+                         const void* aux, int spk_kind, int64_t vec_len, int64_t out_len,
+                         int64_t n, int64_t chunk_size, int corder, void* out, void* workspace,
+                         size_t workspace_bytes, void* stream);
+/* Connectivity dump of generated rows [row_begin, row_begin+n_rows): counts[n_rows] and, when
+ * cols != NULL, the first `cap` columns of each row in walk order at cols[r*cap ..].  Parity
+ * instrument (ref: _jit_scalar/csr.py jits_to_csr count/fill). */
+int be_b200_jitc_row_connections(const int32_t* clen, const int32_t* seed, int64_t row_begin,
+                                 int64_t n_rows, int64_t k, int64_t chunk_size, int stride,
+                                 int32_t* counts, int32_t* cols, int64_t cap, void* stream);
+
+/* ---- dense event ops (ref: _dense/binary.py:79 binary_densemv, :487 binary_densemm;
+ *      _dense/binary_densemv.cu, binary_densemm.cu) --------------------------------------------
+ * W row-major [rows, cols].  transpose=1: events[rows] -> out[cols]; transpose=0: events[cols]
+ * -> out[rows].  mm: events [k, n] -> out [m, n]. */
+int be_b200_binary_densemv(const void* W, int w_dtype, int64_t rows, int64_t cols,
+                           const void* spikes, const void* aux, int spk_kind, int transpose,
+                           void* out, void* workspace, size_t workspace_bytes, void* stream);
+int be_b200_binary_densemm(const void* W, int w_dtype, int64_t rows, int64_t cols,
+                           const void* spikes, const void* aux, int spk_kind, int64_t n,
+                           int transpose, void* out, void* workspace, size_t workspace_bytes,
+                           void* stream);
+
+/* ---- CSC mirror (ref: _misc.py:1341-1384 _csr_to_csc_index_numpy; _csr/csr_to_csc.cu) --------
+ * Stable by-column reordering: csc_indptr[n_post+1], csc_indices[nse] (= row ids), perm[nse].
+ * Offsets are int64 when is64, else int32.  Setup-time; scratch comes from `workspace`
+ * (>= be_b200_csc_workspace_bytes). */
+size_t be_b200_csc_workspace_bytes(int64_t m, int64_t n_post, int64_t nse);
+int be_b200_csr_to_csc(const void* indptr, int is64, const int32_t* indices, int64_t m,
+                       int64_t n_post, int64_t nse, void* csc_indptr, int32_t* csc_indices,
+                       void* perm, void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---- host-buffer session (end-to-end entry: host spikes in, host result out) -----------------
+ * A projection keeps its connectivity resident in HBM (uploaded once at creation, like the
+ * reference's jax arrays) and per call copies the host spike vector in, runs the path on its
+ * own stream and copies the result back, synchronising before it returns. */
+typedef struct be_b200_projection be_b200_projection;
+/* kind: 0 = CSR (weights[nse]|[1], indices[nse], indptr int32[m+1]), 1 = FCN (indices [m, n_conn]),
+ * 2 = JITC (p0, p1, prob -> clen, seed; jit_kind in n_conn's place is NOT used: see jit_kind). */
+be_b200_projection* be_b200_projection_create_csr(const float* weights, int homo,
+                                                  const int32_t* indices, const int32_t* indptr,
+                                                  int64_t m, int64_t k);
+be_b200_projection* be_b200_projection_create_fcn(const float* weights, int homo,
+                                                  const int32_t* indices, int64_t n_rows,
+                                                  int64_t n_conn, int64_t n_post);
+be_b200_projection* be_b200_projection_create_jitc(int jit_kind, float p0, float p1, int32_t clen,
+                                                   int32_t seed, int64_t n_pre, int64_t n_post,
+                                                   int64_t chunk_size, int corder);
+/* events: host uint8[n_pre] (pinned for best speed); out: host float[n_post].  spk @ W. */
+int be_b200_projection_apply_host(be_b200_projection* p, const uint8_t* events_host,
+                                  float* out_host);
+void be_b200_projection_destroy(be_b200_projection* p);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BRAINEVENT_B200_H_ */

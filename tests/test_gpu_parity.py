@@ -1,0 +1,321 @@
+"""Parity of the CUDA path (through the C ABI) with the oracle and the reference-generated
+golden fixtures.  Bit-exact for compaction / packing / connectivity; rtol 1e-5, atol 1e-6 for
+fp32 results (north star), looser only where noted."""
+import numpy as np
+import pytest
+
+torch = pytest.importorskip("torch")
+pytestmark = pytest.mark.gpu
+
+import oracle as O  # noqa: E402
+from tests import cases, golden_cases  # noqa: E402
+
+RTOL, ATOL = 1e-5, 1e-6
+
+
+@pytest.fixture(scope="module")
+def G():
+    if not torch.cuda.is_available():
+        pytest.skip("needs a CUDA device")
+    from tests import gpu_api
+    import brainevent_b200._lib as L
+    L.check(L.lib().be_b200_check_device(), "check_device")
+    return gpu_api
+
+
+# ---- golden fixtures from the reference itself ---------------------------------------------
+@pytest.mark.parametrize("tag,fn,atol", list(golden_cases.op_cases()), ids=lambda x: x if isinstance(x, str) else "")
+def test_ops_fixture(G, tag, fn, atol):
+    g = golden_cases.load("ops")
+    np.testing.assert_allclose(fn(G), g[tag], rtol=RTOL, atol=max(atol, ATOL))
+
+
+def test_compaction_fixture(G):
+    g = golden_cases.load("ops")
+    ids, na = G.binary_1d_array_index(cases.spikes(1, 1000, 0.1))
+    assert int(na[0]) == int(g["compact1d_n"][0])
+    np.testing.assert_array_equal(ids[:na[0]], g["compact1d_ids"])
+    assert not ids[na[0]:].any()
+    p, ids, na = G.binary_2d_array_index(cases.spikes(2, 300, 0.02, batch=70))
+    np.testing.assert_array_equal(p, g["compact2d_packed"])
+    np.testing.assert_array_equal(ids[:na[0]], g["compact2d_ids"])
+
+
+def test_connectivity_index_for_index(G):
+    import brainevent_b200 as be
+    g = golden_cases.load("jitc_connectivity")
+    for tag in ("a", "b"):
+        meta = g[f"{tag}_meta"]
+        m, k, clen, seed, chunk = (int(x) for x in meta[:5])
+        prob = {"a": 0.05, "b": 0.01}[tag]
+        assert O.conn_length(prob) == clen
+        rows = [int(x) for x in meta[5:]]
+        for mode, stride in (("mv", 32), ("mm", 4)):
+            counts, cols = be.jitc_row_connections(prob, seed, (0, m), k, chunk, stride=stride)
+            counts, cols = counts.cpu().numpy(), cols.cpu().numpy()
+            for r, ref_counts in zip(rows, g[f"{tag}_{mode}"]):
+                mine = np.bincount(cols[r, :counts[r]], minlength=k)
+                np.testing.assert_array_equal(mine, ref_counts)          # vs the reference kernel
+                oc = O.jitc_row_connections(seed, clen, r, k, chunk, stride)
+                np.testing.assert_array_equal(cols[r, :counts[r]], oc)    # walk order vs the oracle
+
+
+# ---- kats quoted from the reference's tests --------------------------------------------------
+def test_reference_kats(G):
+    s = np.array([[1, 0, 1, 0], [0, 0, 0, 0], [0, 1, 1, 0]], bool)
+    packed, ids, na = G.binary_2d_array_index(s)
+    np.testing.assert_array_equal(packed[:, 0], [5, 0, 6])
+    np.testing.assert_array_equal(ids[:int(na[0])], [0, 2])
+    data, idx, ptr = np.array([1, 2, 3], np.float32), np.array([0, 2, 1], np.int32), np.array([0, 2, 3], np.int32)
+    np.testing.assert_array_equal(G.binary_csrmv(data, idx, ptr, np.array([True, False, True]), shape=(2, 3)), [3, 0])
+    np.testing.assert_array_equal(G.binary_csrmv(data, idx, ptr, np.array([True, True]), shape=(2, 3), transpose=True), [1, 3, 2])
+    W = np.array([[1, 2], [3, 4], [5, 6]], np.float32)
+    np.testing.assert_array_equal(G.binary_densemv(W, np.array([True, False, True]), transpose=True), [6, 8])
+    np.testing.assert_array_equal(G.binary_fcnmv(np.ones(1, np.float32), np.array([[0, 1], [1, 2]], np.int32),
+                                                 np.array([True, False, True]), shape=(2, 3)), [1, 1])
+
+
+# ---- seeded comparisons against the oracle at larger / ragged / edge sizes --------------------
+@pytest.mark.parametrize("n", [0, 1, 31, 32, 33, 4095, 4096, 4097, 100_003, 1_000_000])
+@pytest.mark.parametrize("float_spikes", [False, True])
+def test_compact_and_pack_1d(G, n, float_spikes):
+    s = cases.spikes(n, n, 0.03, float_spikes)
+    ids, na = G.binary_1d_array_index(s)
+    oids, ona = O.binary_1d_array_index(s)
+    assert int(na[0]) == int(ona[0])
+    np.testing.assert_array_equal(ids, oids)
+    if n:
+        np.testing.assert_array_equal(G.bitpack(s, 0), O.bitpack(s, 0))
+    # run twice: the workspace must have reset itself
+    ids2, na2 = G.binary_1d_array_index(s)
+    np.testing.assert_array_equal(ids2, oids)
+
+
+@pytest.mark.parametrize("n,b", [(1, 1), (7, 3), (300, 70), (5000, 64), (1025, 32), (2049, 33), (20000, 200)])
+@pytest.mark.parametrize("float_spikes", [False, True])
+def test_compact_2d(G, n, b, float_spikes):
+    s = cases.spikes(n * 31 + b, n, 0.02, float_spikes, batch=b)
+    p, ids, na = G.binary_2d_array_index(s)
+    op, oids, ona = O.binary_2d_array_index(s)
+    np.testing.assert_array_equal(p, op)
+    assert int(na[0]) == int(ona[0])
+    np.testing.assert_array_equal(ids, oids)
+    ids2, na2 = G.binary_2d_compact_only(s)
+    np.testing.assert_array_equal(ids2, oids)
+    np.testing.assert_array_equal(G.bitpack(s, 1), O.bitpack(s, 1))
+    np.testing.assert_array_equal(G.bitpack(s, 0), O.bitpack(s, 0))
+
+
+def test_csc_mirror(G):
+    c = cases.csr_case(3, 2000, 1500, 7, 0.1, ragged=True)
+    a = G.csr_to_csc_index(c["indptr"], c["indices"], c["shape"])
+    b = O.csr_to_csc_index(c["indptr"], c["indices"], c["shape"])
+    for x, y in zip(a, b):
+        np.testing.assert_array_equal(x, y)
+
+
+CSR_SHAPES = [(1, 1, 1), (300, 200, 9), (5000, 7000, 3), (4000, 4000, 80), (2000, 3000, 300)]
+
+
+@pytest.mark.parametrize("m,k,nnz", CSR_SHAPES)
+@pytest.mark.parametrize("homo", [False, True])
+@pytest.mark.parametrize("transpose", [False, True])
+@pytest.mark.parametrize("float_spikes", [False, True])
+def test_csr_vs_oracle(G, m, k, nnz, homo, transpose, float_spikes):
+    c = cases.csr_case(m + nnz, m, k, nnz, 0.1, homo=homo, ragged=True)
+    v = cases.spikes(5, m if transpose else k, 0.15, float_spikes)
+    kw = dict(shape=c["shape"], transpose=transpose)
+    np.testing.assert_allclose(G.binary_csrmv(c["data"], c["indices"], c["indptr"], v, **kw),
+                               O.binary_csrmv(c["data"], c["indices"], c["indptr"], v, **kw), rtol=RTOL, atol=1e-5)
+    for batch in (1, 13, 64, 100):
+        if m * batch > 400_000:
+            continue
+        B = cases.spikes(6, m if transpose else k, 0.1, float_spikes, batch=batch)
+        np.testing.assert_allclose(G.binary_csrmm(c["data"], c["indices"], c["indptr"], B, **kw),
+                                   O.binary_csrmm(c["data"], c["indices"], c["indptr"], B, **kw), rtol=RTOL, atol=1e-5)
+    ci, cx, pm = O.csr_to_csc_index(c["indptr"], c["indices"], c["shape"])
+    vi = cases.spikes(7, k if transpose else m, 0.15, float_spikes)
+    kwi = dict(shape=(k, m), transpose=transpose)
+    for perm_dtype in (np.int32, np.int64):
+        np.testing.assert_allclose(
+            G.binary_csrmv_indexed(c["data"], cx, ci.astype(perm_dtype), pm.astype(perm_dtype), vi, **kwi),
+            O.binary_csrmv_indexed(c["data"], cx, ci, pm, vi, **kwi), rtol=RTOL, atol=1e-5)
+    Bi = cases.spikes(8, k if transpose else m, 0.1, float_spikes, batch=5)
+    np.testing.assert_allclose(G.binary_csrmm_indexed(c["data"], cx, ci.astype(np.int32), pm.astype(np.int32), Bi, **kwi),
+                               O.binary_csrmm_indexed(c["data"], cx, ci, pm, Bi, **kwi), rtol=RTOL, atol=1e-5)
+
+
+def test_csr_heavy_rows_and_empty(G):
+    rng = np.random.default_rng(0)
+    m, k = 50, 3000
+    counts = np.zeros(m, np.int64)
+    counts[3], counts[17], counts[40] = 20000, 9000, 5
+    indptr = np.concatenate([[0], np.cumsum(counts)]).astype(np.int32)
+    indices = rng.integers(0, k, indptr[-1]).astype(np.int32)
+    data = rng.standard_normal(indptr[-1]).astype(np.float32)
+    v = np.zeros(m, bool)
+    v[[3, 17, 40, 41]] = True
+    np.testing.assert_allclose(G.binary_csrmv(data, indices, indptr, v, shape=(m, k), transpose=True),
+                               O.binary_csrmv(data, indices, indptr, v, shape=(m, k), transpose=True), rtol=1e-4, atol=1e-3)
+    z = np.zeros(m, bool)
+    assert not G.binary_csrmv(data, indices, indptr, z, shape=(m, k), transpose=True).any()
+    vk = rng.random(k) < 0.3
+    np.testing.assert_allclose(G.binary_csrmv(data, indices, indptr, vk, shape=(m, k)),
+                               O.binary_csrmv(data, indices, indptr, vk, shape=(m, k)), rtol=1e-4, atol=1e-3)
+
+
+@pytest.mark.parametrize("dtype", [np.float64, np.float16])
+def test_csr_other_dtypes(G, dtype):
+    c = cases.csr_case(11, 600, 500, 20, 0.1)
+    data = c["data"].astype(dtype)
+    for transpose in (False, True):
+        v = cases.spikes(5, 600 if transpose else 500, 0.15)
+        got = G.binary_csrmv(data, c["indices"], c["indptr"], v, shape=c["shape"], transpose=transpose)
+        ref = O.binary_csrmv(data.astype(np.float64), c["indices"], c["indptr"], v, shape=c["shape"], transpose=transpose)
+        assert got.dtype == dtype
+        tol = 1e-12 if dtype == np.float64 else 2e-2
+        np.testing.assert_allclose(got.astype(np.float64), ref, rtol=tol, atol=tol)
+
+
+@pytest.mark.parametrize("n_rows,n_post,n_conn", [(1, 1, 1), (250, 180, 11), (4000, 4000, 80), (3000, 5000, 1000), (20000, 100, 4)])
+@pytest.mark.parametrize("homo", [False, True])
+@pytest.mark.parametrize("transpose", [False, True])
+def test_fcn_vs_oracle(G, n_rows, n_post, n_conn, homo, transpose):
+    c = cases.fcn_case(9 + n_conn, n_rows, n_post, n_conn, homo=homo)
+    shape = (n_rows, n_post)
+    for fs in (False, True):
+        v = cases.spikes(10, n_rows if transpose else n_post, 0.1, fs)
+        np.testing.assert_allclose(G.binary_fcnmv(c["weights"], c["indices"], v, shape=shape, transpose=transpose),
+                                   O.binary_fcnmv(c["weights"], c["indices"], v, shape=shape, transpose=transpose),
+                                   rtol=RTOL, atol=2e-5)
+    for batch in (9, 64):
+        if n_rows * n_conn * batch > 3e7:
+            continue
+        B = cases.spikes(11, n_rows if transpose else n_post, 0.05, batch=batch)
+        np.testing.assert_allclose(G.binary_fcnmm(c["weights"], c["indices"], B, shape=shape, transpose=transpose),
+                                   O.binary_fcnmm(c["weights"], c["indices"], B, shape=shape, transpose=transpose),
+                                   rtol=RTOL, atol=2e-5)
+
+
+JIT = [("s", (1.5,)), ("n", (1.0, 0.1)), ("u", (-0.5, 1.0))]
+
+
+@pytest.mark.parametrize("fam,params", JIT)
+@pytest.mark.parametrize("shape,prob", [((230, 310), 0.05), ((1, 5), 0.5), ((3000, 2000), 0.01), ((2000, 4099), 0.002)])
+@pytest.mark.parametrize("transpose", [False, True])
+@pytest.mark.parametrize("corder", [False, True])
+def test_jitc_vs_oracle(G, fam, params, shape, prob, transpose, corder):
+    seed = 1234 + shape[0]
+    vec_len = shape[0] if transpose else shape[1]
+    kw = dict(shape=shape, transpose=transpose, corder=corder)
+    for fs in (False, True):
+        v = cases.spikes(12, vec_len, 0.2, fs)
+        np.testing.assert_allclose(getattr(G, f"binary_jit{fam}mv")(*params, prob, v, seed, **kw),
+                                   getattr(O, f"binary_jit{fam}mv")(*params, prob, v, seed, **kw), rtol=RTOL, atol=2e-5)
+    for batch in (6, 64, 70):
+        B = cases.spikes(13, vec_len, 0.1, batch=batch)
+        np.testing.assert_allclose(getattr(G, f"binary_jit{fam}mm")(*params, prob, B, seed, **kw),
+                                   getattr(O, f"binary_jit{fam}mm")(*params, prob, B, seed, **kw), rtol=RTOL, atol=2e-5)
+
+
+def test_jitc_normal_weight_bit_exact(G):
+    """One active source, scatter: the output IS the per-edge weight; it must equal the strict
+    light_rng_normal01-based weight bit for bit (explicitly rounded device arithmetic)."""
+    shape, prob, seed = (64, 5000), 0.2, 77
+    for r in (0, 5, 63):
+        v = np.zeros(64, bool)
+        v[r] = True
+        got = G.binary_jitnmv(1.0, 0.1, prob, v, seed, shape=shape, transpose=True, corder=False)
+        ref = O.binary_jitnmv(1.0, 0.1, prob, v, seed, shape=shape, transpose=True, corder=False)
+        nz = ref != 0
+        assert nz.sum() > 500
+        np.testing.assert_array_equal(got != 0, nz)
+        np.testing.assert_allclose(got[nz], ref[nz], rtol=0, atol=2.4e-7)  # <= 1 ulp of the final fma
+
+
+@pytest.mark.parametrize("rows,cols", [(1, 1), (90, 130), (1000, 2050), (4097, 300)])
+@pytest.mark.parametrize("transpose", [False, True])
+def test_dense_vs_oracle(G, rows, cols, transpose):
+    W = np.random.default_rng(14).standard_normal((rows, cols)).astype(np.float32)
+    k = rows if transpose else cols
+    for rate in (0.02, 0.5):
+        for fs in (False, True):
+            v = cases.spikes(15, k, rate, fs)
+            np.testing.assert_allclose(G.binary_densemv(W, v, transpose=transpose),
+                                       O.binary_densemv(W, v, transpose=transpose), rtol=1e-4, atol=1e-4)
+        for batch in (7, 64, 100):
+            B = cases.spikes(16, k, rate, batch=batch)
+            np.testing.assert_allclose(G.binary_densemm(W, B, transpose=transpose),
+                                       O.binary_densemm(W, B, transpose=transpose), rtol=1e-4, atol=1e-4)
+
+
+def test_event_containers_and_classes(G):
+    import brainevent_b200 as be
+    c = cases.csr_case(21, 3000, 2500, 40, 0.1)
+    t = lambda x: torch.as_tensor(x, device="cuda")
+    csr = be.CSR((t(c["data"]), t(c["indices"]), t(c["indptr"])), shape=c["shape"])
+    v = cases.spikes(22, 3000, 0.05)
+    ref = O.binary_csrmv(c["data"], c["indices"], c["indptr"], v, shape=c["shape"], transpose=True)
+    for ev in (be.BinaryArray(t(v)), be.BitPackedBinary(t(v)), be.CompactBinary.from_array(t(v))):
+        np.testing.assert_allclose((ev @ csr).cpu().numpy(), ref, rtol=RTOL, atol=1e-5)
+    vk = cases.spikes(23, 2500, 0.05)
+    refk = O.binary_csrmv(c["data"], c["indices"], c["indptr"], vk, shape=c["shape"])
+    for ev in (be.BinaryArray(t(vk)), be.BitPackedBinary(t(vk)), be.CompactBinary.from_array(t(vk))):
+        np.testing.assert_allclose((csr @ ev).cpu().numpy(), refk, rtol=RTOL, atol=1e-5)
+        np.testing.assert_allclose((ev @ csr.T).cpu().numpy(), refk, rtol=RTOL, atol=1e-5)
+    # batch-major 2-D spikes, the reference's `B @ csr`
+    Bm = cases.spikes(24, 3000, 0.02, batch=16).T.copy()
+    refB = O.binary_csrmm(c["data"], c["indices"], c["indptr"], Bm.T.copy(), shape=c["shape"], transpose=True).T
+    np.testing.assert_allclose((be.BinaryArray(t(Bm)) @ csr).cpu().numpy(), refB, rtol=RTOL, atol=1e-5)
+    # FixedNumPerPre / PerPost in both directions
+    f = cases.fcn_case(25, 1500, 1200, 30)
+    pre = be.FixedNumPerPre((t(f["weights"]), t(f["indices"])), shape=(1500, 1200))
+    s_pre, s_post = cases.spikes(26, 1500, 0.1), cases.spikes(27, 1200, 0.1)
+    np.testing.assert_allclose((be.BinaryArray(t(s_pre)) @ pre).cpu().numpy(),
+                               O.binary_fcnmv(f["weights"], f["indices"], s_pre, shape=(1500, 1200), transpose=True), rtol=RTOL, atol=1e-5)
+    np.testing.assert_allclose((pre @ be.BinaryArray(t(s_post))).cpu().numpy(),
+                               O.binary_fcnmv(f["weights"], f["indices"], s_post, shape=(1500, 1200), transpose=False), rtol=RTOL, atol=1e-5)
+    post = be.FixedNumPerPost((t(f["weights"]), t(f["indices"])), shape=(1200, 1500))   # W [pre=1200, post=1500]
+    dense = post.todense().cpu().numpy()
+    s_p, s_q = cases.spikes(28, 1200, 0.1), cases.spikes(29, 1500, 0.1)
+    np.testing.assert_allclose((be.BinaryArray(t(s_p)) @ post).cpu().numpy(), s_p.astype(np.float32) @ dense, rtol=1e-4, atol=1e-4)
+    np.testing.assert_allclose((post @ be.BinaryArray(t(s_q))).cpu().numpy(), dense @ s_q.astype(np.float32), rtol=1e-4, atol=1e-4)
+    # JITC classes: R and C, both operand sides, against the oracle with the reference's routing
+    for corder in (False, True):
+        R = be.JITCScalarR((1.5, 0.05, 42), shape=(400, 500), corder=corder)
+        a, b = cases.spikes(30, 400, 0.2), cases.spikes(31, 500, 0.2)
+        np.testing.assert_allclose((be.BinaryArray(t(a)) @ R).cpu().numpy(),
+                                   O.binary_jitsmv(1.5, 0.05, a, 42, shape=(400, 500), transpose=True, corder=not corder), rtol=RTOL, atol=1e-5)
+        np.testing.assert_allclose((R @ be.BinaryArray(t(b))).cpu().numpy(),
+                                   O.binary_jitsmv(1.5, 0.05, b, 42, shape=(400, 500), transpose=False, corder=corder), rtol=RTOL, atol=1e-5)
+        C = be.JITCNormalC((1.0, 0.1, 0.05, 42), shape=(400, 500), corder=corder)
+        np.testing.assert_allclose((C @ be.BinaryArray(t(b))).cpu().numpy(),
+                                   O.binary_jitnmv(1.0, 0.1, 0.05, b, 42, shape=(500, 400), transpose=True, corder=corder), rtol=RTOL, atol=1e-5)
+        np.testing.assert_allclose((be.BinaryArray(t(a)) @ C).cpu().numpy(),
+                                   O.binary_jitnmv(1.0, 0.1, 0.05, a, 42, shape=(500, 400), transpose=False, corder=not corder), rtol=RTOL, atol=1e-5)
+
+
+def test_size_independent_properties_at_scale(G):
+    """1M-neuron sizes: checksum and linearity properties instead of a CPU oracle run."""
+    import brainevent_b200 as be
+    n, nnz = 1_000_000, 100
+    g = torch.Generator(device="cuda").manual_seed(0)
+    indices = torch.randint(0, n, (n * nnz,), device="cuda", dtype=torch.int32, generator=g)
+    indptr = torch.arange(0, (n + 1) * nnz, nnz, device="cuda", dtype=torch.int32)
+    w = torch.rand(n * nnz, device="cuda", generator=g)
+    s1 = torch.rand(n, device="cuda", generator=g) < 0.01
+    s2 = (torch.rand(n, device="cuda", generator=g) < 0.01) & ~s1
+    y1 = be.binary_csrmv(w, indices, indptr, s1, shape=(n, n), transpose=True)
+    y2 = be.binary_csrmv(w, indices, indptr, s2, shape=(n, n), transpose=True)
+    y12 = be.binary_csrmv(w, indices, indptr, s1 | s2, shape=(n, n), transpose=True)
+    torch.testing.assert_close(y12, y1 + y2, rtol=1e-4, atol=1e-4)            # linearity over disjoint events
+    rows = s1.nonzero().flatten()
+    expect = w.view(n, nnz)[rows].double().sum()
+    assert abs(y1.double().sum().item() - expect.item()) <= 1e-6 * abs(expect.item()) + 1e-3   # checksum
+    # same structure as ELL: FCN scatter must agree with CSR scatter
+    yf = be.binary_fcnmv(w.view(n, nnz), indices.view(n, nnz), s1, shape=(n, n), transpose=True)
+    torch.testing.assert_close(yf, y1, rtol=1e-4, atol=1e-4)
+    # gather direction equals scatter direction of the CSC mirror's transpose: sum check
+    yg = be.binary_csrmv(w, indices, indptr, s1, shape=(n, n), transpose=False)
+    bits = s1[indices.long()].view(n, nnz)
+    torch.testing.assert_close(yg, (w.view(n, nnz) * bits).sum(1), rtol=1e-4, atol=1e-4)
