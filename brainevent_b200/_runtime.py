@@ -51,11 +51,14 @@ _WS = {}
 
 
 def workspace(device, n_src: int, n_batch: int = 1):
-    need = int(_lib.lib().be_b200_workspace_bytes(int(n_src), int(n_batch)))
-    key = (torch.device(device).index, torch.cuda.current_stream(device).cuda_stream)
+    """The carve-up of a workspace depends on (n_src, n_batch) and its header / tile-status words
+    must be zero on first use, so buffers are cached per layout and never shared across layouts."""
+    dev = torch.device(device)
+    key = (dev.index, torch.cuda.current_stream(dev).cuda_stream, int(n_src), int(n_batch))
     buf = _WS.get(key)
-    if buf is None or buf.numel() < need:
-        buf = torch.zeros(max(need, 1 << 16), dtype=torch.uint8, device=device)
+    if buf is None:
+        need = int(_lib.lib().be_b200_workspace_bytes(int(n_src), int(n_batch)))
+        buf = torch.zeros(need, dtype=torch.uint8, device=dev)
         _WS[key] = buf
     return buf
 

@@ -74,7 +74,7 @@ struct Workspace {
 
 static inline size_t ws_packed_words(int64_t n_src, int64_t n_batch) {
     int64_t w1 = ceil_div(n_src, 32) + 4;
-    int64_t w2 = n_batch > 1 ? n_src * ceil_div(n_batch, 32) : 0;
+    int64_t w2 = n_src * ceil_div(n_batch < 1 ? 1 : n_batch, 32);  // 2-D events with batch 1 still use one word per row
     return (size_t)(w1 > w2 ? w1 : w2);
 }
 static inline size_t ws_status_words(int64_t n_src) {

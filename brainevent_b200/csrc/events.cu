@@ -493,7 +493,7 @@ extern "C" int be_b200_compact_1d(const void* spikes, int spk_kind, int64_t n, i
                                   void* workspace, size_t workspace_bytes, void* stream) {
     cudaStream_t s = (cudaStream_t)stream;
     BE_REQUIRE(n >= 0 && n < (1ll << 31), "n out of range");
-    BE_REQUIRE(active_ids && n_active, "NULL output");
+    BE_REQUIRE((active_ids || n == 0) && n_active, "NULL output");
     int rc = check_ws(workspace, workspace_bytes, n, 1);
     if (rc) return rc;
     Workspace ws = ws_carve(workspace, n, 1);
@@ -507,7 +507,7 @@ extern "C" int be_b200_compact_2d(const void* spikes, int spk_kind, int64_t n, i
                                   void* stream) {
     cudaStream_t s = (cudaStream_t)stream;
     BE_REQUIRE(n >= 0 && n < (1ll << 31) && batch >= 1, "shape out of range");
-    BE_REQUIRE(active_ids && n_active, "NULL output");
+    BE_REQUIRE((active_ids || n == 0) && n_active, "NULL output");
     int rc = check_ws(workspace, workspace_bytes, n, batch);
     if (rc) return rc;
     Workspace ws = ws_carve(workspace, n, batch);

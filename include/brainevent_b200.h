@@ -62,7 +62,11 @@ int be_b200_check_device(void);
 
 /* Scratch space.  Every operator takes a caller-owned device workspace (the reference aliases
  * task_begin/task_end/status buffers the same way, ref: _csr/binary.py:55-124).  `n_src` is the
- * number of source (event) rows, `n_batch` the event batch width (1 for matvec). */
+ * number of source (event) rows, `n_batch` the event batch width (1 for matvec).  The buffer
+ * must be 256-byte aligned and ZERO on first use; the library leaves its control words zero
+ * again after every call (self-resetting scan state), so no per-call memset is needed -- but a
+ * buffer must not be re-used with a different (n_src, n_batch) without zeroing it again, and
+ * concurrent calls (different streams) need separate buffers. */
 size_t be_b200_workspace_bytes(int64_t n_src, int64_t n_batch);
 
 /* ---- event encoders (ref: _event/compact.py:258,406,589; _event/compact.cu:70-430;
