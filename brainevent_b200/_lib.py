@@ -46,6 +46,8 @@ _SIGNATURES = {
     "be_b200_abi_version": (_I, []),
     "be_b200_check_device": (_I, []),
     "be_b200_workspace_bytes": (_Z, [_L, _L]),
+    "be_b200_profile_begin": (_I, [_I]),
+    "be_b200_profile_end": (_I, [_P, _I, _P]),
     "be_b200_bitpack_1d": (_I, [_P, _I, _L, _I, _P, _P]),
     "be_b200_compact_1d": (_I, [_P, _I, _L, _I, _P, _P, _P, _P, _Z, _P]),
     "be_b200_compact_2d": (_I, [_P, _I, _L, _L, _I, _P, _P, _P, _P, _Z, _P]),
@@ -62,6 +64,7 @@ _SIGNATURES = {
     "be_b200_csr_to_csc": (_I, [_P, _I, _P, _L, _L, _L, _P, _P, _P, _P, _Z, _P]),
     "be_b200_projection_create_csr": (_P, [_P, _I, _P, _P, _L, _L]),
     "be_b200_projection_create_fcn": (_P, [_P, _I, _P, _L, _L, _L]),
+    "be_b200_projection_adopt_fcn": (_P, [_P, _I, _P, _L, _L, _L]),
     "be_b200_projection_create_jitc": (_P, [_I, ctypes.c_float, ctypes.c_float, ctypes.c_int32, ctypes.c_int32, _L, _L, _L, _I]),
     "be_b200_projection_apply_host": (_I, [_P, _P, _P]),
     "be_b200_projection_destroy": (None, [_P]),

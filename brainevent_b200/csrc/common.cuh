@@ -200,6 +200,16 @@ __device__ __forceinline__ Vec4<__nv_bfloat16> load4(const __nv_bfloat16* p) {
                  return BE_B200_EUNIMPL;                                          \
     }
 
+// Optional timing of the dominant kernel of each operator (bench.py's roofline): when enabled via
+// be_b200_profile_begin, a ProfileScope records a CUDA event pair around the kernel launch on
+// the launching stream.  Disabled (the default) it costs one predictable branch.
+struct ProfileScope {
+    cudaStream_t s;
+    int slot;
+    explicit ProfileScope(cudaStream_t stream);
+    ~ProfileScope();
+};
+
 // events.cu: normalise any supported event encoding into `Events` (packing / compaction as
 // needed by the consumer), enqueued on `stream`.
 int prepare_events_1d(const void* spikes, const void* aux, int spk_kind, int64_t n,

@@ -354,8 +354,11 @@ static int launch_scatter_mv(const Rows& rows, const ConnArgs& c, const Events& 
 #define BE_SC(VEC, LPR)                                                                      \
     scatter_mv_kernel<T, HOMO, PERM, VEC, LPR, Rows><<<blocks, 256, 0, s>>>(                 \
         rows, c.indices, (const T*)c.weights, c.perm, ev.active_ids, ev.n_active, out)
-    if (vec) { if (narrow) BE_SC(true, 8); else BE_SC(true, 32); }
-    else { if (narrow) BE_SC(false, 8); else BE_SC(false, 32); }
+    {
+        ProfileScope prof(s);
+        if (vec) { if (narrow) BE_SC(true, 8); else BE_SC(true, 32); }
+        else { if (narrow) BE_SC(false, 8); else BE_SC(false, 32); }
+    }
 #undef BE_SC
     BE_LAUNCH_CHECK("scatter_mv_kernel");
     return BE_B200_OK;
@@ -373,7 +376,10 @@ static int launch_gather_mv(const Rows& rows, const ConnArgs& c, const Events& e
         rows, c.indices, (const T*)c.weights, c.perm, ev.packed, n_rows, out)
 #define BE_GA2(VEC) switch (lpr) { case 4: BE_GA(VEC, 4); break; case 8: BE_GA(VEC, 8); break; \
                                    case 16: BE_GA(VEC, 16); break; default: BE_GA(VEC, 32); }
-    if (vec) { BE_GA2(true) } else { BE_GA2(false) }
+    {
+        ProfileScope prof(s);
+        if (vec) { BE_GA2(true) } else { BE_GA2(false) }
+    }
 #undef BE_GA2
 #undef BE_GA
     BE_LAUNCH_CHECK("gather_mv_kernel");
@@ -384,9 +390,12 @@ template <typename T, bool HOMO, int PERM, typename Rows>
 static int launch_scatter_mm(const Rows& rows, const ConnArgs& c, const Events& ev, int64_t n_src,
                              int64_t n, T* out, cudaStream_t s) {
     int blocks = (int)std::min<int64_t>(ceil_div(std::max<int64_t>(n_src, 1), 8), kNumSM * 8);
-    scatter_mm_kernel<T, HOMO, PERM, Rows><<<blocks, 256, 0, s>>>(
-        rows, c.indices, (const T*)c.weights, c.perm, ev.active_ids, ev.n_active, ev.packed,
-        ev.words_per_row, n, out);
+    {
+        ProfileScope prof(s);
+        scatter_mm_kernel<T, HOMO, PERM, Rows><<<blocks, 256, 0, s>>>(
+            rows, c.indices, (const T*)c.weights, c.perm, ev.active_ids, ev.n_active, ev.packed,
+            ev.words_per_row, n, out);
+    }
     BE_LAUNCH_CHECK("scatter_mm_kernel");
     return BE_B200_OK;
 }
@@ -400,7 +409,10 @@ static int launch_gather_mm(const Rows& rows, const ConnArgs& c, const Events& e
 #define BE_GM(CPL)                                                                           \
     gather_mm_kernel<T, HOMO, PERM, CPL, Rows><<<blocks, 256, 0, s>>>(                       \
         rows, c.indices, (const T*)c.weights, c.perm, ev.packed, wpr, n_rows, n, out)
-    if (wpr == 1) BE_GM(1); else if (wpr == 2) BE_GM(2); else BE_GM(4);
+    {
+        ProfileScope prof(s);
+        if (wpr == 1) BE_GM(1); else if (wpr == 2) BE_GM(2); else BE_GM(4);
+    }
 #undef BE_GM
     BE_LAUNCH_CHECK("gather_mm_kernel");
     return BE_B200_OK;

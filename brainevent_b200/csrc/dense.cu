@@ -172,12 +172,12 @@ static int run_dense_mv(const T* W, int64_t rows, int64_t cols, const Events& ev
         if (slices > 1) BE_CUDA(cudaMemsetAsync(out, 0, (size_t)cols * sizeof(T), s));
         const bool vec = (((uintptr_t)W & 15u) == 0) && ((cols * sizeof(T)) % 16 == 0);
         dim3 grid((unsigned)col_blocks, (unsigned)slices);
-        dense_mv_t_kernel<T><<<grid, 256, 0, s>>>(W, cols, ev.active_ids, ev.n_active, out, vec);
+        { ProfileScope prof(s); dense_mv_t_kernel<T><<<grid, 256, 0, s>>>(W, cols, ev.active_ids, ev.n_active, out, vec); }
         BE_LAUNCH_CHECK("dense_mv_t_kernel");
     } else {
         if (rows == 0) return BE_B200_OK;
         int blocks = (int)std::min<int64_t>(ceil_div(rows, 8), (int64_t)kNumSM * 16);
-        dense_mv_nt_kernel<T><<<blocks, 256, 0, s>>>(W, rows, cols, ev.packed, ev.active_ids, ev.n_active, out);
+        { ProfileScope prof(s); dense_mv_nt_kernel<T><<<blocks, 256, 0, s>>>(W, rows, cols, ev.packed, ev.active_ids, ev.n_active, out); }
         BE_LAUNCH_CHECK("dense_mv_nt_kernel");
     }
     return BE_B200_OK;
@@ -202,14 +202,14 @@ static int run_dense_mm(const T* W, int64_t rows, int64_t cols, const Events& ev
             attr_set[slot] = true;
         }
         dim3 grid((unsigned)row_blocks, (unsigned)slices);
-        dense_mm_t_kernel<T><<<grid, 256, smem, s>>>(W, m, ev.packed, wpr, ev.active_ids, ev.n_active, n, out);
+        { ProfileScope prof(s); dense_mm_t_kernel<T><<<grid, 256, smem, s>>>(W, m, ev.packed, wpr, ev.active_ids, ev.n_active, n, out); }
         BE_LAUNCH_CHECK("dense_mm_t_kernel");
     } else {
         const int64_t m = rows, k = cols;
         if (m == 0) return BE_B200_OK;
         int blocks = (int)std::min<int64_t>(ceil_div(m, 8), (int64_t)kNumSM * 16);
 #define BE_DN(CPL) dense_mm_nt_kernel<T, CPL><<<blocks, 256, 0, s>>>(W, m, k, ev.packed, wpr, n, out)
-        if (wpr == 1) BE_DN(1); else if (wpr == 2) BE_DN(2); else BE_DN(4);
+        { ProfileScope prof(s); if (wpr == 1) BE_DN(1); else if (wpr == 2) BE_DN(2); else BE_DN(4); }
 #undef BE_DN
         BE_LAUNCH_CHECK("dense_mm_nt_kernel");
     }

@@ -28,6 +28,28 @@ int cuda_fail(cudaError_t e, const char* what) {
 }
 
 // ------------------------------------------------------------------------------------------
+// kernel-duration profiling (diagnostic; process-wide)
+// ------------------------------------------------------------------------------------------
+static struct {
+    volatile int on;
+    int cap;
+    int count;
+    cudaEvent_t* start;
+    cudaEvent_t* stop;
+} g_prof = {0, 0, 0, nullptr, nullptr};
+
+ProfileScope::ProfileScope(cudaStream_t stream) : s(stream), slot(-1) {
+    if (!g_prof.on) return;
+    int i = __sync_fetch_and_add(&g_prof.count, 1);
+    if (i >= g_prof.cap) return;
+    slot = i;
+    cudaEventRecord(g_prof.start[i], s);
+}
+ProfileScope::~ProfileScope() {
+    if (slot >= 0) cudaEventRecord(g_prof.stop[slot], s);
+}
+
+// ------------------------------------------------------------------------------------------
 // tile status word: [63:62] flag, [31:0] value
 // ------------------------------------------------------------------------------------------
 constexpr unsigned long long kFlagAgg = 1ull << 62;
@@ -468,6 +490,40 @@ extern "C" int be_b200_check_device(void) {
     BE_REQUIRE(p.major == 10, "brainevent_b200 is built for sm_100a only; device %d is sm_%d%d",
                dev, p.major, p.minor);
     return BE_B200_OK;
+}
+
+extern "C" int be_b200_profile_begin(int max_records) {
+    BE_REQUIRE(max_records > 0 && max_records <= (1 << 20), "profile_begin: bad capacity");
+    BE_REQUIRE(!be::g_prof.on, "profile_begin: already profiling");
+    be::g_prof.start = new cudaEvent_t[max_records];
+    be::g_prof.stop = new cudaEvent_t[max_records];
+    for (int i = 0; i < max_records; ++i) {
+        BE_CUDA(cudaEventCreate(&be::g_prof.start[i]));
+        BE_CUDA(cudaEventCreate(&be::g_prof.stop[i]));
+    }
+    be::g_prof.cap = max_records;
+    be::g_prof.count = 0;
+    be::g_prof.on = 1;
+    return BE_B200_OK;
+}
+
+extern "C" int be_b200_profile_end(float* ms_out, int capacity, int* n_out) {
+    BE_REQUIRE(be::g_prof.on, "profile_end: not profiling");
+    be::g_prof.on = 0;
+    int n = be::g_prof.count < be::g_prof.cap ? be::g_prof.count : be::g_prof.cap;
+    int rc = BE_B200_OK;
+    for (int i = 0; i < n; ++i) {
+        float ms = 0.f;
+        cudaError_t e = cudaEventSynchronize(be::g_prof.stop[i]);
+        if (e == cudaSuccess) e = cudaEventElapsedTime(&ms, be::g_prof.start[i], be::g_prof.stop[i]);
+        if (e != cudaSuccess) rc = be::cuda_fail(e, "profile_end");
+        if (ms_out && i < capacity) ms_out[i] = ms;
+    }
+    for (int i = 0; i < be::g_prof.cap; ++i) { cudaEventDestroy(be::g_prof.start[i]); cudaEventDestroy(be::g_prof.stop[i]); }
+    delete[] be::g_prof.start; delete[] be::g_prof.stop;
+    be::g_prof.start = be::g_prof.stop = nullptr;
+    if (n_out) *n_out = n;
+    return rc;
 }
 
 extern "C" size_t be_b200_workspace_bytes(int64_t n_src, int64_t n_batch) {

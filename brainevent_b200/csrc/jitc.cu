@@ -370,8 +370,11 @@ static int run_jit_mv(const JitParams& jp, const Events& ev, int64_t vec_len, in
     if (corder) {
         if (row_count == 0) return BE_B200_OK;
         int blocks = (int)std::min<int64_t>(ceil_div(row_count, 8), (int64_t)kNumSM * 32);
-        jit_mv_gather_kernel<T, KIND><<<blocks, 256, 0, s>>>(jp, ev.packed, vec_len, chunk_size,
-                                                            row_offset, row_count, out);
+        {
+            ProfileScope prof(s);
+            jit_mv_gather_kernel<T, KIND><<<blocks, 256, 0, s>>>(jp, ev.packed, vec_len, chunk_size,
+                                                                row_offset, row_count, out);
+        }
         BE_LAUNCH_CHECK("jit_mv_gather_kernel");
     } else {
         const int64_t own = col_end - col_begin;
@@ -380,9 +383,12 @@ static int run_jit_mv(const JitParams& jp, const Events& ev, int64_t vec_len, in
         if (vec_len == 0) return BE_B200_OK;
         const int64_t n_chunks = ceil_div(out_len, chunk_size);
         int blocks = (int)std::min<int64_t>(ceil_div(std::max<int64_t>(vec_len * n_chunks, 1), 8), (int64_t)kNumSM * 8);
-        jit_mv_scatter_kernel<T, KIND><<<blocks, 256, 0, s>>>(jp, ev.active_ids, ev.n_active, out_len,
-                                                             chunk_size, row_offset, row_count,
-                                                             col_begin, col_end, out);
+        {
+            ProfileScope prof(s);
+            jit_mv_scatter_kernel<T, KIND><<<blocks, 256, 0, s>>>(jp, ev.active_ids, ev.n_active, out_len,
+                                                                 chunk_size, row_offset, row_count,
+                                                                 col_begin, col_end, out);
+        }
         BE_LAUNCH_CHECK("jit_mv_scatter_kernel");
     }
     return BE_B200_OK;
@@ -395,7 +401,10 @@ static int run_jit_mm(const JitParams& jp, const Events& ev, int64_t vec_len, in
     if (corder) {
         int blocks = (int)std::min<int64_t>(ceil_div(out_len, 8), (int64_t)kNumSM * 32);
 #define BE_JG(CPL) jit_mm_gather_kernel<T, KIND, CPL><<<blocks, 256, 0, s>>>(jp, ev.packed, wpr, vec_len, out_len, n, chunk_size, out)
-        if (wpr == 1) BE_JG(1); else if (wpr == 2) BE_JG(2); else BE_JG(4);
+        {
+            ProfileScope prof(s);
+            if (wpr == 1) BE_JG(1); else if (wpr == 2) BE_JG(2); else BE_JG(4);
+        }
 #undef BE_JG
         BE_LAUNCH_CHECK("jit_mm_gather_kernel");
     } else {
@@ -403,8 +412,11 @@ static int run_jit_mm(const JitParams& jp, const Events& ev, int64_t vec_len, in
         if (vec_len == 0) return BE_B200_OK;
         const int64_t n_chunks = ceil_div(out_len, chunk_size);
         int blocks = (int)std::min<int64_t>(ceil_div(std::max<int64_t>(vec_len * n_chunks, 1), 8), (int64_t)kNumSM * 8);
-        jit_mm_scatter_kernel<T, KIND><<<blocks, 256, 0, s>>>(jp, ev.active_ids, ev.n_active, ev.packed,
-                                                             wpr, out_len, n, chunk_size, out);
+        {
+            ProfileScope prof(s);
+            jit_mm_scatter_kernel<T, KIND><<<blocks, 256, 0, s>>>(jp, ev.active_ids, ev.n_active, ev.packed,
+                                                                 wpr, out_len, n, chunk_size, out);
+        }
         BE_LAUNCH_CHECK("jit_mm_scatter_kernel");
     }
     return BE_B200_OK;

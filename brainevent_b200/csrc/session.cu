@@ -21,6 +21,7 @@ struct be_b200_projection {
     void* d_ws;
     size_t ws_bytes;
     cudaStream_t stream;
+    int borrowed;  // connectivity pointers belong to the caller
 };
 
 using namespace be;
@@ -75,6 +76,19 @@ extern "C" be_b200_projection* be_b200_projection_create_fcn(const float* weight
     return p;
 }
 
+extern "C" be_b200_projection* be_b200_projection_adopt_fcn(const float* d_weights, int homo,
+                                                            const int32_t* d_indices,
+                                                            int64_t n_rows, int64_t n_conn,
+                                                            int64_t n_post) {
+    if (!d_weights || n_rows < 0 || n_conn < 0 || n_post < 0) { set_error("projection_adopt_fcn: bad arguments"); return nullptr; }
+    be_b200_projection* p = proj_new(1, n_rows, n_post);
+    if (!p) return nullptr;
+    p->homo = homo; p->n_conn = n_conn; p->nse = n_rows * n_conn; p->borrowed = 1;
+    p->d_weights = (void*)d_weights;
+    p->d_indices = (int32_t*)d_indices;
+    return p;
+}
+
 extern "C" be_b200_projection* be_b200_projection_create_jitc(int jit_kind, float p0, float p1,
                                                               int32_t clen, int32_t seed,
                                                               int64_t n_pre, int64_t n_post,
@@ -117,7 +131,8 @@ extern "C" int be_b200_projection_apply_host(be_b200_projection* p, const uint8_
 
 extern "C" void be_b200_projection_destroy(be_b200_projection* p) {
     if (!p) return;
-    cudaFree(p->d_weights); cudaFree(p->d_indices); cudaFree(p->d_indptr); cudaFree(p->d_p);
+    if (!p->borrowed) { cudaFree(p->d_weights); cudaFree(p->d_indices); cudaFree(p->d_indptr); }
+    cudaFree(p->d_p);
     cudaFree(p->d_clen_seed); cudaFree(p->d_events); cudaFree(p->d_out); cudaFree(p->d_ws);
     if (p->stream) cudaStreamDestroy(p->stream);
     delete p;

@@ -1,0 +1,130 @@
+"""Post-synaptic sharding across the GPUs of one box (net-new: the reference has no distributed
+code).
+
+Layout: rank g owns the contiguous block of post-synaptic neurons [lo_g, hi_g) and stores only the
+synapses that END in its block (pre-major, local post ids), so outputs are disjoint and need no
+reduction.  Per timestep every rank bit-packs the spikes of the neurons it owns and ONE all-gather
+of uint32 words delivers the global spike vector (N/32 words in total); propagation then runs on
+the packed words directly (event kind PACKED of the C ABI).  Block sizes are multiples of 32 so
+the concatenation of per-rank words IS the packing of the concatenated spike vector.
+"""
+from typing import List, Optional, Tuple
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+ALIGN = 32
+
+
+def post_block_bounds(n_post: int, world: int, align: int = ALIGN) -> List[Tuple[int, int]]:
+    """Contiguous blocks, every boundary but the last a multiple of `align`."""
+    per = -(-n_post // world)
+    per = -(-per // align) * align
+    out = []
+    for g in range(world):
+        lo = min(g * per, n_post)
+        hi = min(lo + per, n_post)
+        out.append((lo, hi))
+    return out
+
+
+def partition_csr_by_post(indptr, indices, data, n_post: int, world: int):
+    """Split a pre-major CSR (rows = pre, cols = post) into per-rank CSRs holding the synapses that
+    end in each rank's post block, with LOCAL column ids.  Works on numpy arrays (setup time).
+    Returns [(indptr_g, indices_g, data_g, (lo, hi)), ...].  Order within a row is preserved, so
+    each shard sums its synapses in the same order as the unsharded matrix."""
+    indptr = np.asarray(indptr)
+    indices = np.asarray(indices)
+    data = np.asarray(data)
+    homo = data.size == 1
+    m = indptr.shape[0] - 1
+    row_of = np.repeat(np.arange(m, dtype=np.int64), np.diff(indptr))
+    shards = []
+    for lo, hi in post_block_bounds(n_post, world):
+        sel = (indices >= lo) & (indices < hi)
+        counts = np.bincount(row_of[sel], minlength=m)
+        ip = np.zeros(m + 1, indptr.dtype)
+        np.cumsum(counts, out=ip[1:])
+        shards.append((ip, (indices[sel] - lo).astype(np.int32), data if homo else data[sel], (lo, hi)))
+    return shards
+
+
+def partition_fcn_by_post(indices, weights, n_post: int, world: int):
+    """FixedNumPerPre [n_pre, n_conn] -> per-rank ragged CSR shards (the per-rank fan-out of a pre
+    neuron is binomial, so shards are CSR, not ELL)."""
+    indices = np.asarray(indices)
+    n_pre, n_conn = indices.shape
+    indptr = (np.arange(n_pre + 1, dtype=np.int64) * n_conn)
+    w = np.asarray(weights)
+    return partition_csr_by_post(indptr if indptr[-1] >= 2**31 else indptr.astype(np.int32),
+                                 indices.reshape(-1), w if w.size == 1 else w.reshape(-1), n_post, world)
+
+
+class SpikeExchange:
+    """All-gather of bit-packed spike words over the process group (NCCL on GPUs, gloo in tests)."""
+
+    def __init__(self, n_neurons: int, group=None, device="cuda"):
+        self.group = group
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        self.bounds = post_block_bounds(n_neurons, self.world)
+        self.n_neurons = n_neurons
+        self.words_per_rank = (self.bounds[0][1] - self.bounds[0][0] + 31) // 32
+        self.local = self.bounds[self.rank]
+        self.gathered = torch.zeros(self.words_per_rank * self.world, dtype=torch.int32, device=device)
+        self.n_words = (n_neurons + 31) // 32
+
+    def exchange(self, packed_local: torch.Tensor) -> torch.Tensor:
+        """packed_local: int32[words_per_rank] (zero-padded) -> int32[ceil(N/32)] global words."""
+        assert packed_local.numel() == self.words_per_rank and packed_local.dtype == torch.int32
+        if self.world == 1:
+            return packed_local
+        dist.all_gather_into_tensor(self.gathered, packed_local, group=self.group)
+        return self.gathered[: self.n_words]
+
+
+class PostShardedProjection:
+    """One rank's share of a projection pre[N] -> post[N], partitioned by post block.
+
+    `kind`: 'fcn' (weights/indices [n_pre_total, n_conn_local], local post ids), 'csr'
+    (data, indices, indptr with local post ids) or 'jitc' (parameters only; the generated matrix is
+    sliced by a column window for the scatter orientation or a row window for the gather
+    orientation, with the GLOBAL shape keying the RNG walk)."""
+
+    def __init__(self, kind: str, n_pre: int, n_post: int, exchange: SpikeExchange, **conn):
+        self.kind, self.n_pre, self.n_post, self.x = kind, n_pre, n_post, exchange
+        self.lo, self.hi = post_block_bounds(n_post, exchange.world)[exchange.rank]
+        self.conn = conn
+
+    def pack_local(self, local_spikes: torch.Tensor) -> torch.Tensor:
+        """Bit-pack the spikes of the neurons this rank owns into its all-gather slot."""
+        from ._event import bitpack
+        words = bitpack(local_spikes, axis=0)
+        if words.numel() < self.x.words_per_rank:
+            words = torch.nn.functional.pad(words, (0, self.x.words_per_rank - words.numel()))
+        return words
+
+    def propagate(self, packed_all: torch.Tensor) -> torch.Tensor:
+        """packed global spikes -> this rank's block of the output."""
+        from ._csr import binary_csrmv
+        from ._event import BitPackedBinary
+        from ._fcn import binary_fcnmv
+        from . import _jitc
+        ev = BitPackedBinary(packed=packed_all, shape=(self.n_pre,))
+        n_loc = self.hi - self.lo
+        c = self.conn
+        if self.kind == "fcn":
+            return binary_fcnmv(c["weights"], c["indices"], ev, shape=(self.n_pre, n_loc), transpose=True)
+        if self.kind == "csr":
+            return binary_csrmv(c["data"], c["indices"], c["indptr"], ev, shape=(self.n_pre, n_loc), transpose=True)
+        if self.kind == "jitc":
+            op = {"scalar": _jitc.binary_jitsmv, "normal": _jitc.binary_jitnmv, "uniform": _jitc.binary_jitumv}[c["family"]]
+            corder = c["corder"]  # passed corder: True = gather (rows = post), False = scatter (cols = post)
+            extra = dict(row_window=(self.lo, n_loc)) if corder else dict(col_window=(self.lo, self.hi))
+            return op(*c["params"], c["prob"], ev, c["seed"], shape=(self.n_pre, self.n_post), transpose=True,
+                      corder=corder, **extra)
+        raise ValueError(self.kind)
+
+    def step(self, local_spikes: torch.Tensor) -> torch.Tensor:
+        return self.propagate(self.x.exchange(self.pack_local(local_spikes)))

@@ -60,6 +60,12 @@ int be_b200_abi_version(void);
 /* Device capability check: returns 0 when the current device is sm_100 (B200). */
 int be_b200_check_device(void);
 
+/* Kernel-duration instrumentation for benchmarks: between begin/end every operator records a
+ * CUDA event pair around its dominant kernel on the launching stream; end() synchronises those
+ * events and returns the per-launch durations in milliseconds (launch order). */
+int be_b200_profile_begin(int max_records);
+int be_b200_profile_end(float* ms_out, int capacity, int* n_out);
+
 /* Scratch space.  Every operator takes a caller-owned device workspace (the reference aliases
  * task_begin/task_end/status buffers the same way, ref: _csr/binary.py:55-124).  `n_src` is the
  * number of source (event) rows, `n_batch` the event batch width (1 for matvec).  The buffer
@@ -182,6 +188,11 @@ be_b200_projection* be_b200_projection_create_csr(const float* weights, int homo
 be_b200_projection* be_b200_projection_create_fcn(const float* weights, int homo,
                                                   const int32_t* indices, int64_t n_rows,
                                                   int64_t n_conn, int64_t n_post);
+/* Same as create_fcn but the connectivity already lives in device memory and stays owned by the
+ * caller (no copy); used when the matrix is generated on the device. */
+be_b200_projection* be_b200_projection_adopt_fcn(const float* d_weights, int homo,
+                                                 const int32_t* d_indices, int64_t n_rows,
+                                                 int64_t n_conn, int64_t n_post);
 be_b200_projection* be_b200_projection_create_jitc(int jit_kind, float p0, float p1, int32_t clen,
                                                    int32_t seed, int64_t n_pre, int64_t n_post,
                                                    int64_t chunk_size, int corder);
