@@ -250,6 +250,7 @@ class Jitc1M(Workload):
     def __init__(self, torch, be, device, corder, rate=0.01):
         self.be = be
         n = 1_000_000
+        self.corder = corder
         self.dominant_kernel = "jit_mv_scatter_kernel" if corder else "jit_mv_gather_kernel"
         self.m = be.JITCNormalR((1.0, 0.1, 1e-3, 123), shape=(n, n), corder=corder)
         self.pool = spike_pool(torch, n, rate, 5, device)

@@ -15,7 +15,7 @@ from . import _lib
 from ._csr import _EVENT_TYPES
 from ._event import BinaryArray
 from ._op import XLACustomKernel, maybe_decimal, split_mantissa_unit
-from ._runtime import as_tensor, event_args, ptr, stream_ptr, workspace, wt_code
+from ._runtime import EventArgs, as_tensor, event_args, ptr, stream_ptr, workspace, wt_code
 
 MV_STRIDE, MM_STRIDE = 32, 4   # ref: _misc.py:37-38
 _KIND = {"scalar": _lib.JIT_SCALAR, "normal": _lib.JIT_NORMAL, "uniform": _lib.JIT_UNIFORM}
@@ -105,7 +105,7 @@ def _param(x, device, dtype):
 
 
 def _jit_p_call(prim, params, clen, x, seed, shape, transpose, corder, backend, matmat, **extra):
-    ev = event_args(x)
+    ev = x if isinstance(x, EventArgs) else event_args(x)
     dev = ev.device
     assert len(shape) == 2, "The matrix shape should be a tuple of two integers."
     shape = (int(shape[0]), int(shape[1]))
@@ -172,7 +172,7 @@ def jitc_row_connections(prob, seed, rows, k, chunk_size, stride=MV_STRIDE, devi
 # ---------------------------------------------------------------------------------------------
 class JITCMatrix:
     """Base of the just-in-time connectivity matrices (ref: _data.py JITCMatrix)."""
-    _mv = _mm = None
+    _prims = None
 
     def __init__(self, params, prob, seed, *, shape, corder=False, backend=None):
         self.params = tuple(params)
@@ -182,39 +182,47 @@ class JITCMatrix:
         self.corder = bool(corder)
         self.backend = backend
 
+        self._dev = {}
+
+    def _device_params(self, device):
+        """weight parameters, clen and seed as one-element device tensors, created once per device
+        (the reference keeps them as jax arrays); keeps the per-call path free of host->device
+        copies so it can be captured in a CUDA graph."""
+        key = str(device)
+        if key not in self._dev:
+            vals = [_param(split_mantissa_unit(p)[0], device, None) for p in self.params]
+            vals = [v.to(vals[0].dtype) for v in vals]
+            self._dev[key] = (vals, _initialize_conn_length(self.prob, device), _initialize_seed(self.seed, device))
+        return self._dev[key]
+
     def _call(self, other, shape, transpose, corder):
-        mv, mm = type(self)._mv, type(self)._mm
         if not isinstance(other, _EVENT_TYPES):
             raise NotImplementedError("brainevent_b200 implements the event-driven path only: wrap the "
                                       "operand in BinaryArray / BitPackedBinary / CompactBinary")
-        if other.ndim == 1:
-            return mv(*self.params, self.prob, other, self.seed, shape=shape, transpose=transpose,
-                      corder=corder, backend=self.backend)
-        if other.ndim == 2:
-            return mm, other
-        raise NotImplementedError(f"matmul with object of shape {other.shape}")
+        if other.ndim not in (1, 2):
+            raise NotImplementedError(f"matmul with object of shape {other.shape}")
+        return other.ndim == 2
+
+    def _run(self, x, shape, transpose, corder, matmat):
+        prim = type(self)._prims[1 if matmat else 0]
+        ev = event_args(x)
+        vals, clen, seed = self._device_params(ev.device)
+        res = _jit_p_call(prim, vals, clen, ev, seed, shape, transpose, corder, self.backend, matmat)[0]
+        return maybe_decimal(res, split_mantissa_unit(self.params[0])[1])
 
 
 class _JITC_R(JITCMatrix):
     """Row-oriented: the generated matrix has the logical shape (ref: _jit_scalar/main.py:885-1066)."""
 
     def __matmul__(self, other):
-        r = self._call(other, self.shape, False, self.corder)
-        if isinstance(r, tuple):
-            mm, other = r
-            return mm(*self.params, self.prob, other, self.seed, shape=self.shape, transpose=False,
-                      corder=self.corder, backend=self.backend)
-        return r
+        return self._run(other, self.shape, False, self.corder, self._call(other, None, None, None))
 
     def __rmatmul__(self, other):
-        r = self._call(other, self.shape, True, not self.corder)
-        if isinstance(r, tuple):
-            mm, other = r
+        if self._call(other, None, None, None):
             if not isinstance(other, BinaryArray):
                 raise NotImplementedError("2-D packed events must be packed along the batch axis")
-            return mm(*self.params, self.prob, other.value.t(), self.seed, shape=self.shape, transpose=True,
-                      corder=not self.corder, backend=self.backend).t()
-        return r
+            return self._run(other.value.t(), self.shape, True, not self.corder, True).t()
+        return self._run(other, self.shape, True, not self.corder, False)
 
 
 class _JITC_C(JITCMatrix):
@@ -222,35 +230,27 @@ class _JITC_C(JITCMatrix):
     so R and C of the same logical shape draw different matrices."""
 
     def __matmul__(self, other):
-        r = self._call(other, self.shape[::-1], True, self.corder)
-        if isinstance(r, tuple):
-            mm, other = r
-            return mm(*self.params, self.prob, other, self.seed, shape=self.shape[::-1], transpose=True,
-                      corder=self.corder, backend=self.backend)
-        return r
+        return self._run(other, self.shape[::-1], True, self.corder, self._call(other, None, None, None))
 
     def __rmatmul__(self, other):
-        r = self._call(other, self.shape[::-1], False, not self.corder)
-        if isinstance(r, tuple):
-            mm, other = r
+        if self._call(other, None, None, None):
             if not isinstance(other, BinaryArray):
                 raise NotImplementedError("2-D packed events must be packed along the batch axis")
-            return mm(*self.params, self.prob, other.value.t(), self.seed, shape=self.shape[::-1],
-                      transpose=False, corder=not self.corder, backend=self.backend).t()
-        return r
+            return self._run(other.value.t(), self.shape[::-1], False, not self.corder, True).t()
+        return self._run(other, self.shape[::-1], False, not self.corder, False)
 
 
-def _cls(name, base, mv, mm, n_params, doc):
+def _cls(name, base, prims, n_params, doc):
     def __init__(self, data, *, shape, corder=False, backend=None):
         *params, prob, seed = data
         assert len(params) == n_params, f"{name} expects ({', '.join(['w'] * n_params)}, prob, seed)"
         base.__init__(self, params, prob, seed, shape=shape, corder=corder, backend=backend)
-    return type(name, (base,), {"__init__": __init__, "_mv": staticmethod(mv), "_mm": staticmethod(mm), "__doc__": doc})
+    return type(name, (base,), {"__init__": __init__, "_prims": prims, "__doc__": doc})
 
 
-JITCScalarR = _cls("JITCScalarR", _JITC_R, binary_jitsmv, binary_jitsmm, 1, "JITCScalarR((weight, prob, seed), shape=...)")
-JITCScalarC = _cls("JITCScalarC", _JITC_C, binary_jitsmv, binary_jitsmm, 1, "JITCScalarC((weight, prob, seed), shape=...)")
-JITCNormalR = _cls("JITCNormalR", _JITC_R, binary_jitnmv, binary_jitnmm, 2, "JITCNormalR((loc, scale, prob, seed), shape=...)")
-JITCNormalC = _cls("JITCNormalC", _JITC_C, binary_jitnmv, binary_jitnmm, 2, "JITCNormalC((loc, scale, prob, seed), shape=...)")
-JITCUniformR = _cls("JITCUniformR", _JITC_R, binary_jitumv, binary_jitumm, 2, "JITCUniformR((low, high, prob, seed), shape=...)")
-JITCUniformC = _cls("JITCUniformC", _JITC_C, binary_jitumv, binary_jitumm, 2, "JITCUniformC((low, high, prob, seed), shape=...)")
+JITCScalarR = _cls("JITCScalarR", _JITC_R, (binary_jitsmv_p, binary_jitsmm_p), 1, "JITCScalarR((weight, prob, seed), shape=...)")
+JITCScalarC = _cls("JITCScalarC", _JITC_C, (binary_jitsmv_p, binary_jitsmm_p), 1, "JITCScalarC((weight, prob, seed), shape=...)")
+JITCNormalR = _cls("JITCNormalR", _JITC_R, (binary_jitnmv_p, binary_jitnmm_p), 2, "JITCNormalR((loc, scale, prob, seed), shape=...)")
+JITCNormalC = _cls("JITCNormalC", _JITC_C, (binary_jitnmv_p, binary_jitnmm_p), 2, "JITCNormalC((loc, scale, prob, seed), shape=...)")
+JITCUniformR = _cls("JITCUniformR", _JITC_R, (binary_jitumv_p, binary_jitumm_p), 2, "JITCUniformR((low, high, prob, seed), shape=...)")
+JITCUniformC = _cls("JITCUniformC", _JITC_C, (binary_jitumv_p, binary_jitumm_p), 2, "JITCUniformC((low, high, prob, seed), shape=...)")

@@ -1,0 +1,285 @@
+// xla_ffi.cu -- header-less XLA-FFI handlers over the plain C ABI (see brainevent_b200_xla.h).
+#include "common.cuh"
+#include "../../include/brainevent_b200_xla.h"
+
+#include <cstring>
+#include <string>
+
+namespace {
+
+struct Frame {
+    XLA_FFI_CallFrame* f;
+    std::string err;
+    void* stream = nullptr;
+    void* scratch = nullptr;
+    size_t scratch_bytes = 0;
+
+    explicit Frame(XLA_FFI_CallFrame* frame) : f(frame) {}
+
+    XLA_FFI_Error* fail(int code, const std::string& msg) {
+        XLA_FFI_Error_Create_Args a;
+        a.struct_size = sizeof(a); a.extension_start = nullptr; a.message = msg.c_str(); a.errc = code;
+        return f->api->XLA_FFI_Error_Create(&a);
+    }
+    // metadata handshake: returns true when the frame was a metadata query (handled)
+    bool metadata() {
+        for (XLA_FFI_Extension_Base* e = f->extension_start; e; e = e->next) {
+            if (e->type == 1) {
+                XLA_FFI_Metadata* m = reinterpret_cast<XLA_FFI_Metadata_Extension*>(e)->metadata;
+                m->api_version.major_version = f->api ? f->api->api_version.major_version : 0;
+                m->api_version.minor_version = f->api ? f->api->api_version.minor_version : 1;
+                m->traits = 1u;  // COMMAND_BUFFER_COMPATIBLE: memsets + kernel launches only
+                return true;
+            }
+        }
+        return false;
+    }
+    XLA_FFI_Buffer* arg(int i) const { return i < f->args.size ? (XLA_FFI_Buffer*)f->args.args[i] : nullptr; }
+    XLA_FFI_Buffer* ret(int i) const { return i < f->rets.size ? (XLA_FFI_Buffer*)f->rets.rets[i] : nullptr; }
+    bool attr_i64(const char* name, int64_t* out) const {
+        for (int64_t i = 0; i < f->attrs.size; ++i) {
+            XLA_FFI_ByteSpan* n = f->attrs.names[i];
+            if (n->len == strlen(name) && memcmp(n->ptr, name, n->len) == 0 && f->attrs.types[i] == 3) {
+                XLA_FFI_Scalar* s = (XLA_FFI_Scalar*)f->attrs.attrs[i];
+                switch (s->dtype) {
+                    case BE_XLA_PRED: case BE_XLA_S8: case BE_XLA_U8: *out = *(int8_t*)s->value; return true;
+                    case BE_XLA_S32: case BE_XLA_U32: *out = *(int32_t*)s->value; return true;
+                    case BE_XLA_S64: *out = *(int64_t*)s->value; return true;
+                    default: return false;
+                }
+            }
+        }
+        return false;
+    }
+    XLA_FFI_Error* get_stream() {
+        XLA_FFI_Stream_Get_Args a;
+        a.struct_size = sizeof(a); a.extension_start = nullptr; a.ctx = f->ctx; a.stream = nullptr;
+        XLA_FFI_Error* e = f->api->XLA_FFI_Stream_Get(&a);
+        stream = a.stream;
+        return e;
+    }
+    // zero-initialised workspace from XLA's scratch allocator (stream-ordered re-use is XLA's job)
+    XLA_FFI_Error* get_scratch(int64_t n_src, int64_t n_batch) {
+        scratch_bytes = be_b200_workspace_bytes(n_src, n_batch);
+        XLA_FFI_DeviceMemory_Allocate_Args a;
+        a.struct_size = sizeof(a); a.extension_start = nullptr; a.ctx = f->ctx;
+        a.size = scratch_bytes; a.alignment = 256; a.data = nullptr;
+        XLA_FFI_Error* e = f->api->XLA_FFI_DeviceMemory_Allocate(&a);
+        if (e) return e;
+        scratch = a.data;
+        // only the control words need zeroing: the 256-byte header and the tile-status tail
+        be::Workspace ws = be::ws_carve(scratch, n_src, n_batch);
+        if (cudaMemsetAsync(ws.hdr, 0, sizeof(be::WsHeader), (cudaStream_t)stream) != cudaSuccess ||
+            cudaMemsetAsync(ws.status, 0, (size_t)((char*)scratch + scratch_bytes - (char*)ws.status), (cudaStream_t)stream) != cudaSuccess)
+            return fail(BE_B200_EINTERNAL, "workspace memset failed");
+        return nullptr;
+    }
+    void release() {
+        if (!scratch) return;
+        XLA_FFI_DeviceMemory_Free_Args a;
+        a.struct_size = sizeof(a); a.extension_start = nullptr; a.ctx = f->ctx; a.size = scratch_bytes; a.data = scratch;
+        f->api->XLA_FFI_DeviceMemory_Free(&a);
+        scratch = nullptr;
+    }
+    XLA_FFI_Error* finish(int rc, const char* what) {
+        release();
+        if (rc == BE_B200_OK) return nullptr;
+        return fail(rc, std::string(what) + ": " + be_b200_last_error());
+    }
+};
+
+int wt_of(int xla_dtype) {
+    switch (xla_dtype) {
+        case BE_XLA_F32: return BE_B200_F32;
+        case BE_XLA_F64: return BE_B200_F64;
+        case BE_XLA_F16: return BE_B200_F16;
+        case BE_XLA_BF16: return BE_B200_BF16;
+        default: return -1;
+    }
+}
+int spk_of(int xla_dtype) {
+    switch (xla_dtype) {
+        case BE_XLA_PRED: case BE_XLA_S8: case BE_XLA_U8: return BE_B200_SPK_BOOL;
+        case BE_XLA_F32: return BE_B200_SPK_F32;
+        case BE_XLA_U32: return BE_B200_SPK_PACKED;
+        default: return -1;
+    }
+}
+int64_t numel(const XLA_FFI_Buffer* b) {
+    int64_t n = 1;
+    for (int64_t i = 0; i < b->rank; ++i) n *= b->dims[i];
+    return n;
+}
+
+#define BE_XLA_PROLOGUE(NARGS, NRETS, NAME)                                                          \
+    Frame fr(frame);                                                                                 \
+    if (fr.metadata()) return nullptr;                                                               \
+    if (frame->stage != 3) return nullptr; /* only EXECUTE does work */                              \
+    if (frame->args.size != (NARGS) || frame->rets.size < (NRETS))                                   \
+        return fr.fail(BE_B200_EINVAL, NAME ": wrong number of buffers");                            \
+    if (XLA_FFI_Error* e__ = fr.get_stream()) return e__;
+
+XLA_FFI_Error* csr_common(XLA_FFI_CallFrame* frame, bool matmat, bool indexed, const char* name) {
+    const int na = indexed ? 5 : 4;
+    BE_XLA_PROLOGUE(na, 1, "csr");
+    XLA_FFI_Buffer *w = fr.arg(0), *idx = fr.arg(1), *ptr = fr.arg(2), *perm = indexed ? fr.arg(3) : nullptr,
+                   *ev = fr.arg(na - 1), *out = fr.ret(0);
+    int64_t transpose = 0;
+    fr.attr_i64("transpose", &transpose);
+    const int wt = wt_of(w->dtype), sk = spk_of(ev->dtype);
+    if (wt < 0 || sk < 0) return fr.fail(BE_B200_EUNIMPL, std::string(name) + ": unsupported dtype");
+    if (idx->dtype != BE_XLA_S32) return fr.fail(BE_B200_EINVAL, std::string(name) + ": indices must be int32");
+    const int64_t m = ptr->dims[0] - 1, nse = numel(idx);
+    const int64_t n = matmat ? out->dims[1] : 0;
+    const int64_t k = transpose ? out->dims[0] : (sk == BE_B200_SPK_PACKED && !matmat ? -1 : ev->dims[0]);
+    if (k < 0) return fr.fail(BE_B200_EINVAL, std::string(name) + ": packed events need transpose=1 here");
+    const int64_t n_src = transpose ? m : k;
+    if (XLA_FFI_Error* e = fr.get_scratch(n_src, matmat ? n : 1)) return e;
+    int rc;
+    if (matmat)
+        rc = be_b200_binary_csrmm(w->data, wt, numel(w) == 1, (const int32_t*)idx->data, ptr->data, ptr->dtype == BE_XLA_S64,
+                                  perm ? perm->data : nullptr, perm && perm->dtype == BE_XLA_S64, ev->data, nullptr, sk, m, k,
+                                  nse, n, (int)transpose, out->data, fr.scratch, fr.scratch_bytes, fr.stream);
+    else
+        rc = be_b200_binary_csrmv(w->data, wt, numel(w) == 1, (const int32_t*)idx->data, ptr->data, ptr->dtype == BE_XLA_S64,
+                                  perm ? perm->data : nullptr, perm && perm->dtype == BE_XLA_S64, ev->data, nullptr, sk, m, k,
+                                  nse, (int)transpose, out->data, fr.scratch, fr.scratch_bytes, fr.stream);
+    return fr.finish(rc, name);
+}
+
+XLA_FFI_Error* fcn_common(XLA_FFI_CallFrame* frame, bool matmat, const char* name) {
+    BE_XLA_PROLOGUE(3, 1, "fcn");
+    XLA_FFI_Buffer *w = fr.arg(0), *idx = fr.arg(1), *ev = fr.arg(2), *out = fr.ret(0);
+    int64_t transpose = 0;
+    fr.attr_i64("transpose", &transpose);
+    const int wt = wt_of(w->dtype), sk = spk_of(ev->dtype);
+    if (wt < 0 || sk < 0) return fr.fail(BE_B200_EUNIMPL, std::string(name) + ": unsupported dtype");
+    if (idx->dtype != BE_XLA_S32 || idx->rank != 2) return fr.fail(BE_B200_EINVAL, std::string(name) + ": indices must be int32 [n_rows, n_conn]");
+    const int64_t n_rows = idx->dims[0], n_conn = idx->dims[1], n_out = out->dims[0];
+    const int64_t n = matmat ? out->dims[1] : 0;
+    int64_t n_src = transpose ? n_rows : ev->dims[0];
+    if (!transpose && sk == BE_B200_SPK_PACKED && !matmat) {
+        if (!fr.attr_i64("n_src", &n_src)) return fr.fail(BE_B200_EINVAL, std::string(name) + ": packed events need attr n_src");
+    }
+    if (XLA_FFI_Error* e = fr.get_scratch(n_src, matmat ? n : 1)) return e;
+    int rc;
+    if (matmat)
+        rc = be_b200_binary_fcnmm(w->data, wt, numel(w) == 1, (const int32_t*)idx->data, n_rows, n_conn, ev->data, nullptr, sk,
+                                  n_src, n_out, n, (int)transpose, out->data, fr.scratch, fr.scratch_bytes, fr.stream);
+    else
+        rc = be_b200_binary_fcnmv(w->data, wt, numel(w) == 1, (const int32_t*)idx->data, n_rows, n_conn, ev->data, nullptr, sk,
+                                  n_src, n_out, (int)transpose, out->data, fr.scratch, fr.scratch_bytes, fr.stream);
+    return fr.finish(rc, name);
+}
+
+XLA_FFI_Error* jit_common(XLA_FFI_CallFrame* frame, bool matmat, const char* name) {
+    Frame fr(frame);
+    if (fr.metadata()) return nullptr;
+    if (frame->stage != 3) return nullptr;
+    int64_t kind = 0, corder = 1, chunk = 0;
+    fr.attr_i64("kind", &kind);
+    fr.attr_i64("corder", &corder);
+    if (!fr.attr_i64("chunk_size", &chunk)) return fr.fail(BE_B200_EINVAL, std::string(name) + ": attr chunk_size is required");
+    const int np = kind == BE_B200_JIT_SCALAR ? 1 : 2;
+    if (frame->args.size != np + 3 || frame->rets.size < 1) return fr.fail(BE_B200_EINVAL, std::string(name) + ": wrong number of buffers");
+    if (XLA_FFI_Error* e = fr.get_stream()) return e;
+    XLA_FFI_Buffer *p0 = fr.arg(0), *p1 = np == 2 ? fr.arg(1) : nullptr, *clen = fr.arg(np), *seed = fr.arg(np + 1),
+                   *ev = fr.arg(np + 2), *out = fr.ret(0);
+    const int wt = wt_of(p0->dtype), sk = spk_of(ev->dtype);
+    if (wt < 0 || sk < 0) return fr.fail(BE_B200_EUNIMPL, std::string(name) + ": unsupported dtype");
+    const int64_t out_len = out->dims[0];
+    int64_t vec_len = ev->dims[0];
+    if (sk == BE_B200_SPK_PACKED && !matmat) {
+        if (!fr.attr_i64("vector_size", &vec_len)) return fr.fail(BE_B200_EINVAL, std::string(name) + ": packed events need attr vector_size");
+    }
+    const int64_t n = matmat ? out->dims[1] : 1;
+    if (XLA_FFI_Error* e = fr.get_scratch(vec_len, n)) return e;
+    int rc;
+    if (matmat)
+        rc = be_b200_binary_jitmm((int)kind, p0->data, p1 ? p1->data : nullptr, wt, (const int32_t*)clen->data,
+                                  (const int32_t*)seed->data, ev->data, nullptr, sk, vec_len, out_len, n, chunk, (int)corder,
+                                  out->data, fr.scratch, fr.scratch_bytes, fr.stream);
+    else
+        rc = be_b200_binary_jitmv((int)kind, p0->data, p1 ? p1->data : nullptr, wt, (const int32_t*)clen->data,
+                                  (const int32_t*)seed->data, ev->data, nullptr, sk, vec_len, out_len, chunk, (int)corder,
+                                  0, -1, 0, -1, out->data, fr.scratch, fr.scratch_bytes, fr.stream);
+    return fr.finish(rc, name);
+}
+
+XLA_FFI_Error* dense_common(XLA_FFI_CallFrame* frame, bool matmat, const char* name) {
+    BE_XLA_PROLOGUE(2, 1, "dense");
+    XLA_FFI_Buffer *w = fr.arg(0), *ev = fr.arg(1), *out = fr.ret(0);
+    int64_t transpose = 0;
+    fr.attr_i64("transpose", &transpose);
+    const int wt = wt_of(w->dtype), sk = spk_of(ev->dtype);
+    if (wt < 0 || sk < 0 || w->rank != 2) return fr.fail(BE_B200_EUNIMPL, std::string(name) + ": unsupported dtype/rank");
+    const int64_t rows = w->dims[0], cols = w->dims[1], n_src = transpose ? rows : cols;
+    const int64_t n = matmat ? out->dims[1] : 1;
+    if (XLA_FFI_Error* e = fr.get_scratch(n_src, n)) return e;
+    int rc;
+    if (matmat)
+        rc = be_b200_binary_densemm(w->data, wt, rows, cols, ev->data, nullptr, sk, n, (int)transpose, out->data, fr.scratch,
+                                    fr.scratch_bytes, fr.stream);
+    else
+        rc = be_b200_binary_densemv(w->data, wt, rows, cols, ev->data, nullptr, sk, (int)transpose, out->data, fr.scratch,
+                                    fr.scratch_bytes, fr.stream);
+    return fr.finish(rc, name);
+}
+
+}  // namespace
+
+extern "C" {
+
+XLA_FFI_Error* be_b200_xla_binary_csrmv(XLA_FFI_CallFrame* frame) { return csr_common(frame, false, false, "be_b200_xla_binary_csrmv"); }
+XLA_FFI_Error* be_b200_xla_binary_csrmm(XLA_FFI_CallFrame* frame) { return csr_common(frame, true, false, "be_b200_xla_binary_csrmm"); }
+XLA_FFI_Error* be_b200_xla_binary_csrmv_indexed(XLA_FFI_CallFrame* frame) { return csr_common(frame, false, true, "be_b200_xla_binary_csrmv_indexed"); }
+XLA_FFI_Error* be_b200_xla_binary_csrmm_indexed(XLA_FFI_CallFrame* frame) { return csr_common(frame, true, true, "be_b200_xla_binary_csrmm_indexed"); }
+XLA_FFI_Error* be_b200_xla_binary_fcnmv(XLA_FFI_CallFrame* frame) { return fcn_common(frame, false, "be_b200_xla_binary_fcnmv"); }
+XLA_FFI_Error* be_b200_xla_binary_fcnmm(XLA_FFI_CallFrame* frame) { return fcn_common(frame, true, "be_b200_xla_binary_fcnmm"); }
+XLA_FFI_Error* be_b200_xla_binary_jitmv(XLA_FFI_CallFrame* frame) { return jit_common(frame, false, "be_b200_xla_binary_jitmv"); }
+XLA_FFI_Error* be_b200_xla_binary_jitmm(XLA_FFI_CallFrame* frame) { return jit_common(frame, true, "be_b200_xla_binary_jitmm"); }
+XLA_FFI_Error* be_b200_xla_binary_densemv(XLA_FFI_CallFrame* frame) { return dense_common(frame, false, "be_b200_xla_binary_densemv"); }
+XLA_FFI_Error* be_b200_xla_binary_densemm(XLA_FFI_CallFrame* frame) { return dense_common(frame, true, "be_b200_xla_binary_densemm"); }
+
+XLA_FFI_Error* be_b200_xla_compact_1d(XLA_FFI_CallFrame* frame) {
+    BE_XLA_PROLOGUE(1, 2, "compact_1d");
+    XLA_FFI_Buffer *ev = fr.arg(0), *ids = fr.ret(0), *na = fr.ret(1);
+    const int sk = spk_of(ev->dtype);
+    if (sk < 0) return fr.fail(BE_B200_EUNIMPL, "compact_1d: unsupported spike dtype");
+    const int64_t n = ids->dims[0];
+    if (XLA_FFI_Error* e = fr.get_scratch(n, 1)) return e;
+    return fr.finish(be_b200_compact_1d(ev->data, sk, n, 1, (int32_t*)ids->data, (int32_t*)na->data, nullptr, fr.scratch,
+                                        fr.scratch_bytes, fr.stream), "be_b200_xla_compact_1d");
+}
+
+XLA_FFI_Error* be_b200_xla_compact_2d(XLA_FFI_CallFrame* frame) {
+    BE_XLA_PROLOGUE(1, 3, "compact_2d");
+    XLA_FFI_Buffer *ev = fr.arg(0), *packed = fr.ret(0), *ids = fr.ret(1), *na = fr.ret(2);
+    const int sk = spk_of(ev->dtype);
+    if (sk < 0 || ev->rank != 2) return fr.fail(BE_B200_EUNIMPL, "compact_2d: unsupported spike dtype/rank");
+    const int64_t n = ev->dims[0], b = ev->dims[1];
+    if (XLA_FFI_Error* e = fr.get_scratch(n, b)) return e;
+    return fr.finish(be_b200_compact_2d(ev->data, sk, n, b, 1, (uint32_t*)packed->data, (int32_t*)ids->data, (int32_t*)na->data,
+                                        fr.scratch, fr.scratch_bytes, fr.stream), "be_b200_xla_compact_2d");
+}
+
+XLA_FFI_Error* be_b200_xla_compact_2d_only(XLA_FFI_CallFrame* frame) {
+    BE_XLA_PROLOGUE(1, 2, "compact_2d_only");
+    XLA_FFI_Buffer *ev = fr.arg(0), *ids = fr.ret(0), *na = fr.ret(1);
+    const int sk = spk_of(ev->dtype);
+    if (sk < 0 || ev->rank != 2) return fr.fail(BE_B200_EUNIMPL, "compact_2d_only: unsupported spike dtype/rank");
+    const int64_t n = ev->dims[0], b = ev->dims[1];
+    if (XLA_FFI_Error* e = fr.get_scratch(n, b)) return e;
+    return fr.finish(be_b200_compact_2d(ev->data, sk, n, b, 1, nullptr, (int32_t*)ids->data, (int32_t*)na->data, fr.scratch,
+                                        fr.scratch_bytes, fr.stream), "be_b200_xla_compact_2d_only");
+}
+
+XLA_FFI_Error* be_b200_xla_bitpack_1d(XLA_FFI_CallFrame* frame) {
+    BE_XLA_PROLOGUE(1, 1, "bitpack_1d");
+    XLA_FFI_Buffer *ev = fr.arg(0), *packed = fr.ret(0);
+    const int sk = spk_of(ev->dtype);
+    if (sk < 0) return fr.fail(BE_B200_EUNIMPL, "bitpack_1d: unsupported spike dtype");
+    return fr.finish(be_b200_bitpack_1d(ev->data, sk, ev->dims[0], 0, (uint32_t*)packed->data, fr.stream), "be_b200_xla_bitpack_1d");
+}
+
+}  // extern "C"

@@ -1,0 +1,81 @@
+"""CPU-side checks of the drop-in boundary: the shared library loads, exports every symbol that
+include/*.h declares, and the host mirror fails loudly without a GPU (no CPU fallback)."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared():
+    names = set()
+    for h in ("brainevent_b200.h", "brainevent_b200_xla.h"):
+        src = open(os.path.join(ROOT, "include", h)).read()
+        src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+        names |= set(re.findall(r"\b(be_b200_\w+)\s*\(", src))
+    return names
+
+
+def test_library_exports_every_declared_symbol():
+    from brainevent_b200 import _lib
+    L = ctypes.CDLL(_lib.LIB_PATH)
+    declared = _declared()
+    assert len(declared) >= 35
+    missing = [n for n in sorted(declared) if not hasattr(L, n)]
+    assert not missing, missing
+    # and the ctypes table binds exactly the plain-C part
+    plain = {n for n in declared if not n.startswith("be_b200_xla_")}
+    assert plain == set(_lib.EXPORTED_SYMBOLS), plain ^ set(_lib.EXPORTED_SYMBOLS)
+
+
+def test_abi_version_and_workspace_query():
+    from brainevent_b200 import _lib
+    L = _lib.lib()
+    assert L.be_b200_abi_version() == 1
+    a = L.be_b200_workspace_bytes(1_000_000, 1)
+    b = L.be_b200_workspace_bytes(1_000_000, 64)
+    assert a >= 4 * 1_000_000 and b >= a and a % 256 == 0
+
+
+def test_no_cpu_fallback():
+    import brainevent_b200 as be
+    w = torch.ones(3)
+    idx = torch.tensor([0, 2, 1], dtype=torch.int32)
+    ptr = torch.tensor([0, 2, 3], dtype=torch.int32)
+    with pytest.raises(be.KernelExecutionError):
+        be.binary_csrmv(w, idx, ptr, torch.tensor([True, False, True]), shape=(2, 3))
+    with pytest.raises(be.KernelExecutionError):
+        be.BinaryArray(torch.tensor([True, False])) @ be.CSR((w, idx, ptr), shape=(2, 3))
+
+
+def test_primitive_registry_mirrors_reference_names():
+    import brainevent_b200 as be
+    names = set(be.get_all_primitive_names())
+    for n in ("binary_csrmv", "binary_csrmm", "binary_csrmv_indexed", "binary_csrmm_indexed", "binary_fcnmv",
+              "binary_fcnmm", "binary_jitsmv", "binary_jitsmm", "binary_jitnmv", "binary_jitnmm", "binary_jitumv",
+              "binary_jitumm", "binary_densemv", "binary_densemm", "binary_1d_array_index", "binary_2d_array_index",
+              "binary_2d_compact_only"):
+        assert n in names
+        p = be.get_registry()[n]
+        assert p.available_backends("gpu") == ["b200"] and p.get_default("gpu") == "b200"
+    assert set(be.get_primitives_by_tags("csr", "binary")) >= {"binary_csrmv", "binary_csrmm"}
+    with pytest.raises(be.KernelNotAvailableError):
+        be.binary_csrmv_p._resolve("gpu", "numba")
+    with pytest.raises(ValueError):
+        be.config.set_backend("gpu", "pallas")
+
+
+def test_shape_assertions_match_reference_behaviour():
+    import brainevent_b200 as be
+    from brainevent_b200 import _csr
+    w = torch.ones(3)
+    idx = torch.tensor([0, 2, 1], dtype=torch.int32)
+    ptr = torch.tensor([0, 2, 3], dtype=torch.int32)
+    # wrong vector length -> assertion before any launch (ref: _csr/binary.py:827-987 asserts)
+    with pytest.raises((AssertionError, be.KernelExecutionError)):
+        be.binary_csrmv(w, idx, ptr, torch.tensor([True, False]), shape=(2, 3))
+    assert _csr._prep_structure  # host logic is importable without CUDA

@@ -1,0 +1,53 @@
+#!/usr/bin/env python
+"""Summarise gpurun_out/<tag>_launches.csv and <tag>_prof.ncu-rep into profiles/<tag>_*.txt."""
+import collections
+import csv
+import os
+import subprocess
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+tag = sys.argv[1]
+out_dir = os.path.join(ROOT, "profiles")
+src = os.path.join(ROOT, "gpurun_out")
+
+rows = [r for r in csv.reader(open(f"{src}/{tag}_launches.csv")) if len(r) > 10]
+hdr = rows[0]
+ki, vi = hdr.index("Kernel Name"), hdr.index("Metric Value")
+agg = collections.OrderedDict()
+for r in rows[1:]:
+    try:
+        agg.setdefault(r[ki], []).append(float(r[vi].replace(",", "")))
+    except ValueError:
+        pass
+tot = sum(sum(v) for v in agg.values())
+with open(f"{out_dir}/{tag}_launches.txt", "w") as f:
+    f.write("# ncu --metrics gpu__time_duration.sum --clock-control none (cold-cache, serialised: compare SHARES)\n")
+    f.write(f"# source: gpurun_out/{tag}_launches.csv ({sum(len(v) for v in agg.values())} launches)\n")
+    for k, v in sorted(agg.items(), key=lambda kv: -sum(kv[1])):
+        f.write(f"{sum(v) / tot:6.1%}  n={len(v):4d}  avg={sum(v) / len(v) / 1e3:9.2f} us  {k[:110]}\n")
+print(open(f"{out_dir}/{tag}_launches.txt").read())
+
+raw = subprocess.run(["ncu", "-i", f"{src}/{tag}_prof.ncu-rep", "--page", "raw", "--csv"],
+                     capture_output=True, text=True).stdout
+rows = list(csv.reader(raw.splitlines()))
+hdr, units, data = rows[0], rows[1], rows[2:]
+want = ["Kernel Name", "launch__grid_size", "launch__block_size", "launch__registers_per_thread",
+        "gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum",
+        "dram__throughput.avg.pct_of_peak_sustained_elapsed",
+        "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed",
+        "lts__throughput.avg.pct_of_peak_sustained_elapsed", "l1tex__throughput.avg.pct_of_peak_sustained_elapsed",
+        "sm__throughput.avg.pct_of_peak_sustained_elapsed", "sm__warps_active.avg.pct_of_peak_sustained_active",
+        "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active",
+        "l1tex__t_requests_pipe_lsu_mem_global_op_red.sum", "l1tex__t_sectors_pipe_lsu_mem_global_op_ld.sum",
+        "lts__t_sectors_op_red.sum", "lts__t_sectors_op_atom.sum", "lts__t_sectors_srcunit_tex_op_read.sum",
+        "smsp__inst_executed.sum", "smsp__issue_active.avg.pct_of_peak_sustained_active",
+        "smsp__average_warps_issue_stalled_lg_throttle_per_issue_active.ratio",
+        "smsp__average_warps_issue_stalled_long_scoreboard_per_issue_active.ratio"]
+with open(f"{out_dir}/{tag}_full.txt", "w") as f:
+    f.write(f"# ncu --set full --clock-control none --import-source on; source gpurun_out/{tag}_prof.ncu-rep\n")
+    for w in want:
+        if w in hdr:
+            i = hdr.index(w)
+            f.write(f"{w} [{units[i]}]: " + " | ".join(r[i][:90] for r in data) + "\n")
+print(open(f"{out_dir}/{tag}_full.txt").read())
