@@ -385,7 +385,7 @@ def run_reference(args):
             "cpu_baseline": {"value": value, "unit": "events/s", "cores": 1, "kind": "port", "sample": sample},
             "e2e": {"value": value, "unit": "events/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
-    print(json.dumps(line))
+    emit(line)
 
 
 # ------------------------------------------------------------------------------------------------
@@ -402,7 +402,26 @@ def measure_workload(torch, dist, L, wl, K, W, T, world, peak, peak_src, sampler
             "events_per_step": total_events}
 
 
+_REAL_STDOUT = None
+
+
+def _claim_stdout():
+    """Keep fd 1 for the single JSON line: libraries that print to stdout (NCCL's version banner,
+    torchrun notices) are redirected to stderr."""
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+
+
+def emit(line):
+    out = _REAL_STDOUT or sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
+
+
 def main():
+    _claim_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
@@ -549,7 +568,7 @@ def main():
             "events_per_step": res["events_per_step"]}
     if others:
         line["other_workloads"] = others
-    print(json.dumps(line))
+    emit(line)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
