@@ -55,7 +55,9 @@ struct WsHeader {
     unsigned int ticket;   // dynamic tile counter (decoupled look-back)
     unsigned int done;     // tiles finished (self-reset trigger)
     unsigned int n_events; // total set bits (2-D: sum of popcounts), for rate-based selection
-    int pad[60];
+    unsigned int ev_accum; // running event total of the compaction in flight
+    unsigned int cursor;   // slot cursor of the unordered (block-atomic) compaction
+    int pad[58];
 };
 static_assert(sizeof(WsHeader) == 256, "header is 256 B");
 
@@ -212,9 +214,14 @@ struct ProfileScope {
 
 // events.cu: normalise any supported event encoding into `Events` (packing / compaction as
 // needed by the consumer), enqueued on `stream`.
+// `zero_ptr/zero_bytes` (optional): an output region the caller needs cleared before it scatters;
+// it is zeroed by the compaction kernel itself when one is launched (no separate memset node),
+// otherwise by cudaMemsetAsync.  `ordered_ids=false` lets the id list be block-ordered only
+// (one atomic per tile instead of the look-back chain) -- fine for scatter consumers.
 int prepare_events_1d(const void* spikes, const void* aux, int spk_kind, int64_t n,
                       bool need_ids, bool need_packed, void* workspace, size_t workspace_bytes,
-                      cudaStream_t stream, Events* ev);
+                      cudaStream_t stream, Events* ev, void* zero_ptr = nullptr,
+                      size_t zero_bytes = 0, bool ordered_ids = true);
 int prepare_events_2d(const void* spikes, const void* aux, int spk_kind, int64_t n, int64_t batch,
                       bool need_ids, void* workspace, size_t workspace_bytes, cudaStream_t stream,
                       Events* ev);

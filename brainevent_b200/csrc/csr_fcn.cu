@@ -428,11 +428,13 @@ static int run_conn(const Rows& rows, const ConnArgs& c, const void* spikes, con
     Events ev;
     int rc;
     const bool mm = n_batch > 0;
-    if (mm) rc = prepare_events_2d(spikes, aux, spk_kind, n_src, n_batch, scatter, workspace, workspace_bytes, s, &ev);
-    else rc = prepare_events_1d(spikes, aux, spk_kind, n_src, scatter, !scatter, workspace, workspace_bytes, s, &ev);
-    if (rc) return rc;
     const int64_t out_elems = n_out * (mm ? n_batch : 1);
-    if (scatter && out_elems > 0) BE_CUDA(cudaMemsetAsync(out, 0, (size_t)out_elems * sizeof(T), s));
+    if (mm) rc = prepare_events_2d(spikes, aux, spk_kind, n_src, n_batch, scatter, workspace, workspace_bytes, s, &ev);
+    else rc = prepare_events_1d(spikes, aux, spk_kind, n_src, scatter, !scatter, workspace, workspace_bytes, s, &ev,
+                                scatter ? (void*)out : nullptr, scatter ? (size_t)out_elems * sizeof(T) : 0,
+                                /*ordered_ids=*/false);   // the output clear rides on the compaction kernel
+    if (rc) return rc;
+    if (mm && scatter && out_elems > 0) BE_CUDA(cudaMemsetAsync(out, 0, (size_t)out_elems * sizeof(T), s));
     if (out_elems == 0) return BE_B200_OK;
     if (n_src == 0) {
         if (!scatter) BE_CUDA(cudaMemsetAsync(out, 0, (size_t)out_elems * sizeof(T), s));

@@ -70,7 +70,8 @@ __device__ __forceinline__ void st_status(unsigned long long* p, unsigned long l
 // After the call, *tile_total_incl holds the inclusive prefix up to and including this tile.
 __device__ __forceinline__ unsigned int scan_and_lookback(unsigned int count, unsigned int tile,
                                                           unsigned long long* status,
-                                                          unsigned int* tile_total_incl) {
+                                                          unsigned int* tile_total_incl,
+                                                          unsigned int* cursor = nullptr) {
     __shared__ unsigned int s_warp[kCompactThreads / 32];
     __shared__ unsigned int s_excl;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -88,6 +89,13 @@ __device__ __forceinline__ unsigned int scan_and_lookback(unsigned int count, un
         unsigned int t = s_warp[w];
         if (w < warp) warp_base += t;
         block_total += t;
+    }
+    if (cursor != nullptr) {
+        // unordered variant: reserve this tile's slots with one atomic, no look-back chain
+        if (threadIdx.x == 0) s_excl = atomicAdd(cursor, block_total);
+        __syncthreads();
+        *tile_total_incl = s_excl + block_total;
+        return s_excl + warp_base + (incl - count);
     }
     if (warp == 0) {
         unsigned int excl = 0;
@@ -126,21 +134,28 @@ __device__ __forceinline__ unsigned int scan_and_lookback(unsigned int count, un
 // (ticket, done, tile status) to zero and publishes the event total, so the next call needs no
 // memset.
 __device__ __forceinline__ void finish_tile(WsHeader* hdr, unsigned long long* status,
-                                            unsigned int n_tiles, unsigned int block_events) {
+                                            unsigned int n_tiles, unsigned int block_events,
+                                            bool unordered = false, int* n_active_out = nullptr) {
     __shared__ bool s_last;
     __syncthreads();
     if (threadIdx.x == 0) {
-        if (block_events) atomicAdd((unsigned int*)&hdr->pad[0], block_events);
+        if (block_events) atomicAdd(&hdr->ev_accum, block_events);
         __threadfence();
         unsigned int prev = atomicAdd(&hdr->done, 1u);
         s_last = (prev == n_tiles - 1);
     }
     __syncthreads();
     if (s_last) {
-        for (unsigned int i = threadIdx.x; i < n_tiles; i += blockDim.x) status[i] = 0ull;
+        if (!unordered)
+            for (unsigned int i = threadIdx.x; i < n_tiles; i += blockDim.x) status[i] = 0ull;
         if (threadIdx.x == 0) {
             __threadfence();
-            hdr->n_events = (unsigned int)atomicExch((unsigned int*)&hdr->pad[0], 0u);
+            if (unordered) {
+                const int total = (int)atomicExch(&hdr->cursor, 0u);   // every tile has reserved by now
+                hdr->n_active = total;
+                if (n_active_out != nullptr) *n_active_out = total;
+            }
+            hdr->n_events = atomicExch(&hdr->ev_accum, 0u);
             hdr->ticket = 0u;
             hdr->done = 0u;
         }
@@ -216,15 +231,23 @@ __global__ void __launch_bounds__(256) bitpack_1d_kernel(const void* __restrict_
 // ------------------------------------------------------------------------------------------
 // 1-D: ordered compaction (+ optional packed output)
 // ------------------------------------------------------------------------------------------
-template <int KIND, bool NONZERO, bool ALIGNED>
+template <int KIND, bool NONZERO, bool ALIGNED, bool ORDERED>
 __global__ void __launch_bounds__(kCompactThreads) compact_1d_kernel(
     const void* __restrict__ spikes, int64_t n, unsigned int n_tiles, WsHeader* hdr,
     unsigned long long* status, int32_t* __restrict__ active_ids, int* __restrict__ n_active_out,
-    uint32_t* __restrict__ packed) {
+    uint32_t* __restrict__ packed, int4* __restrict__ zero_ptr, size_t zero_vec16) {
     __shared__ unsigned int s_tile;
-    if (threadIdx.x == 0) s_tile = atomicAdd(&hdr->ticket, 1u);
-    __syncthreads();
-    const unsigned int tile = s_tile;
+    if (ORDERED) {
+        if (threadIdx.x == 0) s_tile = atomicAdd(&hdr->ticket, 1u);
+        __syncthreads();
+    }
+    const unsigned int tile = ORDERED ? s_tile : blockIdx.x;
+    if (zero_ptr != nullptr) {
+        // fused clear of the consumer's output: this block's slice, 16-byte stores
+        const size_t per = (zero_vec16 + n_tiles - 1) / n_tiles;
+        const size_t z0 = (size_t)blockIdx.x * per, z1 = min(z0 + per, zero_vec16);
+        for (size_t z = z0 + threadIdx.x; z < z1; z += kCompactThreads) zero_ptr[z] = make_int4(0, 0, 0, 0);
+    }
     const int64_t base = (int64_t)tile * kCompactTile + (int64_t)threadIdx.x * kCompactElemsPerThread;
     unsigned int m = load_mask16<KIND, NONZERO, ALIGNED>(spikes, base, n);
     if (packed != nullptr) {
@@ -232,17 +255,17 @@ __global__ void __launch_bounds__(kCompactThreads) compact_1d_kernel(
         if ((threadIdx.x & 1) == 0 && base < n) packed[base >> 5] = m | (hi << 16);
     }
     unsigned int total_incl;
-    unsigned int pos = scan_and_lookback(__popc(m), tile, status, &total_incl);
+    unsigned int pos = scan_and_lookback(__popc(m), tile, status, &total_incl, ORDERED ? nullptr : &hdr->cursor);
     while (m) {
         int b = __ffs(m) - 1;
         m &= m - 1;
         active_ids[pos++] = (int32_t)(base + b);
     }
-    if (tile == n_tiles - 1 && threadIdx.x == 0) {
+    if (ORDERED && tile == n_tiles - 1 && threadIdx.x == 0) {
         hdr->n_active = (int)total_incl;
         if (n_active_out != nullptr) *n_active_out = (int)total_incl;
     }
-    finish_tile(hdr, status, n_tiles, 0u);
+    finish_tile(hdr, status, n_tiles, 0u, !ORDERED, n_active_out);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -341,12 +364,19 @@ static int launch_bitpack(const void* spikes, int64_t n, bool nonzero, uint32_t*
 
 template <int KIND>
 static int launch_compact_1d(const void* spikes, int64_t n, bool nonzero, const Workspace& ws,
-                             int32_t* ids, int* n_active_out, uint32_t* packed, cudaStream_t s) {
+                             int32_t* ids, int* n_active_out, uint32_t* packed, cudaStream_t s,
+                             void* zero_ptr = nullptr, size_t zero_bytes = 0, bool ordered = true) {
     unsigned int n_tiles = (unsigned int)ceil_div(n, kCompactTile);
     bool al = aligned16(spikes);
+    int4* zp = (int4*)zero_ptr;
+    const size_t zv = zero_bytes / 16;
 #define BE_C1(NZ, AL)                                                                        \
-    compact_1d_kernel<KIND, NZ, AL><<<n_tiles, kCompactThreads, 0, s>>>(                     \
-        spikes, n, n_tiles, ws.hdr, ws.status, ids, n_active_out, packed)
+    do {                                                                                     \
+        if (ordered) compact_1d_kernel<KIND, NZ, AL, true><<<n_tiles, kCompactThreads, 0, s>>>(  \
+            spikes, n, n_tiles, ws.hdr, ws.status, ids, n_active_out, packed, zp, zv);       \
+        else compact_1d_kernel<KIND, NZ, AL, false><<<n_tiles, kCompactThreads, 0, s>>>(     \
+            spikes, n, n_tiles, ws.hdr, ws.status, ids, n_active_out, packed, zp, zv);       \
+    } while (0)
     if (nonzero) { if (al) BE_C1(true, true); else BE_C1(true, false); }
     else { if (al) BE_C1(false, true); else BE_C1(false, false); }
 #undef BE_C1
@@ -368,17 +398,26 @@ static int zero_n_active(int* dst, cudaStream_t s) {
 }
 
 int compact_1d_any(const void* spikes, int spk_kind, int64_t n, bool nonzero, const Workspace& ws,
-                   int32_t* ids, int* n_active_out, uint32_t* packed, cudaStream_t s) {
+                   int32_t* ids, int* n_active_out, uint32_t* packed, cudaStream_t s,
+                   void* zero_ptr = nullptr, size_t zero_bytes = 0, bool ordered = true) {
+    // the fused clear needs a 16-byte aligned region; the (<16 B) tail is cleared separately
+    if (zero_ptr != nullptr && ((uintptr_t)zero_ptr & 15u) != 0) {
+        BE_CUDA(cudaMemsetAsync(zero_ptr, 0, zero_bytes, s));
+        zero_ptr = nullptr;
+    } else if (zero_ptr != nullptr && (zero_bytes & 15u) != 0) {
+        BE_CUDA(cudaMemsetAsync((char*)zero_ptr + (zero_bytes & ~(size_t)15), 0, zero_bytes & 15u, s));
+    }
     if (n == 0) {
+        if (zero_ptr != nullptr && zero_bytes >= 16) BE_CUDA(cudaMemsetAsync(zero_ptr, 0, zero_bytes, s));
         int rc = zero_n_active(&ws.hdr->n_active, s);
         if (rc) return rc;
         if (n_active_out) return zero_n_active(n_active_out, s);
         return BE_B200_OK;
     }
     switch (spk_kind) {
-        case BE_B200_SPK_BOOL: return launch_compact_1d<BE_B200_SPK_BOOL>(spikes, n, nonzero, ws, ids, n_active_out, packed, s);
-        case BE_B200_SPK_F32: return launch_compact_1d<BE_B200_SPK_F32>(spikes, n, nonzero, ws, ids, n_active_out, packed, s);
-        case BE_B200_SPK_PACKED: return launch_compact_1d<BE_B200_SPK_PACKED>(spikes, n, nonzero, ws, ids, n_active_out, nullptr, s);
+        case BE_B200_SPK_BOOL: return launch_compact_1d<BE_B200_SPK_BOOL>(spikes, n, nonzero, ws, ids, n_active_out, packed, s, zero_ptr, zero_bytes, ordered);
+        case BE_B200_SPK_F32: return launch_compact_1d<BE_B200_SPK_F32>(spikes, n, nonzero, ws, ids, n_active_out, packed, s, zero_ptr, zero_bytes, ordered);
+        case BE_B200_SPK_PACKED: return launch_compact_1d<BE_B200_SPK_PACKED>(spikes, n, nonzero, ws, ids, n_active_out, nullptr, s, zero_ptr, zero_bytes, ordered);
         default: set_error("compact_1d: unsupported event kind %d", spk_kind); return BE_B200_EINVAL;
     }
 }
@@ -411,11 +450,13 @@ int compact_2d_any(const void* spikes, int spk_kind, int64_t n, int64_t batch, b
 
 int prepare_events_1d(const void* spikes, const void* aux, int spk_kind, int64_t n, bool need_ids,
                       bool need_packed, void* workspace, size_t workspace_bytes, cudaStream_t s,
-                      Events* ev) {
+                      Events* ev, void* zero_ptr, size_t zero_bytes, bool ordered_ids) {
     int rc = check_ws(workspace, workspace_bytes, n, 1);
     if (rc) return rc;
     Workspace ws = ws_carve(workspace, n, 1);
     ev->words_per_row = 1;
+    const bool compacts = need_ids && spk_kind != BE_B200_SPK_COMPACT;
+    if (!compacts && zero_ptr != nullptr && zero_bytes > 0) BE_CUDA(cudaMemsetAsync(zero_ptr, 0, zero_bytes, s));
     if (spk_kind == BE_B200_SPK_COMPACT) {
         BE_REQUIRE(aux != nullptr, "COMPACT events need aux = active_ids[n] ++ n_active");
         BE_REQUIRE(!need_packed || spikes != nullptr, "COMPACT events: packed words required here");
@@ -429,13 +470,13 @@ int prepare_events_1d(const void* spikes, const void* aux, int spk_kind, int64_t
     ev->n_active = &ws.hdr->n_active;
     if (spk_kind == BE_B200_SPK_PACKED) {
         ev->packed = (const uint32_t*)spikes;
-        if (need_ids) return compact_1d_any(spikes, spk_kind, n, false, ws, ws.active_ids, nullptr, nullptr, s);
+        if (need_ids) return compact_1d_any(spikes, spk_kind, n, false, ws, ws.active_ids, nullptr, nullptr, s, zero_ptr, zero_bytes, ordered_ids);
         return BE_B200_OK;
     }
     ev->packed = ws.packed;
     if (need_ids)
         return compact_1d_any(spikes, spk_kind, n, false, ws, ws.active_ids, nullptr,
-                              need_packed ? ws.packed : nullptr, s);
+                              need_packed ? ws.packed : nullptr, s, zero_ptr, zero_bytes, ordered_ids);
     if (need_packed && n > 0) {
         if (spk_kind == BE_B200_SPK_BOOL) return launch_bitpack<BE_B200_SPK_BOOL>(spikes, n, false, ws.packed, s);
         if (spk_kind == BE_B200_SPK_F32) return launch_bitpack<BE_B200_SPK_F32>(spikes, n, false, ws.packed, s);

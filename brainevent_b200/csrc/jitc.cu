@@ -378,9 +378,7 @@ static int run_jit_mv(const JitParams& jp, const Events& ev, int64_t vec_len, in
         BE_LAUNCH_CHECK("jit_mv_gather_kernel");
     } else {
         const int64_t own = col_end - col_begin;
-        if (own <= 0) return BE_B200_OK;
-        BE_CUDA(cudaMemsetAsync(out, 0, (size_t)own * sizeof(T), s));
-        if (vec_len == 0) return BE_B200_OK;
+        if (own <= 0 || vec_len == 0) return BE_B200_OK;   // output already cleared with the compaction
         const int64_t n_chunks = ceil_div(out_len, chunk_size);
         int blocks = (int)std::min<int64_t>(ceil_div(std::max<int64_t>(vec_len * n_chunks, 1), 8), (int64_t)kNumSM * 8);
         {
@@ -452,7 +450,11 @@ extern "C" int be_b200_binary_jitmv(int kind, const void* p0, const void* p1, in
     BE_REQUIRE(col_begin >= 0 && col_begin <= col_end && col_end <= out_len, "jitmv: column window out of range");
     BE_REQUIRE(!corder || (col_begin == 0 && col_end == out_len), "jitmv: column window only applies to corder=0");
     Events ev;
-    int rc = prepare_events_1d(spikes, aux, spk_kind, vec_len, !corder, corder != 0, workspace, workspace_bytes, s, &ev);
+    static const size_t kWt[4] = {4, 8, 2, 2};
+    BE_REQUIRE(w_dtype >= 0 && w_dtype < 4, "jitmv: unsupported weight dtype %d", w_dtype);
+    int rc = prepare_events_1d(spikes, aux, spk_kind, vec_len, !corder, corder != 0, workspace, workspace_bytes, s, &ev,
+                               corder ? nullptr : out, corder ? 0 : (size_t)(col_end - col_begin) * kWt[w_dtype],
+                               /*ordered_ids=*/false);
     if (rc) return rc;
     JitParams jp{p0, p1, clen, seed};
     BE_DISPATCH_WT(w_dtype, T, {
