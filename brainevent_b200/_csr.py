@@ -42,14 +42,20 @@ def _csr_kernel(outs=None, shape=None, transpose=False, matmat=False, **kw):
         L = _lib.lib()
         if matmat:
             n = ev.batch
-            out = torch.empty((n_out, n), dtype=data.dtype, device=dev)
+            # scatter: physical [n, n_out] (each batch column a contiguous output vector, the
+            # reference's own physical layout, _csr/binary.py:1263-1286), returned as the logical
+            # [n_out, n] view; gather: [n_out, n] row-major
+            out = (torch.empty((n, n_out), dtype=data.dtype, device=dev) if transpose
+                   else torch.empty((n_out, n), dtype=data.dtype, device=dev))
             ws = workspace(dev, ev.n, n)
             rc = L.be_b200_binary_csrmm(ptr(data), wt_code(data.dtype), homo, ptr(indices), ptr(indptr),
                                         int(indptr.dtype == torch.int64), ptr(perm),
                                         int(perm is not None and perm.dtype == torch.int64),
                                         ptr(ev.spikes), ptr(ev.aux), ev.kind, m, k, nse, n, int(transpose),
-                                        ptr(out), ptr(ws), ws.numel(), stream_ptr(dev))
+                                        int(transpose), ptr(out), ptr(ws), ws.numel(), stream_ptr(dev))
             _lib.check(rc, "binary_csrmm")
+            if transpose:
+                out = out.t()
         else:
             out = torch.empty(n_out, dtype=data.dtype, device=dev)
             ws = workspace(dev, ev.n, 1)

@@ -21,12 +21,16 @@ def _fcn_kernel(outs=None, shape=None, transpose=False, matmat=False, **kw):
         L = _lib.lib()
         if matmat:
             n = ev.batch
-            out = torch.empty((n_out, n), dtype=weights.dtype, device=dev)
+            out = (torch.empty((n, n_out), dtype=weights.dtype, device=dev) if transpose
+                   else torch.empty((n_out, n), dtype=weights.dtype, device=dev))   # see _csr.py
             ws = workspace(dev, ev.n, n)
             rc = L.be_b200_binary_fcnmm(ptr(weights), wt_code(weights.dtype), homo, ptr(indices), n_rows,
                                         n_conn, ptr(ev.spikes), ptr(ev.aux), ev.kind, ev.n, n_out, n,
-                                        int(transpose), ptr(out), ptr(ws), ws.numel(), stream_ptr(dev))
+                                        int(transpose), int(transpose), ptr(out), ptr(ws), ws.numel(),
+                                        stream_ptr(dev))
             _lib.check(rc, "binary_fcnmm")
+            if transpose:
+                out = out.t()
         else:
             out = torch.empty(n_out, dtype=weights.dtype, device=dev)
             ws = workspace(dev, ev.n, 1)

@@ -52,9 +52,9 @@ _SIGNATURES = {
     "be_b200_compact_1d": (_I, [_P, _I, _L, _I, _P, _P, _P, _P, _Z, _P]),
     "be_b200_compact_2d": (_I, [_P, _I, _L, _L, _I, _P, _P, _P, _P, _Z, _P]),
     "be_b200_binary_csrmv": (_I, [_P, _I, _I, _P, _P, _I, _P, _I, _P, _P, _I, _L, _L, _L, _I, _P, _P, _Z, _P]),
-    "be_b200_binary_csrmm": (_I, [_P, _I, _I, _P, _P, _I, _P, _I, _P, _P, _I, _L, _L, _L, _L, _I, _P, _P, _Z, _P]),
+    "be_b200_binary_csrmm": (_I, [_P, _I, _I, _P, _P, _I, _P, _I, _P, _P, _I, _L, _L, _L, _L, _I, _I, _P, _P, _Z, _P]),
     "be_b200_binary_fcnmv": (_I, [_P, _I, _I, _P, _L, _L, _P, _P, _I, _L, _L, _I, _P, _P, _Z, _P]),
-    "be_b200_binary_fcnmm": (_I, [_P, _I, _I, _P, _L, _L, _P, _P, _I, _L, _L, _L, _I, _P, _P, _Z, _P]),
+    "be_b200_binary_fcnmm": (_I, [_P, _I, _I, _P, _L, _L, _P, _P, _I, _L, _L, _L, _I, _I, _P, _P, _Z, _P]),
     "be_b200_binary_jitmv": (_I, [_I, _P, _P, _I, _P, _P, _P, _P, _I, _L, _L, _L, _I, _L, _L, _L, _L, _P, _P, _Z, _P]),
     "be_b200_binary_jitmm": (_I, [_I, _P, _P, _I, _P, _P, _P, _P, _I, _L, _L, _L, _L, _I, _P, _P, _Z, _P]),
     "be_b200_jitc_row_connections": (_I, [_P, _P, _L, _L, _L, _L, _I, _P, _P, _L, _P]),

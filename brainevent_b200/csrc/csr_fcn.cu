@@ -57,21 +57,24 @@ __device__ __forceinline__ typename Acc<T>::type weight_at(const T* __restrict__
 // ------------------------------------------------------------------------------------------
 // scatter, matvec:  out[indices[j]] += w[j]  for j in rows of active sources
 // ------------------------------------------------------------------------------------------
-template <typename T, bool HOMO, int PERM, bool VEC, int G>
-__device__ __forceinline__ void scatter_segment(int64_t s, int64_t e, int gl,
-                                                const int32_t* __restrict__ indices,
-                                                const T* __restrict__ weights,
-                                                const void* __restrict__ perm,
-                                                typename Acc<T>::type w0, T* __restrict__ out) {
+// Visit every synapse j in [s, e) of one row with a group of G lanes: f(column, weight).
+// VEC: peel to a 4-element boundary, then one 128-bit index load (+ one 128-bit weight load) per
+// lane per step, all issued before the first use so a row costs ~one memory round trip.
+template <typename T, bool HOMO, int PERM, bool VEC, int G, typename F>
+__device__ __forceinline__ void for_each_synapse(int64_t s, int64_t e, int gl,
+                                                 const int32_t* __restrict__ indices,
+                                                 const T* __restrict__ weights,
+                                                 const void* __restrict__ perm,
+                                                 typename Acc<T>::type w0, F&& f) {
     using A = typename Acc<T>::type;
     if (!VEC) {
         for (int64_t j = s + gl; j < e; j += G)
-            red_add(out + __ldg(indices + j), weight_at<T, HOMO, PERM>(weights, perm, j, w0));
+            f(__ldg(indices + j), weight_at<T, HOMO, PERM>(weights, perm, j, w0));
         return;
     }
     int64_t a = (s + 3) & ~(int64_t)3;
     if (a > e) a = e;
-    if (gl < a - s) red_add(out + __ldg(indices + s + gl), weight_at<T, HOMO, PERM>(weights, perm, s + gl, w0));
+    if (gl < a - s) f(__ldg(indices + s + gl), weight_at<T, HOMO, PERM>(weights, perm, s + gl, w0));
     int64_t aend = a + ((e - a) & ~(int64_t)3);
 #pragma unroll 2
     for (int64_t j = a + (int64_t)gl * 4; j < aend; j += (int64_t)G * 4) {
@@ -83,12 +86,23 @@ __device__ __forceinline__ void scatter_segment(int64_t s, int64_t e, int gl,
 #pragma unroll
             for (int q = 0; q < 4; ++q) wv[q] = weight_at<T, HOMO, PERM>(weights, perm, j + q, w0);
         }
-        red_add(out + ix.x, wv[0]);
-        red_add(out + ix.y, wv[1]);
-        red_add(out + ix.z, wv[2]);
-        red_add(out + ix.w, wv[3]);
+        f(ix.x, wv[0]);
+        f(ix.y, wv[1]);
+        f(ix.z, wv[2]);
+        f(ix.w, wv[3]);
     }
-    if (gl < e - aend) red_add(out + __ldg(indices + aend + gl), weight_at<T, HOMO, PERM>(weights, perm, aend + gl, w0));
+    if (gl < e - aend) f(__ldg(indices + aend + gl), weight_at<T, HOMO, PERM>(weights, perm, aend + gl, w0));
+}
+
+template <typename T, bool HOMO, int PERM, bool VEC, int G>
+__device__ __forceinline__ void scatter_segment(int64_t s, int64_t e, int gl,
+                                                const int32_t* __restrict__ indices,
+                                                const T* __restrict__ weights,
+                                                const void* __restrict__ perm,
+                                                typename Acc<T>::type w0, T* __restrict__ out) {
+    using A = typename Acc<T>::type;
+    for_each_synapse<T, HOMO, PERM, VEC, G>(s, e, gl, indices, weights, perm, w0,
+                                            [&](int col, A w) { red_add(out + col, w); });
 }
 
 template <typename T, bool HOMO, int PERM, bool VEC, int LPR, typename Rows>
@@ -107,10 +121,15 @@ __global__ void __launch_bounds__(256) scatter_mv_kernel(Rows rows, const int32_
     const A w0 = HOMO ? to_acc<T>(__ldg(weights)) : A(0);
     constexpr int GROUPS = 256 / LPR;
     const int g = threadIdx.x / LPR, gl = threadIdx.x % LPR;
-    for (int64_t a = (int64_t)blockIdx.x * GROUPS + g; a < n_active; a += (int64_t)gridDim.x * GROUPS) {
-        const int r = __ldg(ids + a);
-        int64_t s, e;
-        rows.get(r, s, e);
+    const int64_t stride = (int64_t)gridDim.x * GROUPS;
+    int64_t a = (int64_t)blockIdx.x * GROUPS + g;
+    int r_n = 0;
+    int64_t s_n = 0, e_n = 0;
+    if (a < n_active) { r_n = __ldg(ids + a); rows.get(r_n, s_n, e_n); }
+    for (; a < n_active; a += stride) {
+        const int r = r_n;
+        const int64_t s = s_n, e = e_n;
+        if (a + stride < n_active) { r_n = __ldg(ids + a + stride); rows.get(r_n, s_n, e_n); }   // next row's chain in flight
         if (e - s > kHeavyRow) {
             int slot = -1;
             if (gl == 0) slot = atomicAdd(&s_nheavy, 1);
@@ -204,68 +223,128 @@ __global__ void __launch_bounds__(256) gather_mv_kernel(Rows rows, const int32_t
 // One warp per active row; the row's connectivity is read once.  Sparse column masks use
 // lanes = synapses (32 REDs per instruction); dense masks use lanes = columns (contiguous REDs).
 // ------------------------------------------------------------------------------------------
-constexpr int kMaxWpr = 8;  // register-resident mask words (batch <= 256); wider batches loop
 
-template <typename T, bool HOMO, int PERM, typename Rows>
+template <typename T, bool HOMO, int PERM, bool VEC, int MW, typename Rows>
 __global__ void __launch_bounds__(256) scatter_mm_kernel(Rows rows, const int32_t* __restrict__ indices,
                                                          const T* __restrict__ weights,
                                                          const void* __restrict__ perm,
                                                          const int32_t* __restrict__ ids,
                                                          const int* __restrict__ n_active_ptr,
                                                          const uint32_t* __restrict__ packed, int wpr,
-                                                         int64_t n, T* __restrict__ out) {
+                                                         int64_t n, T* __restrict__ out,
+                                                         int post_lo, int post_hi) {
+    // [post_lo, post_hi): the output rows this launch owns.  When [n_out, batch] does not fit in
+    // L2 the host splits the call into passes over L2-sized output tiles so that the reductions
+    // stay L2-resident instead of becoming DRAM read-modify-writes (the matrix rows are re-read
+    // per pass, which is the cheaper side: 8 B/synapse streamed vs 64 B/event of DRAM RMW).
     using A = typename Acc<T>::type;
     const int n_active = *n_active_ptr;
     const A w0 = HOMO ? to_acc<T>(__ldg(weights)) : A(0);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    for (int64_t a = (int64_t)blockIdx.x * 8 + warp; a < n_active; a += (int64_t)gridDim.x * 8) {
-        const int r = __ldg(ids + a);
-        int64_t s, e;
-        rows.get(r, s, e);
+    // the (row id -> row extent) chain of the NEXT row is fetched while the current row streams,
+    // so a row visit costs one memory round trip instead of three dependent ones
+    const int64_t stride = (int64_t)gridDim.x * 8;
+    int64_t a = (int64_t)blockIdx.x * 8 + warp;
+    int r_n = 0;
+    int64_t s_n = 0, e_n = 0;
+    if (a < n_active) { r_n = __ldg(ids + a); rows.get(r_n, s_n, e_n); }
+    for (; a < n_active; a += stride) {
+        const int r = r_n;
+        const int64_t s = s_n, e = e_n;
+        if (a + stride < n_active) { r_n = __ldg(ids + a + stride); rows.get(r_n, s_n, e_n); }
         const uint32_t* mrow = packed + (int64_t)r * wpr;
-        for (int w_base = 0; w_base < wpr; w_base += kMaxWpr) {
-            uint32_t mask[kMaxWpr];
+        for (int w_base = 0; w_base < wpr; w_base += MW) {
+            uint32_t mask[MW];
             int pc = 0;
 #pragma unroll
-            for (int q = 0; q < kMaxWpr; ++q) {
+            for (int q = 0; q < MW; ++q) {
                 mask[q] = (w_base + q < wpr) ? __ldg(mrow + w_base + q) : 0u;
                 pc += __popc(mask[q]);
             }
             if (pc == 0) continue;
             if (pc <= 8) {
                 // lanes = synapses
-                for (int64_t j = s + lane; j < e; j += 32) {
-                    const int64_t o = (int64_t)__ldg(indices + j) * n + (int64_t)w_base * 32;
-                    const A wv = weight_at<T, HOMO, PERM>(weights, perm, j, w0);
+                for_each_synapse<T, HOMO, PERM, VEC, 32>(s, e, lane, indices, weights, perm, w0, [&](int col, A wv) {
+                    if (col < post_lo || col >= post_hi) return;
+                    T* o = out + (int64_t)col * n + (int64_t)w_base * 32;
 #pragma unroll
-                    for (int q = 0; q < kMaxWpr; ++q) {
+                    for (int q = 0; q < MW; ++q) {
                         uint32_t m = mask[q];
                         while (m) {
-                            int c = __ffs(m) - 1;
+                            const int c = __ffs(m) - 1;
                             m &= m - 1;
-                            red_add(out + o + q * 32 + c, wv);
+                            red_add(o + q * 32 + c, wv);
                         }
                     }
-                }
+                });
             } else {
                 // lanes = columns: broadcast one synapse at a time
                 for (int64_t j0 = s; j0 < e; j0 += 32) {
                     const int64_t j = j0 + lane;
                     int64_t my_o = 0;
                     A my_w = A(0);
+                    bool mine = false;
                     if (j < e) {
-                        my_o = (int64_t)__ldg(indices + j) * n + (int64_t)w_base * 32;
-                        my_w = weight_at<T, HOMO, PERM>(weights, perm, j, w0);
+                        const int col = __ldg(indices + j);
+                        mine = col >= post_lo && col < post_hi;
+                        if (mine) {
+                            my_o = (int64_t)col * n + (int64_t)w_base * 32;
+                            my_w = weight_at<T, HOMO, PERM>(weights, perm, j, w0);
+                        }
                     }
-                    const int cnt = (int)min((int64_t)32, e - j0);
-                    for (int t = 0; t < cnt; ++t) {
+                    uint32_t todo = __ballot_sync(0xffffffffu, mine);
+                    while (todo) {
+                        const int t = __ffs(todo) - 1;
+                        todo &= todo - 1;
                         const int64_t o = __shfl_sync(0xffffffffu, my_o, t);
                         const A wv = __shfl_sync(0xffffffffu, my_w, t);
 #pragma unroll
-                        for (int q = 0; q < kMaxWpr; ++q)
+                        for (int q = 0; q < MW; ++q)
                             if ((mask[q] >> lane) & 1u) red_add(out + o + q * 32 + lane, wv);
                     }
                 }
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// scatter, matmat, BATCH-MAJOR output out[c, :] (physical [batch, n_out]): every (active row,
+// active column) pair is one matvec-style row scatter into that column's contiguous output
+// vector.  The host walks the columns in groups whose output vectors fit in L2 together
+// ([col_lo, col_hi) per launch): reductions stay L2-resident, a row is re-read only for the
+// groups it spikes in (~1.3x at 1 % rates instead of once per output tile), and no synapse is
+// filtered away after being loaded.
+// ------------------------------------------------------------------------------------------
+template <typename T, bool HOMO, int PERM, bool VEC, typename Rows>
+__global__ void __launch_bounds__(256) scatter_mm_bm_kernel(Rows rows, const int32_t* __restrict__ indices,
+                                                            const T* __restrict__ weights,
+                                                            const void* __restrict__ perm,
+                                                            const int32_t* __restrict__ ids,
+                                                            const int* __restrict__ n_active_ptr,
+                                                            const uint32_t* __restrict__ packed, int wpr,
+                                                            int64_t n_out, T* __restrict__ out,
+                                                            int col_lo, int col_hi) {
+    using A = typename Acc<T>::type;
+    const int n_active = *n_active_ptr;
+    const A w0 = HOMO ? to_acc<T>(__ldg(weights)) : A(0);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int w_lo = col_lo >> 5, w_hi = (col_hi + 31) >> 5;
+    const int64_t stride = (int64_t)gridDim.x * 8;
+    for (int64_t a = (int64_t)blockIdx.x * 8 + warp; a < n_active; a += stride) {
+        const int r = __ldg(ids + a);
+        const uint32_t* mrow = packed + (int64_t)r * wpr;
+        int64_t s = -1, e = -1;
+        for (int w = w_lo; w < w_hi; ++w) {
+            uint32_t m = __ldg(mrow + w);
+            const int b0 = w * 32;
+            if (col_lo > b0) m &= ~0u << (col_lo - b0);
+            if (col_hi < b0 + 32) m &= (1u << (col_hi - b0)) - 1u;
+            while (m) {
+                const int c = b0 + __ffs(m) - 1;
+                m &= m - 1;
+                if (s < 0) rows.get(r, s, e);
+                scatter_segment<T, HOMO, PERM, VEC, 32>(s, e, lane, indices, weights, perm, w0, out + (int64_t)c * n_out);
             }
         }
     }
@@ -386,17 +465,54 @@ static int launch_gather_mv(const Rows& rows, const ConnArgs& c, const Events& e
     return BE_B200_OK;
 }
 
+constexpr size_t kL2TileBytes = 48u << 20;   // output tile kept L2-resident per scatter pass (L2 = 126 MB)
+
 template <typename T, bool HOMO, int PERM, typename Rows>
 static int launch_scatter_mm(const Rows& rows, const ConnArgs& c, const Events& ev, int64_t n_src,
-                             int64_t n, T* out, cudaStream_t s) {
+                             int64_t n_out, int64_t n, T* out, cudaStream_t s) {
     int blocks = (int)std::min<int64_t>(ceil_div(std::max<int64_t>(n_src, 1), 8), kNumSM * 8);
-    {
-        ProfileScope prof(s);
-        scatter_mm_kernel<T, HOMO, PERM, Rows><<<blocks, 256, 0, s>>>(
-            rows, c.indices, (const T*)c.weights, c.perm, ev.active_ids, ev.n_active, ev.packed,
-            ev.words_per_row, n, out);
+    const size_t row_bytes = (size_t)n * sizeof(T);
+    const int64_t rows_per_pass = std::max<int64_t>(1, (int64_t)(kL2TileBytes / row_bytes));
+    const bool vec = al16(c.indices) && (c.homo || al16(c.weights));
+    ProfileScope prof(s);   // one record for all passes of the call
+    for (int64_t lo = 0; lo < n_out; lo += rows_per_pass) {
+        const int64_t hi = std::min(n_out, lo + rows_per_pass);
+        // clear the tile right before its pass: the zeroed lines are still L2-resident when the
+        // reductions arrive, so the tile reaches DRAM once (write-back), never as RMW traffic
+        BE_CUDA(cudaMemsetAsync(out + lo * n, 0, (size_t)(hi - lo) * row_bytes, s));
+#define BE_SMM(VEC, MW)                                                                         \
+        scatter_mm_kernel<T, HOMO, PERM, VEC, MW, Rows><<<blocks, 256, 0, s>>>(                     \
+            rows, c.indices, (const T*)c.weights, c.perm, ev.active_ids, ev.n_active, ev.packed,    \
+            ev.words_per_row, n, out, (int)lo, (int)hi)
+        if (ev.words_per_row <= 2) { if (vec) BE_SMM(true, 2); else BE_SMM(false, 2); }
+        else { if (vec) BE_SMM(true, 8); else BE_SMM(false, 8); }
+#undef BE_SMM
     }
     BE_LAUNCH_CHECK("scatter_mm_kernel");
+    return BE_B200_OK;
+}
+
+template <typename T, bool HOMO, int PERM, typename Rows>
+static int launch_scatter_mm_bm(const Rows& rows, const ConnArgs& c, const Events& ev, int64_t n_src,
+                                int64_t n_out, int64_t n, T* out, cudaStream_t s) {
+    int blocks = (int)std::min<int64_t>(ceil_div(std::max<int64_t>(n_src, 1), 8), kNumSM * 8);
+    const size_t col_bytes = (size_t)n_out * sizeof(T);
+    const int64_t cols_per_pass = std::max<int64_t>(1, (int64_t)(kL2TileBytes / std::max<size_t>(col_bytes, 1)));
+    const bool vec = al16(c.indices) && (c.homo || al16(c.weights));
+    ProfileScope prof(s);
+    for (int64_t lo = 0; lo < n; lo += cols_per_pass) {
+        const int64_t hi = std::min(n, lo + cols_per_pass);
+        BE_CUDA(cudaMemsetAsync(out + lo * n_out, 0, (size_t)(hi - lo) * col_bytes, s));
+        if (vec)
+            scatter_mm_bm_kernel<T, HOMO, PERM, true, Rows><<<blocks, 256, 0, s>>>(
+                rows, c.indices, (const T*)c.weights, c.perm, ev.active_ids, ev.n_active, ev.packed,
+                ev.words_per_row, n_out, out, (int)lo, (int)hi);
+        else
+            scatter_mm_bm_kernel<T, HOMO, PERM, false, Rows><<<blocks, 256, 0, s>>>(
+                rows, c.indices, (const T*)c.weights, c.perm, ev.active_ids, ev.n_active, ev.packed,
+                ev.words_per_row, n_out, out, (int)lo, (int)hi);
+    }
+    BE_LAUNCH_CHECK("scatter_mm_bm_kernel");
     return BE_B200_OK;
 }
 
@@ -423,7 +539,7 @@ template <typename T, typename Rows>
 static int run_conn(const Rows& rows, const ConnArgs& c, const void* spikes, const void* aux,
                     int spk_kind, int64_t n_src, int64_t n_rows, int64_t n_out, int64_t n_batch,
                     bool scatter, void* out_v, void* workspace, size_t workspace_bytes,
-                    cudaStream_t s) {
+                    cudaStream_t s, bool batch_major = false) {
     T* out = (T*)out_v;
     Events ev;
     int rc;
@@ -434,7 +550,6 @@ static int run_conn(const Rows& rows, const ConnArgs& c, const void* spikes, con
                                 scatter ? (void*)out : nullptr, scatter ? (size_t)out_elems * sizeof(T) : 0,
                                 /*ordered_ids=*/false);   // the output clear rides on the compaction kernel
     if (rc) return rc;
-    if (mm && scatter && out_elems > 0) BE_CUDA(cudaMemsetAsync(out, 0, (size_t)out_elems * sizeof(T), s));
     if (out_elems == 0) return BE_B200_OK;
     if (n_src == 0) {
         if (!scatter) BE_CUDA(cudaMemsetAsync(out, 0, (size_t)out_elems * sizeof(T), s));
@@ -442,7 +557,8 @@ static int run_conn(const Rows& rows, const ConnArgs& c, const void* spikes, con
     }
 #define BE_RUN(HOMO, PERM)                                                                              \
     do {                                                                                                \
-        if (scatter) return mm ? launch_scatter_mm<T, HOMO, PERM, Rows>(rows, c, ev, n_src, n_batch, out, s) \
+        if (scatter && mm && batch_major) return launch_scatter_mm_bm<T, HOMO, PERM, Rows>(rows, c, ev, n_src, n_out, n_batch, out, s); \
+        if (scatter) return mm ? launch_scatter_mm<T, HOMO, PERM, Rows>(rows, c, ev, n_src, n_out, n_batch, out, s) \
                                : launch_scatter_mv<T, HOMO, PERM, Rows>(rows, c, ev, n_src, out, s);         \
         return mm ? launch_gather_mm<T, HOMO, PERM, Rows>(rows, c, ev, n_rows, n_batch, out, s)              \
                   : launch_gather_mv<T, HOMO, PERM, Rows>(rows, c, ev, n_rows, out, s);                      \
@@ -464,8 +580,9 @@ static int csr_entry(const void* weights, int w_dtype, int homo, const int32_t* 
                      const void* indptr, int indptr_is64, const void* perm, int perm_is64,
                      const void* spikes, const void* aux, int spk_kind, int64_t m, int64_t k,
                      int64_t nse, int64_t n, int transpose, void* out, void* workspace,
-                     size_t workspace_bytes, void* stream) {
+                     size_t workspace_bytes, void* stream, int out_batch_major = 0) {
     cudaStream_t s = (cudaStream_t)stream;
+    BE_REQUIRE(!out_batch_major || (transpose && n > 0), "batch-major output is only defined for the scatter matmat");
     BE_REQUIRE(m >= 0 && k >= 0 && m < (1ll << 31) && k < (1ll << 31), "csr: shape out of range");
     BE_REQUIRE(weights && indptr && out, "csr: NULL pointer");
     BE_REQUIRE(indices || nse == 0, "csr: indices is NULL");
@@ -475,10 +592,10 @@ static int csr_entry(const void* weights, int w_dtype, int homo, const int32_t* 
     BE_DISPATCH_WT(w_dtype, T, {
         if (indptr_is64) {
             CsrRows<int64_t> rows{(const int64_t*)indptr};
-            return run_conn<T>(rows, c, spikes, aux, spk_kind, n_src, m, n_out, n, transpose != 0, out, workspace, workspace_bytes, s);
+            return run_conn<T>(rows, c, spikes, aux, spk_kind, n_src, m, n_out, n, transpose != 0, out, workspace, workspace_bytes, s, out_batch_major != 0);
         } else {
             CsrRows<int32_t> rows{(const int32_t*)indptr};
-            return run_conn<T>(rows, c, spikes, aux, spk_kind, n_src, m, n_out, n, transpose != 0, out, workspace, workspace_bytes, s);
+            return run_conn<T>(rows, c, spikes, aux, spk_kind, n_src, m, n_out, n, transpose != 0, out, workspace, workspace_bytes, s, out_batch_major != 0);
         }
     });
     return BE_B200_OK;
@@ -498,18 +615,20 @@ extern "C" int be_b200_binary_csrmm(const void* weights, int w_dtype, int homo,
                                     const int32_t* indices, const void* indptr, int indptr_is64,
                                     const void* perm, int perm_is64, const void* spikes,
                                     const void* aux, int spk_kind, int64_t m, int64_t k,
-                                    int64_t nse, int64_t n, int transpose, void* out,
-                                    void* workspace, size_t workspace_bytes, void* stream) {
+                                    int64_t nse, int64_t n, int transpose, int out_batch_major,
+                                    void* out, void* workspace, size_t workspace_bytes, void* stream) {
     BE_REQUIRE(n >= 1, "csrmm: batch must be >= 1");
     return csr_entry(weights, w_dtype, homo, indices, indptr, indptr_is64, perm, perm_is64, spikes,
-                     aux, spk_kind, m, k, nse, n, transpose, out, workspace, workspace_bytes, stream);
+                     aux, spk_kind, m, k, nse, n, transpose, out, workspace, workspace_bytes, stream, out_batch_major);
 }
 
 static int fcn_entry(const void* weights, int w_dtype, int homo, const int32_t* indices,
                      int64_t n_rows, int64_t n_conn, const void* spikes, const void* aux,
                      int spk_kind, int64_t n_src, int64_t n_out, int64_t n, int transpose,
-                     void* out, void* workspace, size_t workspace_bytes, void* stream) {
+                     void* out, void* workspace, size_t workspace_bytes, void* stream,
+                     int out_batch_major = 0) {
     cudaStream_t s = (cudaStream_t)stream;
+    BE_REQUIRE(!out_batch_major || (transpose && n > 0), "batch-major output is only defined for the scatter matmat");
     BE_REQUIRE(n_rows >= 0 && n_conn >= 0 && n_src >= 0 && n_out >= 0, "fcn: negative size");
     BE_REQUIRE(n_rows < (1ll << 31) && n_src < (1ll << 31) && n_out < (1ll << 31), "fcn: size out of range");
     BE_REQUIRE(weights && out, "fcn: NULL pointer");
@@ -519,7 +638,7 @@ static int fcn_entry(const void* weights, int w_dtype, int homo, const int32_t* 
     ConnArgs c{weights, w_dtype, homo, indices, nullptr, 0, (double)n_conn};
     FcnRows rows{n_conn};
     BE_DISPATCH_WT(w_dtype, T, {
-        return run_conn<T>(rows, c, spikes, aux, spk_kind, n_src, n_rows, n_out, n, transpose != 0, out, workspace, workspace_bytes, s);
+        return run_conn<T>(rows, c, spikes, aux, spk_kind, n_src, n_rows, n_out, n, transpose != 0, out, workspace, workspace_bytes, s, out_batch_major != 0);
     });
     return BE_B200_OK;
 }
@@ -537,9 +656,9 @@ extern "C" int be_b200_binary_fcnmm(const void* weights, int w_dtype, int homo,
                                     const int32_t* indices, int64_t n_rows, int64_t n_conn,
                                     const void* spikes, const void* aux, int spk_kind,
                                     int64_t n_src, int64_t n_out, int64_t n, int transpose,
-                                    void* out, void* workspace, size_t workspace_bytes,
-                                    void* stream) {
+                                    int out_batch_major, void* out, void* workspace,
+                                    size_t workspace_bytes, void* stream) {
     BE_REQUIRE(n >= 1, "fcnmm: batch must be >= 1");
     return fcn_entry(weights, w_dtype, homo, indices, n_rows, n_conn, spikes, aux, spk_kind, n_src,
-                     n_out, n, transpose, out, workspace, workspace_bytes, stream);
+                     n_out, n, transpose, out, workspace, workspace_bytes, stream, out_batch_major);
 }

@@ -124,14 +124,15 @@ XLA_FFI_Error* csr_common(XLA_FFI_CallFrame* frame, bool matmat, bool indexed, c
     BE_XLA_PROLOGUE(na, 1, "csr");
     XLA_FFI_Buffer *w = fr.arg(0), *idx = fr.arg(1), *ptr = fr.arg(2), *perm = indexed ? fr.arg(3) : nullptr,
                    *ev = fr.arg(na - 1), *out = fr.ret(0);
-    int64_t transpose = 0;
+    int64_t transpose = 0, bm = 0;
     fr.attr_i64("transpose", &transpose);
+    fr.attr_i64("out_batch_major", &bm);
     const int wt = wt_of(w->dtype), sk = spk_of(ev->dtype);
     if (wt < 0 || sk < 0) return fr.fail(BE_B200_EUNIMPL, std::string(name) + ": unsupported dtype");
     if (idx->dtype != BE_XLA_S32) return fr.fail(BE_B200_EINVAL, std::string(name) + ": indices must be int32");
     const int64_t m = ptr->dims[0] - 1, nse = numel(idx);
-    const int64_t n = matmat ? out->dims[1] : 0;
-    const int64_t k = transpose ? out->dims[0] : (sk == BE_B200_SPK_PACKED && !matmat ? -1 : ev->dims[0]);
+    const int64_t n = matmat ? out->dims[bm ? 0 : 1] : 0;
+    const int64_t k = transpose ? out->dims[bm ? 1 : 0] : (sk == BE_B200_SPK_PACKED && !matmat ? -1 : ev->dims[0]);
     if (k < 0) return fr.fail(BE_B200_EINVAL, std::string(name) + ": packed events need transpose=1 here");
     const int64_t n_src = transpose ? m : k;
     if (XLA_FFI_Error* e = fr.get_scratch(n_src, matmat ? n : 1)) return e;
@@ -139,7 +140,7 @@ XLA_FFI_Error* csr_common(XLA_FFI_CallFrame* frame, bool matmat, bool indexed, c
     if (matmat)
         rc = be_b200_binary_csrmm(w->data, wt, numel(w) == 1, (const int32_t*)idx->data, ptr->data, ptr->dtype == BE_XLA_S64,
                                   perm ? perm->data : nullptr, perm && perm->dtype == BE_XLA_S64, ev->data, nullptr, sk, m, k,
-                                  nse, n, (int)transpose, out->data, fr.scratch, fr.scratch_bytes, fr.stream);
+                                  nse, n, (int)transpose, (int)bm, out->data, fr.scratch, fr.scratch_bytes, fr.stream);
     else
         rc = be_b200_binary_csrmv(w->data, wt, numel(w) == 1, (const int32_t*)idx->data, ptr->data, ptr->dtype == BE_XLA_S64,
                                   perm ? perm->data : nullptr, perm && perm->dtype == BE_XLA_S64, ev->data, nullptr, sk, m, k,
@@ -150,13 +151,14 @@ XLA_FFI_Error* csr_common(XLA_FFI_CallFrame* frame, bool matmat, bool indexed, c
 XLA_FFI_Error* fcn_common(XLA_FFI_CallFrame* frame, bool matmat, const char* name) {
     BE_XLA_PROLOGUE(3, 1, "fcn");
     XLA_FFI_Buffer *w = fr.arg(0), *idx = fr.arg(1), *ev = fr.arg(2), *out = fr.ret(0);
-    int64_t transpose = 0;
+    int64_t transpose = 0, bm = 0;
     fr.attr_i64("transpose", &transpose);
+    fr.attr_i64("out_batch_major", &bm);
     const int wt = wt_of(w->dtype), sk = spk_of(ev->dtype);
     if (wt < 0 || sk < 0) return fr.fail(BE_B200_EUNIMPL, std::string(name) + ": unsupported dtype");
     if (idx->dtype != BE_XLA_S32 || idx->rank != 2) return fr.fail(BE_B200_EINVAL, std::string(name) + ": indices must be int32 [n_rows, n_conn]");
-    const int64_t n_rows = idx->dims[0], n_conn = idx->dims[1], n_out = out->dims[0];
-    const int64_t n = matmat ? out->dims[1] : 0;
+    const int64_t n_rows = idx->dims[0], n_conn = idx->dims[1], n_out = out->dims[(matmat && bm) ? 1 : 0];
+    const int64_t n = matmat ? out->dims[bm ? 0 : 1] : 0;
     int64_t n_src = transpose ? n_rows : ev->dims[0];
     if (!transpose && sk == BE_B200_SPK_PACKED && !matmat) {
         if (!fr.attr_i64("n_src", &n_src)) return fr.fail(BE_B200_EINVAL, std::string(name) + ": packed events need attr n_src");
@@ -165,7 +167,7 @@ XLA_FFI_Error* fcn_common(XLA_FFI_CallFrame* frame, bool matmat, const char* nam
     int rc;
     if (matmat)
         rc = be_b200_binary_fcnmm(w->data, wt, numel(w) == 1, (const int32_t*)idx->data, n_rows, n_conn, ev->data, nullptr, sk,
-                                  n_src, n_out, n, (int)transpose, out->data, fr.scratch, fr.scratch_bytes, fr.stream);
+                                  n_src, n_out, n, (int)transpose, (int)bm, out->data, fr.scratch, fr.scratch_bytes, fr.stream);
     else
         rc = be_b200_binary_fcnmv(w->data, wt, numel(w) == 1, (const int32_t*)idx->data, n_rows, n_conn, ev->data, nullptr, sk,
                                   n_src, n_out, (int)transpose, out->data, fr.scratch, fr.scratch_bytes, fr.stream);

@@ -99,7 +99,11 @@ int be_b200_compact_2d(const void* spikes, int spk_kind, int64_t n, int64_t batc
  * (indptr_is64).  perm (nullable): indexed variant reads weights[perm[j]] (perm_is64 selects
  * int64).  transpose=1: events[m] -> out[k] (atomic scatter over active rows);
  * transpose=0: events[k] -> out[m] (deterministic gather over all rows).
- * mm: events [m or k, n] row-major, out [k or m, n] row-major (batch innermost). */
+ * mm: events [m or k, n] row-major, out [k or m, n] row-major (batch innermost).  For the
+ * scatter matmat (transpose=1) `out_batch_major=1` writes the physical layout [n, k] instead --
+ * the reference's own physical layout for this op (ref: _csr/binary.py:1263-1286) and the fast
+ * one here: each batch column is a contiguous output vector, columns are processed in L2-sized
+ * groups. */
 int be_b200_binary_csrmv(const void* weights, int w_dtype, int homo, const int32_t* indices,
                          const void* indptr, int indptr_is64, const void* perm, int perm_is64,
                          const void* spikes, const void* aux, int spk_kind, int64_t m, int64_t k,
@@ -108,8 +112,8 @@ int be_b200_binary_csrmv(const void* weights, int w_dtype, int homo, const int32
 int be_b200_binary_csrmm(const void* weights, int w_dtype, int homo, const int32_t* indices,
                          const void* indptr, int indptr_is64, const void* perm, int perm_is64,
                          const void* spikes, const void* aux, int spk_kind, int64_t m, int64_t k,
-                         int64_t nse, int64_t n, int transpose, void* out, void* workspace,
-                         size_t workspace_bytes, void* stream);
+                         int64_t nse, int64_t n, int transpose, int out_batch_major, void* out,
+                         void* workspace, size_t workspace_bytes, void* stream);
 
 /* ---- fixed-number connectivity / ELL (ref: _fcn/binary.py:43 binary_fcnmv, :512 binary_fcnmm;
  *      _fcn/binary_fcnmv.cu:188-252) -----------------------------------------------------------
@@ -122,7 +126,8 @@ int be_b200_binary_fcnmv(const void* weights, int w_dtype, int homo, const int32
 int be_b200_binary_fcnmm(const void* weights, int w_dtype, int homo, const int32_t* indices,
                          int64_t n_rows, int64_t n_conn, const void* spikes, const void* aux,
                          int spk_kind, int64_t n_src, int64_t n_out, int64_t n, int transpose,
-                         void* out, void* workspace, size_t workspace_bytes, void* stream);
+                         int out_batch_major, void* out, void* workspace, size_t workspace_bytes,
+                         void* stream);
 
 /* ---- JITC (ref: _jit_scalar/binary.py:44,171; _jit_normal/binary.py:44,177;
  *      _jit_uniform/binary.py:44,177; CUDA _jit_scalar/binary_jitsmv.cu:127-214) ---------------
