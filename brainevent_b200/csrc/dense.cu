@@ -12,6 +12,8 @@
 #include "common.cuh"
 
 #include <algorithm>
+#include <cstdlib>
+#include <type_traits>
 
 namespace be {
 
@@ -183,6 +185,16 @@ static int run_dense_mv(const T* W, int64_t rows, int64_t cols, const Events& ev
     return BE_B200_OK;
 }
 
+// dense_tc.cu
+int launch_dense_mm_t_tc(const float* W, int64_t k, int64_t m, const uint32_t* packed, int wpr, int64_t n,
+                         float* out, cudaStream_t s);
+
+// BE_B200_DENSE_TC=0 keeps the SIMT kernel (A/B measurements); default: tensor cores at batch >= 64
+static bool dense_tc_enabled() {
+    const char* e = getenv("BE_B200_DENSE_TC");
+    return !(e && e[0] == '0');
+}
+
 template <typename T>
 static int run_dense_mm(const T* W, int64_t rows, int64_t cols, const Events& ev, int64_t n,
                         bool transpose, T* out, cudaStream_t s) {
@@ -191,6 +203,11 @@ static int run_dense_mm(const T* W, int64_t rows, int64_t cols, const Events& ev
     if (transpose) {
         const int64_t m = cols;
         if (m == 0) return BE_B200_OK;
+        if constexpr (std::is_same<T, float>::value) {
+            // the one real contraction on the path: fp32-exact 3 x bf16 split on tcgen05
+            if (n >= 64 && (((uintptr_t)W & 15u) == 0) && (m % 4 == 0) && dense_tc_enabled())
+                return launch_dense_mm_t_tc(W, rows, m, ev.packed, wpr, n, out, s);
+        }
         const int64_t row_blocks = ceil_div(m, 256);
         int slices = (int)std::max<int64_t>(1, std::min<int64_t>(32, (2 * kNumSM) / row_blocks));
         if (slices > 1) BE_CUDA(cudaMemsetAsync(out, 0, (size_t)(m * n) * sizeof(T), s));

@@ -1,0 +1,294 @@
+// dense_tc.cu -- tcgen05 (5th-gen tensor core) path for the dense event matmul at batch >= 64.
+//
+//   out[m, n] = sum_k W[k, m] * e(S[k, n])          (binary_densemm, transpose=True, fp32 weights)
+//
+// This is the one place on the path that really is a contraction (north star: "tensor cores only
+// for the dense BinaryArray@dense path at batch >= 64").  To stay inside the fp32 tolerance
+// (rtol 1e-5) the fp32 weight is split on the fly into three bf16 planes, w = hi + mid + lo
+// (8+8+8 significand bits: an error-free split up to 2^-24 relative); the event operand is an
+// exact 0/1 bf16 matrix expanded from the bit-packed spikes, so every product is exact and the
+// tensor core only performs fp32 accumulation (3 MMAs per K-step into the same TMEM tile).
+//
+// Mapping: one CTA per (128 output rows) x (64 batch columns) x (split of the K range).
+//   * all 256 threads stream a [64 k, 128 m] fp32 tile of W with 128-bit loads, split it into the
+//     three bf16 planes and write them straight into the canonical MN-major (no-swizzle) UMMA
+//     shared-memory layout; the spike bits of the same 64 sources are expanded to bf16 0/1;
+//   * one elected thread issues tcgen05.mma.kind::f16 (M=128, N=64, K=16) with the accumulator
+//     in TMEM; tcgen05.commit on an mbarrier hands the shared-memory stage back (2 stages);
+//   * k-blocks whose 64 sources are all silent are skipped before W is even read (event-driven);
+//   * epilogue: tcgen05.ld (32 lanes x 32 columns per warp) -> registers -> out (plain stores, or
+//     RED when the K range is split across CTAs).
+#include "common.cuh"
+
+#include <algorithm>
+
+namespace be {
+
+constexpr int TC_BM = 128, TC_BN = 64, TC_BK = 32, TC_THREADS = 256, TC_STAGES = 2;
+constexpr int TC_A_PLANE = TC_BM * TC_BK * 2;            // 8 KB: one bf16 plane of the A tile
+constexpr int TC_B_TILE = TC_BN * TC_BK * 2;             // 4 KB
+constexpr int TC_ITEMS = (TC_BK / 8) * 8 / 8;            // [8 k x 16 m] load items per warp per k-block
+constexpr int TC_STAGE_BYTES = 3 * TC_A_PLANE + TC_B_TILE;
+constexpr int TC_SMEM_BYTES = TC_STAGES * TC_STAGE_BYTES + 1024;
+
+// canonical MN-major, no swizzle: core matrix = 8 (K) rows x 16 B (8 bf16 along MN), 128 B each.
+// A: core (mi, kk) at (kk * 16 + mi) * 128  -> SBO (MN step) = 128 B, LBO (K step) = 2048 B
+// B: core (ni, kk) at (kk *  8 + ni) * 128  -> SBO = 128 B, LBO = 1024 B
+constexpr uint32_t TC_A_SBO = 128, TC_A_LBO = 16 * 128, TC_B_SBO = 128, TC_B_LBO = 8 * 128;
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t lbo, uint32_t sbo) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr >> 4) & 0x3fff);
+    d |= (uint64_t)((lbo >> 4) & 0x3fff) << 16;
+    d |= (uint64_t)((sbo >> 4) & 0x3fff) << 32;
+    d |= (uint64_t)1 << 46;   // descriptor version (Blackwell)
+    return d;                 // base_offset 0, lbo_mode 0, layout_type 0 (SWIZZLE_NONE)
+}
+
+// kind::f16 instruction descriptor: D=f32, A=B=bf16, both MN-major, M=128, N=64
+constexpr uint32_t TC_IDESC = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) |
+                              ((uint32_t)(TC_BN >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t done = 0;
+    const uint32_t addr = smem_u32(bar);
+    while (!done) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done)
+            : "r"(addr), "r"(parity)
+            : "memory");
+    }
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d), "l"(adesc), "l"(bdesc),
+        "r"(TC_IDESC), "r"(accumulate)
+        : "memory");
+}
+
+__device__ __forceinline__ uint32_t pack_bf16(__nv_bfloat16 a, __nv_bfloat16 b) {
+    return (uint32_t)__bfloat16_as_ushort(a) | ((uint32_t)__bfloat16_as_ushort(b) << 16);
+}
+
+__global__ void __launch_bounds__(TC_THREADS, 3)
+dense_mm_t_tc_kernel(const float* __restrict__ W, int64_t k, int64_t m, const uint32_t* __restrict__ packed, int wpr,
+                     int64_t n, float* __restrict__ out, int kb_per_split, int split_k) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    __shared__ uint64_t empty_bar[TC_STAGES];
+    __shared__ uint64_t done_bar;
+    __shared__ uint32_t tmem_base_s;
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int64_t m0 = (int64_t)blockIdx.x * TC_BM;
+    const int64_t n0 = (int64_t)blockIdx.z * TC_BN;
+    const int total_kb = (int)((k + TC_BK - 1) / TC_BK);
+    const int kb_begin = blockIdx.y * kb_per_split;
+    const int kb_end = min(total_kb, kb_begin + kb_per_split);
+
+    if (tid == 0) {
+        for (int s = 0; s < TC_STAGES; ++s) mbar_init(&empty_bar[s], 1);
+        mbar_init(&done_bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)),
+                     "n"(TC_BN)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_d = tmem_base_s;
+
+    // next k-block >= kb whose TC_BK sources are not all silent in my columns (event-driven skip:
+    // a silent block is dropped before its weights are read); uniform across the CTA
+    auto find_next = [&](int kb) {
+        for (; kb < kb_end; ++kb) {
+            uint32_t my_word = 0;
+            if (tid < 2 * TC_BK) {
+                const int64_t kr = (int64_t)kb * TC_BK + (tid >> 1);
+                const int w = (int)(n0 >> 5) + (tid & 1);
+                if (kr < k && w < wpr) my_word = __ldg(packed + kr * wpr + w);
+                const int64_t cbase = (int64_t)w * 32;
+                if (cbase + 32 > n) my_word &= (n > cbase) ? ((1u << (n - cbase)) - 1u) : 0u;
+            }
+            if (__syncthreads_or(my_word != 0u)) break;
+        }
+        return kb;
+    };
+    // each warp streams TC_ITEMS [8 k x 16 m] patches of the tile: lane = (k8 = lane/4, quad = lane%4)
+    auto load_tile = [&](int kb, float4 (&wv)[TC_ITEMS]) {
+        const int64_t k0 = (int64_t)kb * TC_BK;
+#pragma unroll
+        for (int i = 0; i < TC_ITEMS; ++i) {
+            const int item = warp * TC_ITEMS + i;          // (kk, mq) = (item / 8, item % 8)
+            const int64_t kr = k0 + (item >> 3) * 8 + (lane >> 2);
+            const int64_t mc = m0 + (item & 7) * 16 + (lane & 3) * 4;
+            if (kr < k && mc + 3 < m) wv[i] = __ldg(reinterpret_cast<const float4*>(W + kr * m + mc));
+            else {
+                float t[4];
+#pragma unroll
+                for (int q = 0; q < 4; ++q) t[q] = (kr < k && mc + q < m) ? __ldg(W + kr * m + mc + q) : 0.0f;
+                wv[i] = make_float4(t[0], t[1], t[2], t[3]);
+            }
+        }
+    };
+
+    int n_issued = 0;      // k-blocks that actually reached the tensor core (uniform across the CTA)
+    float4 cur[TC_ITEMS], nxt[TC_ITEMS];
+    int kb = find_next(kb_begin);
+    if (kb < kb_end) load_tile(kb, cur);
+    while (kb < kb_end) {
+        const int64_t k0 = (int64_t)kb * TC_BK;
+        // software pipeline: the next live block's weights are in flight while this one is
+        // converted, staged and multiplied
+        const int kb_next = find_next(kb + 1);
+        if (kb_next < kb_end) load_tile(kb_next, nxt);
+
+        const int stage = n_issued % TC_STAGES;
+        uint8_t* sA = smem + stage * TC_STAGE_BYTES;
+        uint8_t* sB = sA + 3 * TC_A_PLANE;
+        if (n_issued >= TC_STAGES) mbar_wait(&empty_bar[stage], ((n_issued / TC_STAGES) - 1) & 1);
+        // ---- A: split into bf16 hi/mid/lo planes, MN-major core matrices ------------------------
+#pragma unroll
+        for (int i = 0; i < TC_ITEMS; ++i) {
+            const int item = warp * TC_ITEMS + i;
+            const int kk = item >> 3, mq = item & 7;
+            const int k8 = lane >> 2;
+            const int m_local = mq * 16 + (lane & 3) * 4;
+            const uint32_t off = (uint32_t)((kk * 16 + (m_local >> 3)) * 128 + k8 * 16 + (m_local & 7) * 2);
+            const float w4[4] = {cur[i].x, cur[i].y, cur[i].z, cur[i].w};
+            __nv_bfloat16 hi[4], mid[4], lo[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                hi[q] = __float2bfloat16_rn(w4[q]);
+                const float r1 = w4[q] - __bfloat162float(hi[q]);
+                mid[q] = __float2bfloat16_rn(r1);
+                const float r2 = r1 - __bfloat162float(mid[q]);
+                lo[q] = __float2bfloat16_rn(r2);
+            }
+            *reinterpret_cast<uint2*>(sA + off) = make_uint2(pack_bf16(hi[0], hi[1]), pack_bf16(hi[2], hi[3]));
+            *reinterpret_cast<uint2*>(sA + TC_A_PLANE + off) = make_uint2(pack_bf16(mid[0], mid[1]), pack_bf16(mid[2], mid[3]));
+            *reinterpret_cast<uint2*>(sA + 2 * TC_A_PLANE + off) = make_uint2(pack_bf16(lo[0], lo[1]), pack_bf16(lo[2], lo[3]));
+        }
+        // ---- B: 0/1 bf16 from the spike bits: TC_BK x 8 (k, n-octet) cells ------------------------
+        for (int cell = tid; cell < TC_BK * 8; cell += TC_THREADS) {
+            const int k_local = cell >> 3, ni = cell & 7;
+            const int64_t kr = k0 + k_local;
+            const int64_t c0 = n0 + ni * 8;
+            uint32_t bits = 0;
+            if (kr < k && c0 < n) {
+                const uint32_t word = __ldg(packed + kr * wpr + (c0 >> 5));
+                bits = (word >> (c0 & 31)) & 0xffu;
+                if (c0 + 8 > n) bits &= (1u << (n - c0)) - 1u;
+            }
+            uint32_t v[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+                v[q] = ((bits >> (2 * q)) & 1u ? 0x3f80u : 0u) | ((bits >> (2 * q + 1)) & 1u ? 0x3f800000u : 0u);
+            const uint32_t off = (uint32_t)(((k_local >> 3) * 8 + ni) * 128 + (k_local & 7) * 16);
+            *reinterpret_cast<uint4*>(sB + off) = make_uint4(v[0], v[1], v[2], v[3]);
+        }
+        // generic-proxy writes -> visible to the tensor core (async proxy)
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        __syncthreads();
+        if (tid == 0) {
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const uint32_t a0 = smem_u32(sA), b0 = smem_u32(sB);
+#pragma unroll
+            for (int ks = 0; ks < TC_BK / 16; ++ks) {
+                const uint64_t bd = umma_desc(b0 + ks * 2 * TC_B_LBO, TC_B_LBO, TC_B_SBO);
+#pragma unroll
+                for (int p = 0; p < 3; ++p) {
+                    const uint64_t ad = umma_desc(a0 + p * TC_A_PLANE + ks * 2 * TC_A_LBO, TC_A_LBO, TC_A_SBO);
+                    umma_bf16(tmem_d, ad, bd, (n_issued > 0 || ks > 0 || p > 0) ? 1u : 0u);
+                }
+            }
+            umma_commit(&empty_bar[stage]);     // arrives when these MMAs have finished reading smem
+        }
+        ++n_issued;
+        kb = kb_next;
+#pragma unroll
+        for (int i = 0; i < TC_ITEMS; ++i) cur[i] = nxt[i];
+    }
+
+    // ---- drain + epilogue ---------------------------------------------------------------------
+    if (n_issued > 0) {
+        if (tid == 0) umma_commit(&done_bar);
+        mbar_wait(&done_bar, 0);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        // warp w reads TMEM lanes 32*(w%4)..+31 (its rows) and columns 32*(w/4)..+31
+        const int row_q = warp & 3, col_h = warp >> 2;
+        uint32_t r[32];
+        const uint32_t taddr = tmem_d + ((uint32_t)(row_q * 32) << 16) + (uint32_t)(col_h * 32);
+        asm volatile(
+            "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+            "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+            "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+            : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+              "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+              "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+              "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+            : "r"(taddr)
+            : "memory");
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        const int64_t row = m0 + row_q * 32 + lane;
+        if (row < m) {
+            float* o = out + row * n + n0 + col_h * 32;
+#pragma unroll
+            for (int c = 0; c < 32; ++c) {
+                if (n0 + col_h * 32 + c >= n) break;
+                const float v = __uint_as_float(r[c]);
+                if (split_k > 1) { if (v != 0.0f) atomicAdd(o + c, v); }
+                else o[c] = v;
+            }
+        }
+    } else if (split_k == 1) {
+        // nothing fired in this tile: the result is zero
+        for (int e = tid; e < TC_BM * TC_BN; e += TC_THREADS) {
+            const int64_t row = m0 + e / TC_BN, col = n0 + e % TC_BN;
+            if (row < m && col < n) out[row * n + col] = 0.0f;
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 0)
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_d), "n"(TC_BN) : "memory");
+}
+
+// Host entry used by dense.cu: W [k, m] fp32, packed events [k, wpr] -> out [m, n] fp32.
+int launch_dense_mm_t_tc(const float* W, int64_t k, int64_t m, const uint32_t* packed, int wpr, int64_t n,
+                         float* out, cudaStream_t s) {
+    if (m == 0 || n == 0) return BE_B200_OK;
+    const int total_kb = (int)ceil_div(k, TC_BK);
+    const int64_t tiles = ceil_div(m, TC_BM) * ceil_div(n, TC_BN);
+    int split_k = (int)std::max<int64_t>(1, std::min<int64_t>({(int64_t)total_kb, (6 * kNumSM) / std::max<int64_t>(tiles, 1), (int64_t)32}));
+    const int kb_per_split = (int)ceil_div(std::max(total_kb, 1), split_k);
+    split_k = (int)ceil_div(std::max(total_kb, 1), kb_per_split);
+    if (split_k > 1) BE_CUDA(cudaMemsetAsync(out, 0, (size_t)(m * n) * sizeof(float), s));
+    BE_CUDA(cudaFuncSetAttribute(dense_mm_t_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES));
+    dim3 grid((unsigned)ceil_div(m, TC_BM), (unsigned)split_k, (unsigned)ceil_div(n, TC_BN));
+    {
+        ProfileScope prof(s);
+        dense_mm_t_tc_kernel<<<grid, TC_THREADS, TC_SMEM_BYTES, s>>>(W, k, m, packed, wpr, n, out, kb_per_split, split_k);
+    }
+    BE_LAUNCH_CHECK("dense_mm_t_tc_kernel");
+    return BE_B200_OK;
+}
+
+}  // namespace be

@@ -249,6 +249,22 @@ def test_dense_vs_oracle(G, rows, cols, transpose):
                                        O.binary_densemm(W, B, transpose=transpose), rtol=1e-4, atol=1e-4)
 
 
+@pytest.mark.parametrize("k,m,batch,rate", [(64, 128, 64, 0.3), (4097, 300, 64, 0.05), (1000, 2048, 100, 0.01),
+                                             (3000, 1028, 256, 0.2), (513, 132, 70, 0.5), (8192, 4096, 64, 0.02)])
+def test_dense_tensor_core_path(G, k, m, batch, rate):
+    """binary_densemm(transpose=True) at batch >= 64 runs on tcgen05 with a 3 x bf16 split of the
+    fp32 weights: must still meet the fp32 tolerance (exact products, fp32 accumulation)."""
+    rng = np.random.default_rng(k + m)
+    W = (rng.standard_normal((k, m)) * rng.choice([1e-3, 1.0, 30.0], (k, m))).astype(np.float32)
+    B = cases.spikes(17, k, rate, batch=batch)
+    got = G.binary_densemm(W, B, transpose=True)
+    ref = (W.astype(np.float64).T @ B.astype(np.float64))
+    scale = (np.abs(W).astype(np.float64).T @ B.astype(np.float64))          # sum |w| of each output
+    err = np.abs(got - ref)
+    assert np.all(err <= 1e-5 * np.abs(ref) + 2e-6 * scale + 1e-6), float((err / (scale + 1e-6)).max())
+    np.testing.assert_allclose(got, O.binary_densemm(W, B, transpose=True), rtol=1e-4, atol=1e-3)
+
+
 def test_event_containers_and_classes(G):
     import brainevent_b200 as be
     c = cases.csr_case(21, 3000, 2500, 40, 0.1)
