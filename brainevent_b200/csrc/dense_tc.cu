@@ -24,17 +24,16 @@
 
 namespace be {
 
-constexpr int TC_BM = 128, TC_BN = 64, TC_BK = 32, TC_THREADS = 256, TC_STAGES = 2;
+constexpr int TC_BM = 128, TC_BK = 32, TC_THREADS = 256, TC_STAGES = 2;   // BN (batch tile) is a template parameter: 64 / 128 / 256
 constexpr int TC_A_PLANE = TC_BM * TC_BK * 2;            // 8 KB: one bf16 plane of the A tile
-constexpr int TC_B_TILE = TC_BN * TC_BK * 2;             // 4 KB
 constexpr int TC_ITEMS = (TC_BK / 8) * 8 / 8;            // [8 k x 16 m] load items per warp per k-block
-constexpr int TC_STAGE_BYTES = 3 * TC_A_PLANE + TC_B_TILE;
-constexpr int TC_SMEM_BYTES = TC_STAGES * TC_STAGE_BYTES + 1024;
+__host__ __device__ constexpr int tc_stage_bytes(int bn) { return 3 * TC_A_PLANE + bn * TC_BK * 2; }
+__host__ __device__ constexpr int tc_smem_bytes(int bn) { return TC_STAGES * tc_stage_bytes(bn) + 1024; }
 
 // canonical MN-major, no swizzle: core matrix = 8 (K) rows x 16 B (8 bf16 along MN), 128 B each.
 // A: core (mi, kk) at (kk * 16 + mi) * 128  -> SBO (MN step) = 128 B, LBO (K step) = 2048 B
-// B: core (ni, kk) at (kk *  8 + ni) * 128  -> SBO = 128 B, LBO = 1024 B
-constexpr uint32_t TC_A_SBO = 128, TC_A_LBO = 16 * 128, TC_B_SBO = 128, TC_B_LBO = 8 * 128;
+// B: core (ni, kk) at (kk * BN/8 + ni) * 128  -> SBO = 128 B, LBO = BN/8 * 128 B
+constexpr uint32_t TC_A_SBO = 128, TC_A_LBO = 16 * 128, TC_B_SBO = 128;
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -47,9 +46,11 @@ __device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t lbo, uint
     return d;                 // base_offset 0, lbo_mode 0, layout_type 0 (SWIZZLE_NONE)
 }
 
-// kind::f16 instruction descriptor: D=f32, A=B=bf16, both MN-major, M=128, N=64
-constexpr uint32_t TC_IDESC = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) |
-                              ((uint32_t)(TC_BN >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
+// kind::f16 instruction descriptor: D=f32, A=B=bf16, both MN-major, M=128, N=bn
+__host__ __device__ constexpr uint32_t tc_idesc(int bn) {
+    return (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(bn >> 3) << 17) |
+           ((uint32_t)(TC_BM >> 4) << 24);
+}
 
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
@@ -71,12 +72,12 @@ __device__ __forceinline__ void umma_commit(uint64_t* bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
                  : "memory");
 }
-__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t accumulate) {
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
         "setp.ne.b32 p, %4, 0;\n\t"
         "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d), "l"(adesc), "l"(bdesc),
-        "r"(TC_IDESC), "r"(accumulate)
+        "r"(idesc), "r"(accumulate)
         : "memory");
 }
 
@@ -84,7 +85,8 @@ __device__ __forceinline__ uint32_t pack_bf16(__nv_bfloat16 a, __nv_bfloat16 b) 
     return (uint32_t)__bfloat16_as_ushort(a) | ((uint32_t)__bfloat16_as_ushort(b) << 16);
 }
 
-__global__ void __launch_bounds__(TC_THREADS, 3)
+template <int TC_BN>
+__global__ void __launch_bounds__(TC_THREADS, (TC_BN == 64) ? 3 : 2)
 dense_mm_t_tc_kernel(const float* __restrict__ W, int64_t k, int64_t m, const uint32_t* __restrict__ packed, int wpr,
                      int64_t n, float* __restrict__ out, int kb_per_split, int split_k) {
     extern __shared__ __align__(1024) uint8_t smem[];
@@ -92,6 +94,9 @@ dense_mm_t_tc_kernel(const float* __restrict__ W, int64_t k, int64_t m, const ui
     __shared__ uint64_t done_bar;
     __shared__ uint32_t tmem_base_s;
 
+    constexpr int TC_STAGE_BYTES = tc_stage_bytes(TC_BN);
+    constexpr uint32_t TC_B_LBO = (TC_BN / 8) * 128;
+    constexpr int WPT = TC_BN / 32;                    // spike words per source row in this tile
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int64_t m0 = (int64_t)blockIdx.x * TC_BM;
     const int64_t n0 = (int64_t)blockIdx.z * TC_BN;
@@ -120,9 +125,9 @@ dense_mm_t_tc_kernel(const float* __restrict__ W, int64_t k, int64_t m, const ui
     auto find_next = [&](int kb) {
         for (; kb < kb_end; ++kb) {
             uint32_t my_word = 0;
-            if (tid < 2 * TC_BK) {
-                const int64_t kr = (int64_t)kb * TC_BK + (tid >> 1);
-                const int w = (int)(n0 >> 5) + (tid & 1);
+            if (tid < WPT * TC_BK) {
+                const int64_t kr = (int64_t)kb * TC_BK + (tid / WPT);
+                const int w = (int)(n0 >> 5) + (tid % WPT);
                 if (kr < k && w < wpr) my_word = __ldg(packed + kr * wpr + w);
                 const int64_t cbase = (int64_t)w * 32;
                 if (cbase + 32 > n) my_word &= (n > cbase) ? ((1u << (n - cbase)) - 1u) : 0u;
@@ -187,8 +192,8 @@ dense_mm_t_tc_kernel(const float* __restrict__ W, int64_t k, int64_t m, const ui
             *reinterpret_cast<uint2*>(sA + 2 * TC_A_PLANE + off) = make_uint2(pack_bf16(lo[0], lo[1]), pack_bf16(lo[2], lo[3]));
         }
         // ---- B: 0/1 bf16 from the spike bits: TC_BK x 8 (k, n-octet) cells ------------------------
-        for (int cell = tid; cell < TC_BK * 8; cell += TC_THREADS) {
-            const int k_local = cell >> 3, ni = cell & 7;
+        for (int cell = tid; cell < TC_BK * (TC_BN / 8); cell += TC_THREADS) {
+            const int k_local = cell / (TC_BN / 8), ni = cell % (TC_BN / 8);
             const int64_t kr = k0 + k_local;
             const int64_t c0 = n0 + ni * 8;
             uint32_t bits = 0;
@@ -201,7 +206,7 @@ dense_mm_t_tc_kernel(const float* __restrict__ W, int64_t k, int64_t m, const ui
 #pragma unroll
             for (int q = 0; q < 4; ++q)
                 v[q] = ((bits >> (2 * q)) & 1u ? 0x3f80u : 0u) | ((bits >> (2 * q + 1)) & 1u ? 0x3f800000u : 0u);
-            const uint32_t off = (uint32_t)(((k_local >> 3) * 8 + ni) * 128 + (k_local & 7) * 16);
+            const uint32_t off = (uint32_t)(((k_local >> 3) * (TC_BN / 8) + ni) * 128 + (k_local & 7) * 16);
             *reinterpret_cast<uint4*>(sB + off) = make_uint4(v[0], v[1], v[2], v[3]);
         }
         // generic-proxy writes -> visible to the tensor core (async proxy)
@@ -216,7 +221,7 @@ dense_mm_t_tc_kernel(const float* __restrict__ W, int64_t k, int64_t m, const ui
 #pragma unroll
                 for (int p = 0; p < 3; ++p) {
                     const uint64_t ad = umma_desc(a0 + p * TC_A_PLANE + ks * 2 * TC_A_LBO, TC_A_LBO, TC_A_SBO);
-                    umma_bf16(tmem_d, ad, bd, (n_issued > 0 || ks > 0 || p > 0) ? 1u : 0u);
+                    umma_bf16(tmem_d, ad, bd, tc_idesc(TC_BN), (n_issued > 0 || ks > 0 || p > 0) ? 1u : 0u);
                 }
             }
             umma_commit(&empty_bar[stage]);     // arrives when these MMAs have finished reading smem
@@ -232,30 +237,33 @@ dense_mm_t_tc_kernel(const float* __restrict__ W, int64_t k, int64_t m, const ui
         if (tid == 0) umma_commit(&done_bar);
         mbar_wait(&done_bar, 0);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        // warp w reads TMEM lanes 32*(w%4)..+31 (its rows) and columns 32*(w/4)..+31
-        const int row_q = warp & 3, col_h = warp >> 2;
-        uint32_t r[32];
-        const uint32_t taddr = tmem_d + ((uint32_t)(row_q * 32) << 16) + (uint32_t)(col_h * 32);
-        asm volatile(
-            "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-            "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-            "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-            : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
-              "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
-              "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
-              "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-            : "r"(taddr)
-            : "memory");
-        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        // warp w reads TMEM lanes 32*(w%4)..+31 (its rows); 32-column chunks alternate between
+        // the two warps that share a lane quadrant
+        const int row_q = warp & 3;
         const int64_t row = m0 + row_q * 32 + lane;
-        if (row < m) {
-            float* o = out + row * n + n0 + col_h * 32;
+        for (int ch = warp >> 2; ch < TC_BN / 32; ch += 2) {
+            uint32_t r[32];
+            const uint32_t taddr = tmem_d + ((uint32_t)(row_q * 32) << 16) + (uint32_t)(ch * 32);
+            asm volatile(
+                "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+                "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+                "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+                : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+                  "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+                  "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+                  "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+                : "r"(taddr)
+                : "memory");
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+            if (row < m) {
+                float* o = out + row * n + n0 + ch * 32;
 #pragma unroll
-            for (int c = 0; c < 32; ++c) {
-                if (n0 + col_h * 32 + c >= n) break;
-                const float v = __uint_as_float(r[c]);
-                if (split_k > 1) { if (v != 0.0f) atomicAdd(o + c, v); }
-                else o[c] = v;
+                for (int c = 0; c < 32; ++c) {
+                    if (n0 + ch * 32 + c >= n) break;
+                    const float v = __uint_as_float(r[c]);
+                    if (split_k > 1) { if (v != 0.0f) atomicAdd(o + c, v); }
+                    else o[c] = v;
+                }
             }
         }
     } else if (split_k == 1) {
@@ -275,18 +283,25 @@ dense_mm_t_tc_kernel(const float* __restrict__ W, int64_t k, int64_t m, const ui
 int launch_dense_mm_t_tc(const float* W, int64_t k, int64_t m, const uint32_t* packed, int wpr, int64_t n,
                          float* out, cudaStream_t s) {
     if (m == 0 || n == 0) return BE_B200_OK;
+    // widest batch tile that the batch fills: W is read once per batch tile
+    const int bn = n > 128 ? 256 : (n > 64 ? 128 : 64);
     const int total_kb = (int)ceil_div(k, TC_BK);
-    const int64_t tiles = ceil_div(m, TC_BM) * ceil_div(n, TC_BN);
+    const int64_t tiles = ceil_div(m, TC_BM) * ceil_div(n, bn);
     int split_k = (int)std::max<int64_t>(1, std::min<int64_t>({(int64_t)total_kb, (6 * kNumSM) / std::max<int64_t>(tiles, 1), (int64_t)32}));
     const int kb_per_split = (int)ceil_div(std::max(total_kb, 1), split_k);
     split_k = (int)ceil_div(std::max(total_kb, 1), kb_per_split);
     if (split_k > 1) BE_CUDA(cudaMemsetAsync(out, 0, (size_t)(m * n) * sizeof(float), s));
-    BE_CUDA(cudaFuncSetAttribute(dense_mm_t_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES));
-    dim3 grid((unsigned)ceil_div(m, TC_BM), (unsigned)split_k, (unsigned)ceil_div(n, TC_BN));
-    {
-        ProfileScope prof(s);
-        dense_mm_t_tc_kernel<<<grid, TC_THREADS, TC_SMEM_BYTES, s>>>(W, k, m, packed, wpr, n, out, kb_per_split, split_k);
-    }
+#define BE_TC_LAUNCH(BN)                                                                                       \
+    do {                                                                                                       \
+        BE_CUDA(cudaFuncSetAttribute(dense_mm_t_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,   \
+                                     tc_smem_bytes(BN)));                                                      \
+        dim3 grid((unsigned)ceil_div(m, TC_BM), (unsigned)split_k, (unsigned)ceil_div(n, BN));                 \
+        ProfileScope prof(s);                                                                                  \
+        dense_mm_t_tc_kernel<BN><<<grid, TC_THREADS, tc_smem_bytes(BN), s>>>(W, k, m, packed, wpr, n, out,     \
+                                                                            kb_per_split, split_k);           \
+    } while (0)
+    if (bn == 64) BE_TC_LAUNCH(64); else if (bn == 128) BE_TC_LAUNCH(128); else BE_TC_LAUNCH(256);
+#undef BE_TC_LAUNCH
     BE_LAUNCH_CHECK("dense_mm_t_tc_kernel");
     return BE_B200_OK;
 }
