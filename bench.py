@@ -243,6 +243,62 @@ class CsrSpmm(Workload):
                                     transpose=True)
 
 
+class CsrMv1M(Workload):
+    """1M x 1M CSR, 100 nnz/row matvec (configs[2] structure): scatter `spk @ csr` or the
+    deterministic post-major gather `csr @ spk`."""
+    name = "csr_1m_matvec"
+
+    def __init__(self, torch, be, device, gather, homo=False, rate=0.01):
+        self.be = be
+        n, nnz = 1_000_000, 100
+        g = torch.Generator(device=device).manual_seed(7)
+        self.n = n
+        self.gather = gather
+        self.indptr = torch.arange(0, (n + 1) * nnz, nnz, device=device, dtype=torch.int32)
+        self.indices = torch.randint(0, n, (n * nnz,), device=device, dtype=torch.int32, generator=g)
+        self.weights = torch.tensor([0.5], device=device) if homo else torch.randn(n * nnz, device=device, generator=g)
+        self.pool = spike_pool(torch, n, rate, 5, device)
+        act = float(self.pool.sum(1).double().mean().item())
+        self.events_per_timestep = act * nnz
+        if gather:
+            self.dominant_kernel = "gather_mv_kernel"
+            self.bytes_per_event = 0.0
+            # whole index stream + output + packed spikes; hetero adds the weight quads actually touched
+            touched = 0.0 if homo else 4.0 * n * nnz * (1.0 - (1.0 - rate) ** 4)
+            self.extra_bytes_per_timestep = 4.0 * n * nnz + 4.0 * n + n / 8 + touched
+        else:
+            self.dominant_kernel = "scatter_mv_kernel"
+            self.bytes_per_event = 4.0 if homo else 8.0
+            self.extra_bytes_per_timestep = 12.0 * act
+        self.config = {"workload": f"{'csr @ spk (post-major gather)' if gather else 'spk @ csr (scatter)'}: 1M x 1M CSR, "
+                                   f"100 nnz/row, {'homogeneous' if homo else 'fp32 hetero'} weights, {rate:.0%} spikes "
+                                   "(matvec on the BASELINE configs[2] matrix)"}
+
+    def timestep(self, t):
+        return self.be.binary_csrmv(self.weights, self.indices, self.indptr, self.pool[t % POOL], shape=(self.n, self.n),
+                                    transpose=not self.gather)
+
+
+class DenseMm(Workload):
+    """BinaryArray @ dense at batch 64: the tcgen05 path (3 x bf16 split of the fp32 weights)."""
+    name = "dense_mm_b64"
+    dominant_kernel = "dense_mm_t_tc_kernel"
+
+    def __init__(self, torch, be, device, k=16384, m=16384, batch=64, rate=0.05):
+        self.be = be
+        g = torch.Generator(device=device).manual_seed(3)
+        self.W = torch.randn((k, m), device=device, generator=g)
+        self.pool = torch.rand((4, k, batch), device=device, generator=g) < rate
+        self.events_per_timestep = float(self.pool.sum((1, 2)).double().mean().item()) * m
+        self.bytes_per_event = 0.0
+        self.extra_bytes_per_timestep = 4.0 * k * m + 4.0 * m * batch      # W streamed once + output
+        self.config = {"workload": f"BinaryArray[{batch},{k}] @ dense W[{k},{m}] fp32, {rate:.0%} spikes "
+                                   "(binary_densemm transpose=True on tcgen05; events = active (source, column) pairs x m)"}
+
+    def timestep(self, t):
+        return self.be.binary_densemm(self.W, self.pool[t % 4], transpose=True)
+
+
 class Jitc1M(Workload):
     name = "jitc_normal_1m"
     bytes_per_event = 8.0
@@ -543,10 +599,14 @@ def main():
                      lambda: CubaJitc(torch, be, device, corder=False),
                      lambda: Jitc1M(torch, be, device, corder=True),
                      lambda: Jitc1M(torch, be, device, corder=False),
-                     lambda: CsrSpmm(torch, be, device)):
+                     lambda: CsrMv1M(torch, be, device, gather=False),
+                     lambda: CsrMv1M(torch, be, device, gather=True, homo=True),
+                     lambda: CsrMv1M(torch, be, device, gather=True, homo=False),
+                     lambda: CsrSpmm(torch, be, device),
+                     lambda: DenseMm(torch, be, device)):
             try:
                 w2 = make()
-                heavy = isinstance(w2, CsrSpmm) or (isinstance(w2, Jitc1M) and not w2.corder)
+                heavy = isinstance(w2, (CsrSpmm, DenseMm)) or (isinstance(w2, Jitc1M) and not w2.corder)
                 r2 = measure_workload(torch, dist, L, w2, 3 if heavy else 5, 3, 4 if heavy else 50, 1, peak, peak_src)
                 others.append({"workload": w2.config["workload"], "value": r2["value"], "unit": "events/s",
                                "ms_per_timestep": r2["ms_per_step"] / (4 if heavy else 50), "roofline": r2["roofline"]})

@@ -15,7 +15,7 @@
 //  * mm: the connectivity row is read ONCE per call and applied to every batch column
 //    (the reference loops over columns on the host); outputs are [rows, batch] with
 //    batch innermost so one synapse touches one contiguous segment.
-#include "common.cuh"
+#include "conn.cuh"
 
 #include <algorithm>
 #include <type_traits>
@@ -24,35 +24,6 @@ namespace be {
 
 constexpr int kHeavyRow = 8192;   // rows longer than this are processed by the whole CTA
 constexpr int kHeavyCap = 32;     // deferred heavy rows per CTA before falling back to the warp
-
-// ------------------------------------------------------------------------------------------
-// row accessors
-// ------------------------------------------------------------------------------------------
-template <typename PT>
-struct CsrRows {
-    const PT* indptr;
-    __device__ __forceinline__ void get(int64_t r, int64_t& s, int64_t& e) const {
-        s = (int64_t)__ldg(indptr + r);
-        e = (int64_t)__ldg(indptr + r + 1);
-    }
-};
-struct FcnRows {
-    int64_t n_conn;
-    __device__ __forceinline__ void get(int64_t r, int64_t& s, int64_t& e) const {
-        s = r * n_conn;
-        e = s + n_conn;
-    }
-};
-
-template <typename T, bool HOMO, int PERM>
-__device__ __forceinline__ typename Acc<T>::type weight_at(const T* __restrict__ w,
-                                                           const void* __restrict__ perm,
-                                                           int64_t j, typename Acc<T>::type w0) {
-    if (HOMO) return w0;
-    if (PERM == 1) return to_acc<T>(__ldg(w + __ldg((const int32_t*)perm + j)));
-    if (PERM == 2) return to_acc<T>(__ldg(w + __ldg((const int64_t*)perm + j)));
-    return to_acc<T>(__ldg(w + j));
-}
 
 // ------------------------------------------------------------------------------------------
 // scatter, matvec:  out[indices[j]] += w[j]  for j in rows of active sources
@@ -146,75 +117,6 @@ __global__ void __launch_bounds__(256) scatter_mv_kernel(Rows rows, const int32_
         int64_t s, e;
         rows.get(s_heavy[h], s, e);
         scatter_segment<T, HOMO, PERM, VEC, 256>(s, e, threadIdx.x, indices, weights, perm, w0, out);
-    }
-}
-
-// ------------------------------------------------------------------------------------------
-// gather, matvec:  out[i] = sum_j w[j] * bit(indices[j])   (all rows, deterministic)
-// ------------------------------------------------------------------------------------------
-template <typename T, bool HOMO, int PERM, bool VEC, int LPR, typename Rows>
-__global__ void __launch_bounds__(256) gather_mv_kernel(Rows rows, const int32_t* __restrict__ indices,
-                                                        const T* __restrict__ weights,
-                                                        const void* __restrict__ perm,
-                                                        const uint32_t* __restrict__ packed,
-                                                        int64_t n_rows, T* __restrict__ out) {
-    using A = typename Acc<T>::type;
-    const A w0 = HOMO ? to_acc<T>(__ldg(weights)) : A(0);
-    constexpr int GROUPS = 256 / LPR;
-    const int g = threadIdx.x / LPR, gl = threadIdx.x % LPR;
-    const int64_t row_iters = ceil_div(n_rows, (int64_t)gridDim.x * GROUPS);
-    for (int64_t it = 0; it < row_iters; ++it) {
-        const int64_t r = (it * gridDim.x + blockIdx.x) * GROUPS + g;
-        A acc = A(0);
-        int cnt = 0;
-        if (r < n_rows) {
-            int64_t s, e;
-            rows.get(r, s, e);
-            int64_t a = s, aend = s;
-            if (VEC) {
-                a = (s + 3) & ~(int64_t)3;
-                if (a > e) a = e;
-                aend = a + ((e - a) & ~(int64_t)3);
-                if (gl < a - s && bit_test(packed, __ldg(indices + s + gl))) {
-                    if (HOMO) ++cnt; else acc += weight_at<T, HOMO, PERM>(weights, perm, s + gl, w0);
-                }
-#pragma unroll 2
-                for (int64_t j = a + (int64_t)gl * 4; j < aend; j += (int64_t)LPR * 4) {
-                    int4 ix = ldg_stream((const int4*)(indices + j));
-                    bool b0 = bit_test(packed, ix.x), b1 = bit_test(packed, ix.y),
-                         b2 = bit_test(packed, ix.z), b3 = bit_test(packed, ix.w);
-                    if (HOMO) cnt += (int)b0 + (int)b1 + (int)b2 + (int)b3;
-                    else if (b0 | b1 | b2 | b3) {
-                        if (PERM == 0) {
-                            Vec4<T> v = load4(weights + j);
-                            acc += (b0 ? v.v[0] : A(0)) + (b1 ? v.v[1] : A(0)) + (b2 ? v.v[2] : A(0)) + (b3 ? v.v[3] : A(0));
-                        } else {
-                            if (b0) acc += weight_at<T, HOMO, PERM>(weights, perm, j, w0);
-                            if (b1) acc += weight_at<T, HOMO, PERM>(weights, perm, j + 1, w0);
-                            if (b2) acc += weight_at<T, HOMO, PERM>(weights, perm, j + 2, w0);
-                            if (b3) acc += weight_at<T, HOMO, PERM>(weights, perm, j + 3, w0);
-                        }
-                    }
-                }
-                if (gl < e - aend && bit_test(packed, __ldg(indices + aend + gl))) {
-                    if (HOMO) ++cnt; else acc += weight_at<T, HOMO, PERM>(weights, perm, aend + gl, w0);
-                }
-            } else {
-                for (int64_t j = s + gl; j < e; j += LPR)
-                    if (bit_test(packed, __ldg(indices + j))) {
-                        if (HOMO) ++cnt; else acc += weight_at<T, HOMO, PERM>(weights, perm, j, w0);
-                    }
-            }
-        }
-        if (HOMO) {
-#pragma unroll
-            for (int o = LPR / 2; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
-            acc = w0 * (A)cnt;
-        } else {
-#pragma unroll
-            for (int o = LPR / 2; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-        }
-        if (gl == 0 && r < n_rows) out[r] = from_acc<T>(acc);
     }
 }
 
@@ -351,78 +253,8 @@ __global__ void __launch_bounds__(256) scatter_mm_bm_kernel(Rows rows, const int
 }
 
 // ------------------------------------------------------------------------------------------
-// gather, matmat: out[i, c] = sum_j w[j] * bit(B[indices[j], c]); lanes = columns,
-// CPL columns per lane (batch tile of 32*CPL columns per pass).
-// ------------------------------------------------------------------------------------------
-template <typename T, bool HOMO, int PERM, int CPL, typename Rows>
-__global__ void __launch_bounds__(256) gather_mm_kernel(Rows rows, const int32_t* __restrict__ indices,
-                                                        const T* __restrict__ weights,
-                                                        const void* __restrict__ perm,
-                                                        const uint32_t* __restrict__ packed, int wpr,
-                                                        int64_t n_rows, int64_t n, T* __restrict__ out) {
-    using A = typename Acc<T>::type;
-    const A w0 = HOMO ? to_acc<T>(__ldg(weights)) : A(0);
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int n_pass = (wpr + CPL - 1) / CPL;
-    for (int64_t r = (int64_t)blockIdx.x * 8 + warp; r < n_rows; r += (int64_t)gridDim.x * 8) {
-        int64_t s, e;
-        rows.get(r, s, e);
-        for (int pass = 0; pass < n_pass; ++pass) {
-            const int wb = pass * CPL;
-            A acc[CPL];
-#pragma unroll
-            for (int q = 0; q < CPL; ++q) acc[q] = A(0);
-            for (int64_t j0 = s; j0 < e; j0 += 32) {
-                const int64_t j = j0 + lane;
-                uint32_t mw[CPL];
-                A my_w = A(0);
-                bool nz = false;
-#pragma unroll
-                for (int q = 0; q < CPL; ++q) mw[q] = 0u;
-                if (j < e) {
-                    const uint32_t* brow = packed + (int64_t)__ldg(indices + j) * wpr + wb;
-#pragma unroll
-                    for (int q = 0; q < CPL; ++q) {
-                        mw[q] = (wb + q < wpr) ? __ldg(brow + q) : 0u;
-                        nz |= (mw[q] != 0u);
-                    }
-                    if (nz) my_w = weight_at<T, HOMO, PERM>(weights, perm, j, w0);
-                }
-                uint32_t live = __ballot_sync(0xffffffffu, nz);
-                while (live) {
-                    const int t = __ffs(live) - 1;
-                    live &= live - 1;
-                    const A wv = __shfl_sync(0xffffffffu, my_w, t);
-#pragma unroll
-                    for (int q = 0; q < CPL; ++q) {
-                        const uint32_t m = __shfl_sync(0xffffffffu, mw[q], t);
-                        if ((m >> lane) & 1u) acc[q] += wv;
-                    }
-                }
-            }
-#pragma unroll
-            for (int q = 0; q < CPL; ++q) {
-                const int64_t c = (int64_t)(wb + q) * 32 + lane;
-                if (c < n) out[r * n + c] = from_acc<T>(acc[q]);
-            }
-        }
-    }
-}
-
-// ------------------------------------------------------------------------------------------
 // launch helpers
 // ------------------------------------------------------------------------------------------
-static inline bool al16(const void* p) { return ((uintptr_t)p & 15u) == 0; }
-
-struct ConnArgs {
-    const void* weights;
-    int w_dtype, homo;
-    const int32_t* indices;
-    const void* perm;
-    int perm_kind;  // 0 none, 1 int32, 2 int64
-    double avg_row;  // mean synapses per row (launch-shape heuristic only)
-};
-
 template <typename T, bool HOMO, int PERM, typename Rows>
 static int launch_scatter_mv(const Rows& rows, const ConnArgs& c, const Events& ev, int64_t n_src,
                              T* out, cudaStream_t s) {
@@ -440,28 +272,6 @@ static int launch_scatter_mv(const Rows& rows, const ConnArgs& c, const Events& 
     }
 #undef BE_SC
     BE_LAUNCH_CHECK("scatter_mv_kernel");
-    return BE_B200_OK;
-}
-
-template <typename T, bool HOMO, int PERM, typename Rows>
-static int launch_gather_mv(const Rows& rows, const ConnArgs& c, const Events& ev, int64_t n_rows,
-                            T* out, cudaStream_t s) {
-    if (n_rows == 0) return BE_B200_OK;
-    const bool vec = al16(c.indices) && (c.homo || al16(c.weights));
-    const int lpr = c.avg_row <= 12 ? 4 : (c.avg_row <= 48 ? 8 : (c.avg_row <= 160 ? 16 : 32));
-    int blocks = (int)std::min<int64_t>(ceil_div(n_rows, 256 / lpr), (int64_t)kNumSM * 16);
-#define BE_GA(VEC, LPR)                                                                      \
-    gather_mv_kernel<T, HOMO, PERM, VEC, LPR, Rows><<<blocks, 256, 0, s>>>(                  \
-        rows, c.indices, (const T*)c.weights, c.perm, ev.packed, n_rows, out)
-#define BE_GA2(VEC) switch (lpr) { case 4: BE_GA(VEC, 4); break; case 8: BE_GA(VEC, 8); break; \
-                                   case 16: BE_GA(VEC, 16); break; default: BE_GA(VEC, 32); }
-    {
-        ProfileScope prof(s);
-        if (vec) { BE_GA2(true) } else { BE_GA2(false) }
-    }
-#undef BE_GA2
-#undef BE_GA
-    BE_LAUNCH_CHECK("gather_mv_kernel");
     return BE_B200_OK;
 }
 
@@ -516,27 +326,9 @@ static int launch_scatter_mm_bm(const Rows& rows, const ConnArgs& c, const Event
     return BE_B200_OK;
 }
 
-template <typename T, bool HOMO, int PERM, typename Rows>
-static int launch_gather_mm(const Rows& rows, const ConnArgs& c, const Events& ev, int64_t n_rows,
-                            int64_t n, T* out, cudaStream_t s) {
-    if (n_rows == 0) return BE_B200_OK;
-    int blocks = (int)std::min<int64_t>(ceil_div(n_rows, 8), (int64_t)kNumSM * 16);
-    const int wpr = ev.words_per_row;
-#define BE_GM(CPL)                                                                           \
-    gather_mm_kernel<T, HOMO, PERM, CPL, Rows><<<blocks, 256, 0, s>>>(                       \
-        rows, c.indices, (const T*)c.weights, c.perm, ev.packed, wpr, n_rows, n, out)
-    {
-        ProfileScope prof(s);
-        if (wpr == 1) BE_GM(1); else if (wpr == 2) BE_GM(2); else BE_GM(4);
-    }
-#undef BE_GM
-    BE_LAUNCH_CHECK("gather_mm_kernel");
-    return BE_B200_OK;
-}
-
 // One entry for all four shapes.  n == 0 means matvec.
 template <typename T, typename Rows>
-static int run_conn(const Rows& rows, const ConnArgs& c, const void* spikes, const void* aux,
+static int run_conn(const Rows& rows, const RowsDesc& rd, const ConnArgs& c, const void* spikes, const void* aux,
                     int spk_kind, int64_t n_src, int64_t n_rows, int64_t n_out, int64_t n_batch,
                     bool scatter, void* out_v, void* workspace, size_t workspace_bytes,
                     cudaStream_t s, bool batch_major = false) {
@@ -558,11 +350,10 @@ static int run_conn(const Rows& rows, const ConnArgs& c, const void* spikes, con
 #define BE_RUN(HOMO, PERM)                                                                              \
     do {                                                                                                \
         if (scatter && mm && batch_major) return launch_scatter_mm_bm<T, HOMO, PERM, Rows>(rows, c, ev, n_src, n_out, n_batch, out, s); \
-        if (scatter) return mm ? launch_scatter_mm<T, HOMO, PERM, Rows>(rows, c, ev, n_src, n_out, n_batch, out, s) \
-                               : launch_scatter_mv<T, HOMO, PERM, Rows>(rows, c, ev, n_src, out, s);         \
-        return mm ? launch_gather_mm<T, HOMO, PERM, Rows>(rows, c, ev, n_rows, n_batch, out, s)              \
-                  : launch_gather_mv<T, HOMO, PERM, Rows>(rows, c, ev, n_rows, out, s);                      \
+        return mm ? launch_scatter_mm<T, HOMO, PERM, Rows>(rows, c, ev, n_src, n_out, n_batch, out, s)       \
+                  : launch_scatter_mv<T, HOMO, PERM, Rows>(rows, c, ev, n_src, out, s);                      \
     } while (0)
+    if (!scatter) return run_gather(rd, c, ev, n_src, n_rows, n_batch, out, s);
     if (c.homo) BE_RUN(true, 0);
     if constexpr (!std::is_same<Rows, FcnRows>::value) {
         if (c.perm_kind == 1) BE_RUN(false, 1);
@@ -592,10 +383,10 @@ static int csr_entry(const void* weights, int w_dtype, int homo, const int32_t* 
     BE_DISPATCH_WT(w_dtype, T, {
         if (indptr_is64) {
             CsrRows<int64_t> rows{(const int64_t*)indptr};
-            return run_conn<T>(rows, c, spikes, aux, spk_kind, n_src, m, n_out, n, transpose != 0, out, workspace, workspace_bytes, s, out_batch_major != 0);
+            return run_conn<T>(rows, RowsDesc{1, indptr, 0}, c, spikes, aux, spk_kind, n_src, m, n_out, n, transpose != 0, out, workspace, workspace_bytes, s, out_batch_major != 0);
         } else {
             CsrRows<int32_t> rows{(const int32_t*)indptr};
-            return run_conn<T>(rows, c, spikes, aux, spk_kind, n_src, m, n_out, n, transpose != 0, out, workspace, workspace_bytes, s, out_batch_major != 0);
+            return run_conn<T>(rows, RowsDesc{0, indptr, 0}, c, spikes, aux, spk_kind, n_src, m, n_out, n, transpose != 0, out, workspace, workspace_bytes, s, out_batch_major != 0);
         }
     });
     return BE_B200_OK;
@@ -638,7 +429,7 @@ static int fcn_entry(const void* weights, int w_dtype, int homo, const int32_t* 
     ConnArgs c{weights, w_dtype, homo, indices, nullptr, 0, (double)n_conn};
     FcnRows rows{n_conn};
     BE_DISPATCH_WT(w_dtype, T, {
-        return run_conn<T>(rows, c, spikes, aux, spk_kind, n_src, n_rows, n_out, n, transpose != 0, out, workspace, workspace_bytes, s, out_batch_major != 0);
+        return run_conn<T>(rows, RowsDesc{2, nullptr, n_conn}, c, spikes, aux, spk_kind, n_src, n_rows, n_out, n, transpose != 0, out, workspace, workspace_bytes, s, out_batch_major != 0);
     });
     return BE_B200_OK;
 }

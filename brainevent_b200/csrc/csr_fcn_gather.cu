@@ -1,0 +1,260 @@
+// csr_fcn_gather.cu -- deterministic post-major gather through stored connectivity
+// (ref: _csr/binary_csrmv.cu NT, _csr/binary_csrmm.cu NT, FCN gather).  Split from csr_fcn.cu so
+// the two translation units compile in parallel.
+#include "conn.cuh"
+
+#include <algorithm>
+#include <cstdlib>
+#include <type_traits>
+
+namespace be {
+
+// ------------------------------------------------------------------------------------------
+// gather, matvec:  out[i] = sum_j w[j] * bit(indices[j])   (all rows, deterministic)
+//
+// The kernel streams the whole index array once (HBM-bound by construction); what decides
+// whether it reaches the HBM roofline is the cost of the per-synapse random lookup into the
+// bit-packed spike vector.  Through L1 a warp's 32 random addresses cost up to 32 wavefronts, which
+// caps the chip at ~5e11 lookups/s (2 TB/s of int32 indices).  SMEM=true copies the packed vector
+// (n/8 bytes: 125 KB for 1 M neurons) into shared memory once per persistent CTA, where 32 random
+// 4-byte reads cost ~3-4 bank cycles, and runs 1024 threads per SM to keep the streams full.
+// ------------------------------------------------------------------------------------------
+template <typename T, bool HOMO, int PERM, bool VEC, int LPR, bool SMEM, typename Rows>
+__global__ void __launch_bounds__(SMEM ? 1024 : 256) gather_mv_kernel(Rows rows, const int32_t* __restrict__ indices,
+                                                                      const T* __restrict__ weights,
+                                                                      const void* __restrict__ perm,
+                                                                      const uint32_t* __restrict__ packed,
+                                                                      int64_t n_words, int64_t n_rows,
+                                                                      T* __restrict__ out) {
+    using A = typename Acc<T>::type;
+    extern __shared__ __align__(16) uint32_t s_bits[];
+    if (SMEM) {
+        const int64_t n16 = n_words >> 2;
+        for (int64_t i = threadIdx.x; i < n16; i += blockDim.x)
+            reinterpret_cast<int4*>(s_bits)[i] = __ldg(reinterpret_cast<const int4*>(packed) + i);
+        for (int64_t i = (n16 << 2) + threadIdx.x; i < n_words; i += blockDim.x) s_bits[i] = __ldg(packed + i);
+        __syncthreads();
+    }
+    auto bit = [&](int idx) -> bool {
+        const uint32_t w = SMEM ? s_bits[idx >> 5] : __ldg(packed + (idx >> 5));
+        return (w >> (idx & 31)) & 1u;
+    };
+    const A w0 = HOMO ? to_acc<T>(__ldg(weights)) : A(0);
+    const int GROUPS = blockDim.x / LPR;
+    const int g = threadIdx.x / LPR, gl = threadIdx.x % LPR;
+    const int64_t row_stride = (int64_t)gridDim.x * GROUPS;
+    const int64_t row_iters = ceil_div(n_rows, row_stride);
+    int64_t r = (int64_t)blockIdx.x * GROUPS + g;
+    int64_t s_n = 0, e_n = 0;
+    if (r < n_rows) rows.get(r, s_n, e_n);
+    for (int64_t it = 0; it < row_iters; ++it, r += row_stride) {
+        A acc = A(0);
+        int cnt = 0;
+        const int64_t s = s_n, e = e_n;
+        const bool live = r < n_rows;
+        if (r + row_stride < n_rows) rows.get(r + row_stride, s_n, e_n);   // next row's extent in flight
+        if (live) {
+            if (VEC) {
+                int64_t a = (s + 3) & ~(int64_t)3;
+                if (a > e) a = e;
+                const int64_t aend = a + ((e - a) & ~(int64_t)3);
+                if (gl < a - s && bit(__ldg(indices + s + gl))) {
+                    if (HOMO) ++cnt; else acc += weight_at<T, HOMO, PERM>(weights, perm, s + gl, w0);
+                }
+                // 4 independent 128-bit index loads per lane are issued before the first lookup
+                constexpr int U = 4;
+                for (int64_t j0 = a + (int64_t)gl * 4; j0 < aend; j0 += (int64_t)LPR * 4 * U) {
+                    int4 ix[U];
+#pragma unroll
+                    for (int u = 0; u < U; ++u) {
+                        const int64_t j = j0 + (int64_t)u * LPR * 4;
+                        ix[u] = (j < aend) ? ldg_stream((const int4*)(indices + j)) : make_int4(-1, -1, -1, -1);
+                    }
+#pragma unroll
+                    for (int u = 0; u < U; ++u) {
+                        if (ix[u].x < 0) continue;
+                        const int64_t j = j0 + (int64_t)u * LPR * 4;
+                        const bool b0 = bit(ix[u].x), b1 = bit(ix[u].y), b2 = bit(ix[u].z), b3 = bit(ix[u].w);
+                        if (HOMO) cnt += (int)b0 + (int)b1 + (int)b2 + (int)b3;
+                        else if (b0 | b1 | b2 | b3) {
+                            if (PERM == 0) {
+                                Vec4<T> v = load4(weights + j);
+                                acc += (b0 ? v.v[0] : A(0)) + (b1 ? v.v[1] : A(0)) + (b2 ? v.v[2] : A(0)) + (b3 ? v.v[3] : A(0));
+                            } else {
+                                if (b0) acc += weight_at<T, HOMO, PERM>(weights, perm, j, w0);
+                                if (b1) acc += weight_at<T, HOMO, PERM>(weights, perm, j + 1, w0);
+                                if (b2) acc += weight_at<T, HOMO, PERM>(weights, perm, j + 2, w0);
+                                if (b3) acc += weight_at<T, HOMO, PERM>(weights, perm, j + 3, w0);
+                            }
+                        }
+                    }
+                }
+                if (gl < e - aend && bit(__ldg(indices + aend + gl))) {
+                    if (HOMO) ++cnt; else acc += weight_at<T, HOMO, PERM>(weights, perm, aend + gl, w0);
+                }
+            } else {
+                for (int64_t j = s + gl; j < e; j += LPR)
+                    if (bit(__ldg(indices + j))) {
+                        if (HOMO) ++cnt; else acc += weight_at<T, HOMO, PERM>(weights, perm, j, w0);
+                    }
+            }
+        }
+        if (HOMO) {
+#pragma unroll
+            for (int o = LPR / 2; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+            acc = w0 * (A)cnt;
+        } else {
+#pragma unroll
+            for (int o = LPR / 2; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+        }
+        if (gl == 0 && live) out[r] = from_acc<T>(acc);
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// gather, matmat: out[i, c] = sum_j w[j] * bit(B[indices[j], c]); lanes = columns,
+// CPL columns per lane (batch tile of 32*CPL columns per pass).
+// ------------------------------------------------------------------------------------------
+template <typename T, bool HOMO, int PERM, int CPL, typename Rows>
+__global__ void __launch_bounds__(256) gather_mm_kernel(Rows rows, const int32_t* __restrict__ indices,
+                                                        const T* __restrict__ weights,
+                                                        const void* __restrict__ perm,
+                                                        const uint32_t* __restrict__ packed, int wpr,
+                                                        int64_t n_rows, int64_t n, T* __restrict__ out) {
+    using A = typename Acc<T>::type;
+    const A w0 = HOMO ? to_acc<T>(__ldg(weights)) : A(0);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int n_pass = (wpr + CPL - 1) / CPL;
+    for (int64_t r = (int64_t)blockIdx.x * 8 + warp; r < n_rows; r += (int64_t)gridDim.x * 8) {
+        int64_t s, e;
+        rows.get(r, s, e);
+        for (int pass = 0; pass < n_pass; ++pass) {
+            const int wb = pass * CPL;
+            A acc[CPL];
+#pragma unroll
+            for (int q = 0; q < CPL; ++q) acc[q] = A(0);
+            for (int64_t j0 = s; j0 < e; j0 += 32) {
+                const int64_t j = j0 + lane;
+                uint32_t mw[CPL];
+                A my_w = A(0);
+                bool nz = false;
+#pragma unroll
+                for (int q = 0; q < CPL; ++q) mw[q] = 0u;
+                if (j < e) {
+                    const uint32_t* brow = packed + (int64_t)__ldg(indices + j) * wpr + wb;
+#pragma unroll
+                    for (int q = 0; q < CPL; ++q) {
+                        mw[q] = (wb + q < wpr) ? __ldg(brow + q) : 0u;
+                        nz |= (mw[q] != 0u);
+                    }
+                    if (nz) my_w = weight_at<T, HOMO, PERM>(weights, perm, j, w0);
+                }
+                uint32_t live = __ballot_sync(0xffffffffu, nz);
+                while (live) {
+                    const int t = __ffs(live) - 1;
+                    live &= live - 1;
+                    const A wv = __shfl_sync(0xffffffffu, my_w, t);
+#pragma unroll
+                    for (int q = 0; q < CPL; ++q) {
+                        const uint32_t m = __shfl_sync(0xffffffffu, mw[q], t);
+                        if ((m >> lane) & 1u) acc[q] += wv;
+                    }
+                }
+            }
+#pragma unroll
+            for (int q = 0; q < CPL; ++q) {
+                const int64_t c = (int64_t)(wb + q) * 32 + lane;
+                if (c < n) out[r * n + c] = from_acc<T>(acc[q]);
+            }
+        }
+    }
+}
+
+constexpr size_t kGatherSmemMax = 200u << 10;   // packed spikes up to 200 KB (1.6 M sources) go to shared memory
+
+template <typename T, bool HOMO, int PERM, typename Rows>
+static int launch_gather_mv(const Rows& rows, const ConnArgs& c, const Events& ev, int64_t n_src, int64_t n_rows,
+                            T* out, cudaStream_t s) {
+    if (n_rows == 0) return BE_B200_OK;
+    const bool vec = al16(c.indices) && (c.homo || al16(c.weights));
+    const int lpr = c.avg_row <= 24 ? 4 : (c.avg_row <= 192 ? 8 : (c.avg_row <= 640 ? 16 : 32));
+    const int64_t n_words = ceil_div(n_src, 32);
+    const size_t smem = (size_t)n_words * 4;
+    // the shared-memory variant pays for itself when every CTA has enough rows to amortise the copy
+    bool use_smem = vec && al16(ev.packed) && smem <= kGatherSmemMax &&
+                    (double)n_rows * c.avg_row >= 4.0 * (double)n_words * kNumSM;
+    if (const char* e = getenv("BE_B200_GATHER_SMEM")) use_smem = use_smem && e[0] != '0';   // A/B switch
+    ProfileScope prof(s);
+    if (use_smem) {
+        const int blocks = kNumSM;
+#define BE_GAS(LPR)                                                                                           \
+        do {                                                                                                  \
+            BE_CUDA(cudaFuncSetAttribute(gather_mv_kernel<T, HOMO, PERM, true, LPR, true, Rows>,              \
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kGatherSmemMax));  \
+            gather_mv_kernel<T, HOMO, PERM, true, LPR, true, Rows><<<blocks, 1024, smem, s>>>(                \
+                rows, c.indices, (const T*)c.weights, c.perm, ev.packed, n_words, n_rows, out);               \
+        } while (0)
+        switch (lpr) { case 4: BE_GAS(4); break; case 8: BE_GAS(8); break; case 16: BE_GAS(16); break; default: BE_GAS(32); }
+#undef BE_GAS
+    } else {
+        int blocks = (int)std::min<int64_t>(ceil_div(n_rows, 256 / lpr), (int64_t)kNumSM * 16);
+#define BE_GA(VEC, LPR)                                                                      \
+        gather_mv_kernel<T, HOMO, PERM, VEC, LPR, false, Rows><<<blocks, 256, 0, s>>>(       \
+            rows, c.indices, (const T*)c.weights, c.perm, ev.packed, n_words, n_rows, out)
+#define BE_GA2(VEC) switch (lpr) { case 4: BE_GA(VEC, 4); break; case 8: BE_GA(VEC, 8); break; \
+                                   case 16: BE_GA(VEC, 16); break; default: BE_GA(VEC, 32); }
+        if (vec) { BE_GA2(true) } else { BE_GA2(false) }
+#undef BE_GA2
+#undef BE_GA
+    }
+    BE_LAUNCH_CHECK("gather_mv_kernel");
+    return BE_B200_OK;
+}
+
+template <typename T, bool HOMO, int PERM, typename Rows>
+static int launch_gather_mm(const Rows& rows, const ConnArgs& c, const Events& ev, int64_t n_rows,
+                            int64_t n, T* out, cudaStream_t s) {
+    if (n_rows == 0) return BE_B200_OK;
+    int blocks = (int)std::min<int64_t>(ceil_div(n_rows, 8), (int64_t)kNumSM * 16);
+    const int wpr = ev.words_per_row;
+#define BE_GM(CPL)                                                                           \
+    gather_mm_kernel<T, HOMO, PERM, CPL, Rows><<<blocks, 256, 0, s>>>(                       \
+        rows, c.indices, (const T*)c.weights, c.perm, ev.packed, wpr, n_rows, n, out)
+    {
+        ProfileScope prof(s);
+        if (wpr == 1) BE_GM(1); else if (wpr == 2) BE_GM(2); else BE_GM(4);
+    }
+#undef BE_GM
+    BE_LAUNCH_CHECK("gather_mm_kernel");
+    return BE_B200_OK;
+}
+
+
+template <typename T, typename Rows>
+static int run_gather_t(const Rows& rows, const ConnArgs& c, const Events& ev, int64_t n_src, int64_t n_rows,
+                        int64_t n_batch, T* out, cudaStream_t s) {
+    const bool mm = n_batch > 0;
+#define BE_RUNG(HOMO, PERM)                                                                         \
+    return mm ? launch_gather_mm<T, HOMO, PERM, Rows>(rows, c, ev, n_rows, n_batch, out, s)          \
+              : launch_gather_mv<T, HOMO, PERM, Rows>(rows, c, ev, n_src, n_rows, out, s)
+    if (c.homo) { BE_RUNG(true, 0); }
+    if constexpr (!std::is_same<Rows, FcnRows>::value) {
+        if (c.perm_kind == 1) { BE_RUNG(false, 1); }
+        if (c.perm_kind == 2) { BE_RUNG(false, 2); }
+    }
+    BE_RUNG(false, 0);
+#undef BE_RUNG
+}
+
+int run_gather(const RowsDesc& rd, const ConnArgs& c, const Events& ev, int64_t n_src, int64_t n_rows,
+               int64_t n_batch, void* out, cudaStream_t s) {
+    BE_DISPATCH_WT(c.w_dtype, T, {
+        if (rd.kind == 0) { CsrRows<int32_t> rows{(const int32_t*)rd.indptr}; return run_gather_t<T>(rows, c, ev, n_src, n_rows, n_batch, (T*)out, s); }
+        if (rd.kind == 1) { CsrRows<int64_t> rows{(const int64_t*)rd.indptr}; return run_gather_t<T>(rows, c, ev, n_src, n_rows, n_batch, (T*)out, s); }
+        FcnRows rows{rd.n_conn};
+        return run_gather_t<T>(rows, c, ev, n_src, n_rows, n_batch, (T*)out, s);
+    });
+    return BE_B200_OK;
+}
+
+}  // namespace be
