@@ -530,20 +530,39 @@ def main():
         host_spk = [torch.empty(n_in, dtype=torch.uint8).pin_memory() for _ in range(POOL)]
         for i in range(POOL):
             host_spk[i].copy_(wl.pool[i].to(torch.uint8))
-        host_out = torch.empty(n_out, dtype=torch.float32).pin_memory()
+        host_out = [torch.empty(n_out, dtype=torch.float32).pin_memory() for _ in range(2)]
         Te = min(T, 50)
+        sync_value = None
         if world == 1:
             lib = L.lib()
             proj = lib.be_b200_projection_adopt_fcn(ctypes.c_void_p(wl.weights.data_ptr()), 0,
                                                     ctypes.c_void_p(wl.indices.data_ptr()), wl.n_total,
                                                     wl.conn_local, wl.n_local)
             assert proj, lib.be_b200_last_error()
+            proj = ctypes.c_void_p(proj)
 
-            def e2e_step():
+            def e2e_step_sync():
                 for t in range(Te):
                     rc = lib.be_b200_projection_apply_host(proj, ctypes.c_void_p(host_spk[t % POOL].data_ptr()),
-                                                           ctypes.c_void_p(host_out.data_ptr()))
+                                                           ctypes.c_void_p(host_out[0].data_ptr()))
                     assert rc == 0
+
+            def e2e_step():
+                # pipelined C-ABI entry: copy-in / hot path / copy-out of neighbouring timesteps overlap;
+                # every timestep still moves its own inputs in and its own result out
+                for t in range(Te):
+                    rc = lib.be_b200_projection_submit_host(proj, ctypes.c_void_p(host_spk[t % POOL].data_ptr()),
+                                                            ctypes.c_void_p(host_out[t & 1].data_ptr()))
+                    assert rc == 0
+                assert lib.be_b200_projection_wait(proj) == 0
+
+            for _ in range(2):
+                e2e_step_sync()
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            for _ in range(3):
+                e2e_step_sync()
+            sync_value = wl.total_events_per_timestep() * Te * 3 / (time.perf_counter() - t0)
         else:
             d_spk = torch.empty(n_in, dtype=torch.uint8, device=device)
 
@@ -551,7 +570,7 @@ def main():
                 for t in range(Te):
                     d_spk.copy_(host_spk[t % POOL], non_blocking=True)
                     out = wl.proj.step(d_spk)
-                    host_out.copy_(out, non_blocking=True)
+                    host_out[0].copy_(out, non_blocking=True)
                     torch.cuda.current_stream().synchronize()
         for _ in range(2):
             e2e_step()
@@ -572,10 +591,13 @@ def main():
                "note": f"per timestep: pinned host spikes (uint8[{n_in}]) -> device, hot path, fp32[{n_out}] result -> "
                        f"pinned host, stream sync; timed over {Ke}x{Te} timesteps with the host clock, bytes scaled to "
                        f"{T} timesteps/step; entry point: " +
-                       ("be_b200_projection_apply_host (C ABI)" if world == 1 else
+                       ("be_b200_projection_submit_host/_wait (C ABI, 2 calls in flight; `sync_value` is the "
+                        "blocking be_b200_projection_apply_host)" if world == 1 else
                         "PostShardedProjection.step (per rank: its own spike block in, its own output block out)")}
+        if sync_value is not None:
+            e2e["sync_value"] = sync_value
         if world == 1:
-            L.lib().be_b200_projection_destroy(ctypes.c_void_p(proj))
+            L.lib().be_b200_projection_destroy(proj)
 
     if rank != 0:
         if world > 1:

@@ -67,6 +67,8 @@ _SIGNATURES = {
     "be_b200_projection_adopt_fcn": (_P, [_P, _I, _P, _L, _L, _L]),
     "be_b200_projection_create_jitc": (_P, [_I, ctypes.c_float, ctypes.c_float, ctypes.c_int32, ctypes.c_int32, _L, _L, _L, _I]),
     "be_b200_projection_apply_host": (_I, [_P, _P, _P]),
+    "be_b200_projection_submit_host": (_I, [_P, _P, _P]),
+    "be_b200_projection_wait": (_I, [_P]),
     "be_b200_projection_destroy": (None, [_P]),
 }
 

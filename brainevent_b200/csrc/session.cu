@@ -22,6 +22,13 @@ struct be_b200_projection {
     size_t ws_bytes;
     cudaStream_t stream;
     int borrowed;  // connectivity pointers belong to the caller
+    // pipelined submit/wait: two slots of device-side event/output buffers, copy streams either
+    // side of the compute stream so PCIe transfers of neighbouring calls overlap the kernels
+    uint8_t* d_ev2[2];
+    float* d_out2[2];
+    cudaStream_t s_in, s_out;
+    cudaEvent_t ev_in[2], ev_done[2], ev_out[2];
+    int slot, inflight[2];
 };
 
 using namespace be;
@@ -36,6 +43,15 @@ static be_b200_projection* proj_new(int kind, int64_t n_pre, int64_t n_post) {
     ok = ok && cudaMemset(p->d_ws, 0, p->ws_bytes) == cudaSuccess;
     ok = ok && cudaMalloc((void**)&p->d_events, (size_t)std::max<int64_t>(n_pre, 16)) == cudaSuccess;
     ok = ok && cudaMalloc((void**)&p->d_out, (size_t)std::max<int64_t>(n_post, 4) * sizeof(float)) == cudaSuccess;
+    ok = ok && cudaStreamCreateWithFlags(&p->s_in, cudaStreamNonBlocking) == cudaSuccess;
+    ok = ok && cudaStreamCreateWithFlags(&p->s_out, cudaStreamNonBlocking) == cudaSuccess;
+    for (int i = 0; i < 2 && ok; ++i) {
+        ok = ok && cudaMalloc((void**)&p->d_ev2[i], (size_t)std::max<int64_t>(n_pre, 16)) == cudaSuccess;
+        ok = ok && cudaMalloc((void**)&p->d_out2[i], (size_t)std::max<int64_t>(n_post, 4) * sizeof(float)) == cudaSuccess;
+        ok = ok && cudaEventCreateWithFlags(&p->ev_in[i], cudaEventDisableTiming) == cudaSuccess;
+        ok = ok && cudaEventCreateWithFlags(&p->ev_done[i], cudaEventDisableTiming) == cudaSuccess;
+        ok = ok && cudaEventCreateWithFlags(&p->ev_out[i], cudaEventDisableTiming) == cudaSuccess;
+    }
     if (!ok) { set_error("projection: device allocation failed: %s", cudaGetErrorString(cudaGetLastError())); be_b200_projection_destroy(p); return nullptr; }
     return p;
 }
@@ -104,25 +120,57 @@ extern "C" be_b200_projection* be_b200_projection_create_jitc(int jit_kind, floa
     return p;
 }
 
+static int proj_compute(be_b200_projection* p, const uint8_t* d_events, float* d_out, cudaStream_t s) {
+    if (p->kind == 0)
+        return be_b200_binary_csrmv(p->d_weights, BE_B200_F32, p->homo, p->d_indices, p->d_indptr, 0, nullptr, 0,
+                                    d_events, nullptr, BE_B200_SPK_BOOL, p->n_pre, p->n_post, p->nse, 1,
+                                    d_out, p->d_ws, p->ws_bytes, s);
+    if (p->kind == 1)
+        return be_b200_binary_fcnmv(p->d_weights, BE_B200_F32, p->homo, p->d_indices, p->n_pre, p->n_conn,
+                                    d_events, nullptr, BE_B200_SPK_BOOL, p->n_pre, p->n_post, 1, d_out,
+                                    p->d_ws, p->ws_bytes, s);
+    return be_b200_binary_jitmv(p->jit_kind, p->d_p, p->d_p + 1, BE_B200_F32, p->d_clen_seed,
+                                p->d_clen_seed + 1, d_events, nullptr, BE_B200_SPK_BOOL, p->n_pre,
+                                p->n_post, p->chunk_size, p->corder, 0, -1, 0, -1, d_out, p->d_ws,
+                                p->ws_bytes, s);
+}
+
+// Asynchronous variant: returns once the call is enqueued.  Host buffers must be pinned and stay
+// untouched until be_b200_projection_wait() (or the second-next submit) returns; at most two
+// calls are in flight, the third submit first waits for the oldest one.
+extern "C" int be_b200_projection_submit_host(be_b200_projection* p, const uint8_t* events_host,
+                                              float* out_host) {
+    BE_REQUIRE(p && events_host && out_host, "projection_submit_host: NULL pointer");
+    const int i = p->slot;
+    if (p->inflight[i]) { BE_CUDA(cudaEventSynchronize(p->ev_out[i])); p->inflight[i] = 0; }
+    if (p->n_pre > 0) BE_CUDA(cudaMemcpyAsync(p->d_ev2[i], events_host, (size_t)p->n_pre, cudaMemcpyHostToDevice, p->s_in));
+    BE_CUDA(cudaEventRecord(p->ev_in[i], p->s_in));
+    BE_CUDA(cudaStreamWaitEvent(p->stream, p->ev_in[i], 0));
+    int rc = proj_compute(p, p->d_ev2[i], p->d_out2[i], p->stream);
+    if (rc) return rc;
+    BE_CUDA(cudaEventRecord(p->ev_done[i], p->stream));
+    BE_CUDA(cudaStreamWaitEvent(p->s_out, p->ev_done[i], 0));
+    if (p->n_post > 0) BE_CUDA(cudaMemcpyAsync(out_host, p->d_out2[i], (size_t)p->n_post * sizeof(float), cudaMemcpyDeviceToHost, p->s_out));
+    BE_CUDA(cudaEventRecord(p->ev_out[i], p->s_out));
+    p->inflight[i] = 1;
+    p->slot ^= 1;
+    return BE_B200_OK;
+}
+
+// Blocks until every submitted call has delivered its result to host memory.
+extern "C" int be_b200_projection_wait(be_b200_projection* p) {
+    BE_REQUIRE(p, "projection_wait: NULL pointer");
+    for (int i = 0; i < 2; ++i)
+        if (p->inflight[i]) { BE_CUDA(cudaEventSynchronize(p->ev_out[i])); p->inflight[i] = 0; }
+    return BE_B200_OK;
+}
+
 extern "C" int be_b200_projection_apply_host(be_b200_projection* p, const uint8_t* events_host,
                                              float* out_host) {
     BE_REQUIRE(p && events_host && out_host, "projection_apply_host: NULL pointer");
     cudaStream_t s = p->stream;
     if (p->n_pre > 0) BE_CUDA(cudaMemcpyAsync(p->d_events, events_host, (size_t)p->n_pre, cudaMemcpyHostToDevice, s));
-    int rc = BE_B200_OK;
-    if (p->kind == 0)
-        rc = be_b200_binary_csrmv(p->d_weights, BE_B200_F32, p->homo, p->d_indices, p->d_indptr, 0, nullptr, 0,
-                                  p->d_events, nullptr, BE_B200_SPK_BOOL, p->n_pre, p->n_post, p->nse, 1,
-                                  p->d_out, p->d_ws, p->ws_bytes, s);
-    else if (p->kind == 1)
-        rc = be_b200_binary_fcnmv(p->d_weights, BE_B200_F32, p->homo, p->d_indices, p->n_pre, p->n_conn,
-                                  p->d_events, nullptr, BE_B200_SPK_BOOL, p->n_pre, p->n_post, 1, p->d_out,
-                                  p->d_ws, p->ws_bytes, s);
-    else
-        rc = be_b200_binary_jitmv(p->jit_kind, p->d_p, p->d_p + 1, BE_B200_F32, p->d_clen_seed,
-                                  p->d_clen_seed + 1, p->d_events, nullptr, BE_B200_SPK_BOOL, p->n_pre,
-                                  p->n_post, p->chunk_size, p->corder, 0, -1, 0, -1, p->d_out, p->d_ws,
-                                  p->ws_bytes, s);
+    int rc = proj_compute(p, p->d_events, p->d_out, s);
     if (rc) return rc;
     if (p->n_post > 0) BE_CUDA(cudaMemcpyAsync(out_host, p->d_out, (size_t)p->n_post * sizeof(float), cudaMemcpyDeviceToHost, s));
     BE_CUDA(cudaStreamSynchronize(s));
@@ -134,6 +182,14 @@ extern "C" void be_b200_projection_destroy(be_b200_projection* p) {
     if (!p->borrowed) { cudaFree(p->d_weights); cudaFree(p->d_indices); cudaFree(p->d_indptr); }
     cudaFree(p->d_p);
     cudaFree(p->d_clen_seed); cudaFree(p->d_events); cudaFree(p->d_out); cudaFree(p->d_ws);
+    for (int i = 0; i < 2; ++i) {
+        cudaFree(p->d_ev2[i]); cudaFree(p->d_out2[i]);
+        if (p->ev_in[i]) cudaEventDestroy(p->ev_in[i]);
+        if (p->ev_done[i]) cudaEventDestroy(p->ev_done[i]);
+        if (p->ev_out[i]) cudaEventDestroy(p->ev_out[i]);
+    }
+    if (p->s_in) cudaStreamDestroy(p->s_in);
+    if (p->s_out) cudaStreamDestroy(p->s_out);
     if (p->stream) cudaStreamDestroy(p->stream);
     delete p;
 }

@@ -335,3 +335,37 @@ def test_size_independent_properties_at_scale(G):
     yg = be.binary_csrmv(w, indices, indptr, s1, shape=(n, n), transpose=False)
     bits = s1[indices.long()].view(n, nnz)
     torch.testing.assert_close(yg, (w.view(n, nnz) * bits).sum(1), rtol=1e-4, atol=1e-4)
+
+
+def test_host_projection_session(G):
+    """C-ABI host-buffer entry points (apply_host and the pipelined submit/wait) against the oracle."""
+    import ctypes
+    from brainevent_b200 import _lib
+    L = _lib.lib()
+    f = cases.fcn_case(31, 5000, 4000, 50)
+    c = cases.csr_case(32, 5000, 4000, 30, 0.1, ragged=True)
+    spikes = [cases.spikes(40 + i, 5000, 0.05) for i in range(5)]
+    P = ctypes.c_void_p
+    projs = {
+        "fcn": (P(L.be_b200_projection_create_fcn(f["weights"].ctypes.data_as(P), 0, f["indices"].ctypes.data_as(P), 5000, 50, 4000)),
+                lambda s: O.binary_fcnmv(f["weights"], f["indices"], s, shape=(5000, 4000), transpose=True)),
+        "csr": (P(L.be_b200_projection_create_csr(c["data"].ctypes.data_as(P), 0, c["indices"].ctypes.data_as(P),
+                                                  c["indptr"].ctypes.data_as(P), 5000, 4000)),
+                lambda s: O.binary_csrmv(c["data"], c["indices"], c["indptr"], s, shape=(5000, 4000), transpose=True)),
+        "jitc": (P(L.be_b200_projection_create_jitc(1, 1.0, 0.1, O.conn_length(0.01), 7, 5000, 4000, O.normalize_chunk_size(4000), 0)),
+                 lambda s: O.binary_jitnmv(1.0, 0.1, 0.01, s, 7, shape=(5000, 4000), transpose=True, corder=False)),
+    }
+    for name, (proj, ref) in projs.items():
+        assert proj.value, name
+        hs = [torch.from_numpy(s.view(np.uint8).copy()).pin_memory() for s in spikes]
+        outs = [torch.empty(4000, dtype=torch.float32).pin_memory() for _ in spikes]
+        assert L.be_b200_projection_apply_host(proj, P(hs[0].data_ptr()), P(outs[0].data_ptr())) == 0
+        np.testing.assert_allclose(outs[0].numpy(), ref(spikes[0]), rtol=RTOL, atol=2e-5)
+        for o in outs:
+            o.zero_()
+        for h, o in zip(hs, outs):
+            assert L.be_b200_projection_submit_host(proj, P(h.data_ptr()), P(o.data_ptr())) == 0
+        assert L.be_b200_projection_wait(proj) == 0
+        for s, o in zip(spikes, outs):
+            np.testing.assert_allclose(o.numpy(), ref(s), rtol=RTOL, atol=2e-5)
+        L.be_b200_projection_destroy(proj)
