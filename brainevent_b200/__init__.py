@@ -2,7 +2,7 @@
 that one path of chaobrain/brainevent.  Public names follow brainevent/__init__.py."""
 from . import config
 from ._csr import (CSC, CSR, binary_csrmm, binary_csrmm_indexed, binary_csrmm_indexed_p, binary_csrmm_p,
-                   binary_csrmm_p_call, binary_csrmv, binary_csrmv_indexed, binary_csrmv_indexed_p,
+                   binary_csrmm_p_call, binary_csrmv, binary_csrmv_auto, binary_csrmv_indexed, binary_csrmv_indexed_p,
                    binary_csrmv_p, binary_csrmv_p_call, csr_to_csc_index)
 from ._dense import (binary_densemm, binary_densemm_p, binary_densemm_p_call, binary_densemv,
                      binary_densemv_p, binary_densemv_p_call)

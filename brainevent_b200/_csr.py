@@ -146,6 +146,33 @@ def binary_csrmm_indexed(data, indices, indptr, perm, B, *, shape, workspace=Non
     return maybe_decimal(res, unitd, unitb)
 
 
+SCATTER_GATHER_RATE_THRESHOLD = 0.25   # above this fraction of active sources the gather wins
+
+
+def binary_csrmv_auto(data, indices, indptr, mirror, v, *, shape, rate_threshold=SCATTER_GATHER_RATE_THRESHOLD):
+    """`e(v) @ A` for a CSR `A` [m, k] whose CSC mirror `(csc_indptr, csc_indices, perm)` is
+    available: atomic scatter over active rows or deterministic post-major gather, chosen on the
+    device from the spike count (no host sync)."""
+    data, unitd = split_mantissa_unit(data)
+    v, unitv = split_mantissa_unit(v)
+    data, indices, indptr, _ = _prep_structure(data, indices, indptr)
+    csc_indptr, csc_indices, perm = mirror
+    m, k = int(shape[0]), int(shape[1])
+    ev = event_args(v, n_expected=m)
+    assert ev.batch is None, "binary_csrmv_auto needs a 1-D event vector"
+    assert csc_indptr.dtype == indptr.dtype == perm.dtype or data.numel() == 1
+    dev = data.device
+    out = torch.empty(k, dtype=data.dtype, device=dev)
+    ws = workspace(dev, m, 1)
+    rc = _lib.lib().be_b200_binary_csrmv_auto(ptr(data), wt_code(data.dtype), int(data.numel() == 1), ptr(indices),
+                                              ptr(indptr), int(indptr.dtype == torch.int64), ptr(csc_indptr),
+                                              ptr(csc_indices), ptr(perm), ptr(ev.spikes), ptr(ev.aux), ev.kind,
+                                              m, k, indices.numel(), float(rate_threshold), ptr(out), ptr(ws),
+                                              ws.numel(), stream_ptr(dev))
+    _lib.check(rc, "binary_csrmv_auto")
+    return maybe_decimal(out, unitd, unitv)
+
+
 def csr_to_csc_index(csr_indptr, csr_indices, *, shape):
     """Stable by-column mirror -> (csc_indptr, csc_indices = row ids, perm); ref: _misc.py:1341-1384."""
     indptr, indices = as_tensor(csr_indptr).contiguous(), as_tensor(csr_indices).contiguous()
@@ -226,6 +253,10 @@ class CSR(_Compressed):
         # other @ csr (ref: _csr/main.py:1731-1776)
         if isinstance(other, _EVENT_TYPES):
             if other.ndim == 1:
+                if self._mirror is not None:
+                    # mirror built (build_weight_indices): scatter vs gather picked by spike rate
+                    return binary_csrmv_auto(self.data, self.indices, self.indptr, self._mirror, other,
+                                             shape=self.shape)
                 return binary_csrmv(self.data, self.indices, self.indptr, other, shape=self.shape,
                                     transpose=True, backend=self.backend)
             if other.ndim == 2:

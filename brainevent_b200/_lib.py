@@ -52,6 +52,7 @@ _SIGNATURES = {
     "be_b200_compact_1d": (_I, [_P, _I, _L, _I, _P, _P, _P, _P, _Z, _P]),
     "be_b200_compact_2d": (_I, [_P, _I, _L, _L, _I, _P, _P, _P, _P, _Z, _P]),
     "be_b200_binary_csrmv": (_I, [_P, _I, _I, _P, _P, _I, _P, _I, _P, _P, _I, _L, _L, _L, _I, _P, _P, _Z, _P]),
+    "be_b200_binary_csrmv_auto": (_I, [_P, _I, _I, _P, _P, _I, _P, _P, _P, _P, _P, _I, _L, _L, _L, ctypes.c_float, _P, _P, _Z, _P]),
     "be_b200_binary_csrmm": (_I, [_P, _I, _I, _P, _P, _I, _P, _I, _P, _P, _I, _L, _L, _L, _L, _I, _I, _P, _P, _Z, _P]),
     "be_b200_binary_fcnmv": (_I, [_P, _I, _I, _P, _L, _L, _P, _P, _I, _L, _L, _I, _P, _P, _Z, _P]),
     "be_b200_binary_fcnmm": (_I, [_P, _I, _I, _P, _L, _L, _P, _P, _I, _L, _L, _L, _I, _I, _P, _P, _Z, _P]),

@@ -104,6 +104,10 @@ struct Events {
     const int32_t* active_ids;  // ascending active source rows (may be null if not needed)
     const int* n_active;        // device scalar
     int words_per_row;          // 2-D only
+    // rate-based selection between the atomic scatter and the deterministic gather of the same
+    // product (decided on the device, no host sync): with sel_thr >= 0 a scatter kernel runs only
+    // when n_active <= sel_thr and a gather kernel only when n_active > sel_thr.
+    int sel_thr = -1;
 };
 
 // ------------------------------------------------------------------------------------------

@@ -82,8 +82,9 @@ __global__ void __launch_bounds__(256) scatter_mv_kernel(Rows rows, const int32_
                                                          const void* __restrict__ perm,
                                                          const int32_t* __restrict__ ids,
                                                          const int* __restrict__ n_active_ptr,
-                                                         T* __restrict__ out) {
+                                                         T* __restrict__ out, int sel_thr) {
     using A = typename Acc<T>::type;
+    if (sel_thr >= 0 && *n_active_ptr > sel_thr) return;   // the gather variant owns this call
     __shared__ int s_heavy[kHeavyCap];
     __shared__ int s_nheavy;
     if (threadIdx.x == 0) s_nheavy = 0;
@@ -264,7 +265,7 @@ static int launch_scatter_mv(const Rows& rows, const ConnArgs& c, const Events& 
     int blocks = (int)std::min<int64_t>(ceil_div(std::max<int64_t>(n_src, 1), groups), kNumSM * 8);
 #define BE_SC(VEC, LPR)                                                                      \
     scatter_mv_kernel<T, HOMO, PERM, VEC, LPR, Rows><<<blocks, 256, 0, s>>>(                 \
-        rows, c.indices, (const T*)c.weights, c.perm, ev.active_ids, ev.n_active, out)
+        rows, c.indices, (const T*)c.weights, c.perm, ev.active_ids, ev.n_active, out, ev.sel_thr)
     {
         ProfileScope prof(s);
         if (vec) { if (narrow) BE_SC(true, 8); else BE_SC(true, 32); }
@@ -400,6 +401,45 @@ extern "C" int be_b200_binary_csrmv(const void* weights, int w_dtype, int homo,
                                     size_t workspace_bytes, void* stream) {
     return csr_entry(weights, w_dtype, homo, indices, indptr, indptr_is64, perm, perm_is64, spikes,
                      aux, spk_kind, m, k, nse, 0, transpose, out, workspace, workspace_bytes, stream);
+}
+
+// spk @ csr with the variant chosen by spike rate on the device (north star: "CSC/post-major
+// gather (deterministic) next to an atomic CSR scatter variant chosen by spike rate").
+extern "C" int be_b200_binary_csrmv_auto(const void* weights, int w_dtype, int homo,
+                                         const int32_t* indices, const void* indptr, int indptr_is64,
+                                         const void* csc_indptr, const int32_t* csc_indices,
+                                         const void* perm, const void* spikes, const void* aux,
+                                         int spk_kind, int64_t m, int64_t k, int64_t nse,
+                                         float rate_threshold, void* out, void* workspace,
+                                         size_t workspace_bytes, void* stream) {
+    cudaStream_t s = (cudaStream_t)stream;
+    BE_REQUIRE(m >= 0 && k >= 0 && m < (1ll << 31) && k < (1ll << 31), "csrmv_auto: shape out of range");
+    BE_REQUIRE(weights && indptr && csc_indptr && out, "csrmv_auto: NULL pointer");
+    BE_REQUIRE((indices && csc_indices && (homo || perm)) || nse == 0, "csrmv_auto: NULL structure pointer");
+    BE_REQUIRE(w_dtype >= 0 && w_dtype < 4, "csrmv_auto: unsupported weight dtype %d", w_dtype);
+    static const size_t kWt[4] = {4, 8, 2, 2};
+    if (k == 0) return BE_B200_OK;
+    Events ev;
+    int rc = prepare_events_1d(spikes, aux, spk_kind, m, true, true, workspace, workspace_bytes, s, &ev, out,
+                               (size_t)k * kWt[w_dtype], /*ordered_ids=*/false);
+    if (rc) return rc;
+    if (m == 0) return BE_B200_OK;
+    ev.sel_thr = (int)std::min<double>((double)rate_threshold * (double)m, 2147483647.0);
+    ConnArgs cs{weights, w_dtype, homo, indices, nullptr, 0, m > 0 ? (double)nse / (double)m : 0.0};
+    ConnArgs cg{weights, w_dtype, homo, csc_indices, homo ? nullptr : perm, homo ? 0 : (indptr_is64 ? 2 : 1),
+                k > 0 ? (double)nse / (double)k : 0.0};
+    RowsDesc rg{indptr_is64 ? 1 : 0, csc_indptr, 0};
+    BE_DISPATCH_WT(w_dtype, T, {
+        if (indptr_is64) {
+            CsrRows<int64_t> rows{(const int64_t*)indptr};
+            rc = homo ? launch_scatter_mv<T, true, 0>(rows, cs, ev, m, (T*)out, s) : launch_scatter_mv<T, false, 0>(rows, cs, ev, m, (T*)out, s);
+        } else {
+            CsrRows<int32_t> rows{(const int32_t*)indptr};
+            rc = homo ? launch_scatter_mv<T, true, 0>(rows, cs, ev, m, (T*)out, s) : launch_scatter_mv<T, false, 0>(rows, cs, ev, m, (T*)out, s);
+        }
+    });
+    if (rc) return rc;
+    return run_gather(rg, cg, ev, m, k, 0, out, s);
 }
 
 extern "C" int be_b200_binary_csrmm(const void* weights, int w_dtype, int homo,

@@ -25,8 +25,10 @@ __global__ void __launch_bounds__(SMEM ? 1024 : 256) gather_mv_kernel(Rows rows,
                                                                       const void* __restrict__ perm,
                                                                       const uint32_t* __restrict__ packed,
                                                                       int64_t n_words, int64_t n_rows,
-                                                                      T* __restrict__ out) {
+                                                                      T* __restrict__ out,
+                                                                      const int* __restrict__ sel_n_active, int sel_thr) {
     using A = typename Acc<T>::type;
+    if (sel_thr >= 0 && *sel_n_active <= sel_thr) return;   // the scatter variant owns this call
     extern __shared__ __align__(16) uint32_t s_bits[];
     if (SMEM) {
         const int64_t n16 = n_words >> 2;
@@ -192,7 +194,7 @@ static int launch_gather_mv(const Rows& rows, const ConnArgs& c, const Events& e
             BE_CUDA(cudaFuncSetAttribute(gather_mv_kernel<T, HOMO, PERM, true, LPR, true, Rows>,              \
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kGatherSmemMax));  \
             gather_mv_kernel<T, HOMO, PERM, true, LPR, true, Rows><<<blocks, 1024, smem, s>>>(                \
-                rows, c.indices, (const T*)c.weights, c.perm, ev.packed, n_words, n_rows, out);               \
+                rows, c.indices, (const T*)c.weights, c.perm, ev.packed, n_words, n_rows, out, ev.n_active, ev.sel_thr); \
         } while (0)
         switch (lpr) { case 4: BE_GAS(4); break; case 8: BE_GAS(8); break; case 16: BE_GAS(16); break; default: BE_GAS(32); }
 #undef BE_GAS
@@ -200,7 +202,7 @@ static int launch_gather_mv(const Rows& rows, const ConnArgs& c, const Events& e
         int blocks = (int)std::min<int64_t>(ceil_div(n_rows, 256 / lpr), (int64_t)kNumSM * 16);
 #define BE_GA(VEC, LPR)                                                                      \
         gather_mv_kernel<T, HOMO, PERM, VEC, LPR, false, Rows><<<blocks, 256, 0, s>>>(       \
-            rows, c.indices, (const T*)c.weights, c.perm, ev.packed, n_words, n_rows, out)
+            rows, c.indices, (const T*)c.weights, c.perm, ev.packed, n_words, n_rows, out, ev.n_active, ev.sel_thr)
 #define BE_GA2(VEC) switch (lpr) { case 4: BE_GA(VEC, 4); break; case 8: BE_GA(VEC, 8); break; \
                                    case 16: BE_GA(VEC, 16); break; default: BE_GA(VEC, 32); }
         if (vec) { BE_GA2(true) } else { BE_GA2(false) }

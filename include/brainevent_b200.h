@@ -109,6 +109,17 @@ int be_b200_binary_csrmv(const void* weights, int w_dtype, int homo, const int32
                          const void* spikes, const void* aux, int spk_kind, int64_t m, int64_t k,
                          int64_t nse, int transpose, void* out, void* workspace,
                          size_t workspace_bytes, void* stream);
+/* spk @ csr (events[m] -> out[k]) with the variant picked ON THE DEVICE from the spike rate: the
+ * active-row atomic scatter over the CSR when n_active <= rate_threshold * m, else the
+ * deterministic post-major gather over the CSC mirror (csc_indptr/csc_indices/perm from
+ * be_b200_csr_to_csc; offsets share indptr's width).  No host synchronisation: both kernels are
+ * enqueued and the one not selected exits at once.  ref: _csr/main.py:1641-1655 (mirror route). */
+int be_b200_binary_csrmv_auto(const void* weights, int w_dtype, int homo, const int32_t* indices,
+                              const void* indptr, int indptr_is64, const void* csc_indptr,
+                              const int32_t* csc_indices, const void* perm, const void* spikes,
+                              const void* aux, int spk_kind, int64_t m, int64_t k, int64_t nse,
+                              float rate_threshold, void* out, void* workspace,
+                              size_t workspace_bytes, void* stream);
 int be_b200_binary_csrmm(const void* weights, int w_dtype, int homo, const int32_t* indices,
                          const void* indptr, int indptr_is64, const void* perm, int perm_is64,
                          const void* spikes, const void* aux, int spk_kind, int64_t m, int64_t k,

@@ -369,3 +369,24 @@ def test_host_projection_session(G):
         for s, o in zip(spikes, outs):
             np.testing.assert_allclose(o.numpy(), ref(s), rtol=RTOL, atol=2e-5)
         L.be_b200_projection_destroy(proj)
+
+
+@pytest.mark.parametrize("homo", [False, True])
+@pytest.mark.parametrize("rate", [0.0, 0.02, 0.24, 0.26, 0.9])
+def test_rate_selected_scatter_or_gather(G, homo, rate):
+    """spk @ csr with the CSC mirror built: both sides of the device-side rate threshold must give
+    the same product (scatter below, deterministic gather above)."""
+    import brainevent_b200 as be
+    c = cases.csr_case(50, 4000, 3000, 25, 0.1, homo=homo, ragged=True)
+    t = lambda x: torch.as_tensor(x, device="cuda")
+    csr = be.CSR((t(c["data"]), t(c["indices"]), t(c["indptr"])), shape=c["shape"])
+    csr.build_weight_indices()
+    v = cases.spikes(51, 4000, rate)
+    ref = O.binary_csrmv(c["data"], c["indices"], c["indptr"], v, shape=c["shape"], transpose=True)
+    for ev in (be.BinaryArray(t(v)), be.BitPackedBinary(t(v)), be.CompactBinary.from_array(t(v))):
+        got = (ev @ csr).cpu().numpy()
+        np.testing.assert_allclose(got, ref, rtol=RTOL, atol=2e-5)
+    if rate > 0.25:   # gather side: bit-reproducible
+        a = (be.BinaryArray(t(v)) @ csr).cpu().numpy()
+        b = (be.BinaryArray(t(v)) @ csr).cpu().numpy()
+        np.testing.assert_array_equal(a, b)
