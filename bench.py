@@ -112,12 +112,15 @@ class FcnWeak(Workload):
     name = "fcn_perpre_postsharded"
     dominant_kernel = "scatter_mv_kernel"
 
-    def __init__(self, torch, be, rank, world, device, neurons_per_gpu=FCN_NEURONS_PER_GPU, n_conn=FCN_CONN, rate=RATE):
+    def __init__(self, torch, be, rank, world, device, neurons_per_gpu=FCN_NEURONS_PER_GPU, n_conn=FCN_CONN, rate=RATE,
+                 emulate_world=0):
         from brainevent_b200 import dist as bd
         self.torch, self.be, self.world, self.rank = torch, be, world, rank
+        self.emulate = emulate_world      # profile one rank's shard of an `emulate_world`-GPU run on a single GPU
+        shards = emulate_world if emulate_world else world
         self.n_local = neurons_per_gpu
-        self.n_total = neurons_per_gpu * world
-        self.conn_local = n_conn // world          # targets stratified evenly over the post blocks
+        self.n_total = neurons_per_gpu * shards
+        self.conn_local = n_conn // shards          # targets stratified evenly over the post blocks
         g = torch.Generator(device=device).manual_seed(1234 + rank)
         # this rank's incoming synapses: for every pre neuron of the whole network, conn_local
         # targets inside the local post block (local ids) with U(0,1) fp32 weights
@@ -130,7 +133,12 @@ class FcnWeak(Workload):
                                              weights=self.weights, indices=self.indices)
         self.launches_per_timestep = 2 if world == 1 else 3
         # events: every rank sees ALL spikes; count from the global pool (same seeds on every rank)
-        if world == 1:
+        if emulate_world:
+            # no exchange: the global packed spike vector of every timestep is precomputed
+            gpool = torch.cat([spike_pool(torch, self.n_local, rate, 99 + r, device) for r in range(shards)], 1)
+            self.packed_pool = [be.BitPackedBinary(gpool[i]) for i in range(POOL)]
+            per_t = gpool.sum(1).double()
+        elif world == 1:
             per_t = self.pool.sum(1).double()
         else:
             per_t = sum(spike_pool(torch, self.n_local, rate, 99 + r, device).sum(1).double() for r in range(world))
@@ -144,6 +152,9 @@ class FcnWeak(Workload):
                        "neurons": self.n_total, "synapses_per_neuron": n_conn, "spike_rate": rate}
 
     def timestep(self, t):
+        if self.emulate:
+            return self.be.binary_fcnmv(self.weights, self.indices, self.packed_pool[t % POOL],
+                                        shape=(self.n_total, self.n_local), transpose=True)
         if self.world == 1:
             return self.be.binary_fcnmv(self.weights, self.indices, self.pool[t % POOL],
                                         shape=(self.n_total, self.n_local), transpose=True)
@@ -488,6 +499,8 @@ def main():
     ap.add_argument("--no-extra", action="store_true", help="skip the other BASELINE configs at N=1")
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--emulate-world", type=int, default=0,
+                    help="(profiling) run rank 0's shard of an N-GPU post-sharded fcn run on one GPU, no exchange")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     if args.impl == "reference":
@@ -510,7 +523,7 @@ def main():
     K, W, T = args.steps, args.warmup, args.timesteps
 
     if args.workload == "fcn":
-        wl = FcnWeak(torch, be, rank, world, device)
+        wl = FcnWeak(torch, be, rank, world, device, emulate_world=args.emulate_world)
     elif args.workload == "coba":
         wl = Coba(torch, be, device)
     elif args.workload == "cuba_jitc":
@@ -525,7 +538,7 @@ def main():
 
     # ---- e2e: host buffers in, host buffers out, every timestep -------------------------------
     e2e = None
-    if args.workload == "fcn":
+    if args.workload == "fcn" and not args.emulate_world:
         n_in, n_out = wl.n_local, wl.n_local
         host_spk = [torch.empty(n_in, dtype=torch.uint8).pin_memory() for _ in range(POOL)]
         for i in range(POOL):

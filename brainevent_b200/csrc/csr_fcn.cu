@@ -31,41 +31,71 @@ constexpr int kHeavyCap = 32;     // deferred heavy rows per CTA before falling 
 // Visit every synapse j in [s, e) of one row with a group of G lanes: f(column, weight).
 // VEC: peel to a 4-element boundary, then one 128-bit index load (+ one 128-bit weight load) per
 // lane per step, all issued before the first use so a row costs ~one memory round trip.
-template <typename T, bool HOMO, int PERM, bool VEC, int G, typename F>
+template <typename T, bool HOMO, int PERM, int VEC, int G, typename F>
 __device__ __forceinline__ void for_each_synapse(int64_t s, int64_t e, int gl,
                                                  const int32_t* __restrict__ indices,
                                                  const T* __restrict__ weights,
                                                  const void* __restrict__ perm,
                                                  typename Acc<T>::type w0, F&& f) {
     using A = typename Acc<T>::type;
-    if (!VEC) {
+    if (VEC == 0) {
         for (int64_t j = s + gl; j < e; j += G)
             f(__ldg(indices + j), weight_at<T, HOMO, PERM>(weights, perm, j, w0));
         return;
     }
-    int64_t a = (s + 3) & ~(int64_t)3;
-    if (a > e) a = e;
-    if (gl < a - s) f(__ldg(indices + s + gl), weight_at<T, HOMO, PERM>(weights, perm, s + gl, w0));
-    int64_t aend = a + ((e - a) & ~(int64_t)3);
+    // One loop covers head, body and tail: quads start at the 16-byte boundary at or below s, so
+    // every lane issues aligned 128-bit loads (the first quad may reach up to 3 slots into the
+    // previous row: masked, in bounds); only the single partial quad at the row's end falls back to
+    // scalar loads.  No separate head/tail instruction streams, no extra partially-filled REDs.
+    if (VEC == 2) {
+        // rows are known to start and end on 4-element boundaries (ELL with n_conn % 4 == 0):
+        // pure 128-bit streaming, no boundary handling at all
 #pragma unroll 2
-    for (int64_t j = a + (int64_t)gl * 4; j < aend; j += (int64_t)G * 4) {
-        int4 ix = ldg_stream((const int4*)(indices + j));
-        A wv[4];
-        if (HOMO) { wv[0] = wv[1] = wv[2] = wv[3] = w0; }
-        else if (PERM == 0) { Vec4<T> v = load4(weights + j); wv[0] = v.v[0]; wv[1] = v.v[1]; wv[2] = v.v[2]; wv[3] = v.v[3]; }
-        else {
+        for (int64_t j = s + (int64_t)gl * 4; j < e; j += (int64_t)G * 4) {
+            const int4 ix = ldg_stream((const int4*)(indices + j));
+            A wv[4];
+            if (HOMO) { wv[0] = wv[1] = wv[2] = wv[3] = w0; }
+            else if (PERM == 0) { Vec4<T> v = load4(weights + j); wv[0] = v.v[0]; wv[1] = v.v[1]; wv[2] = v.v[2]; wv[3] = v.v[3]; }
+            else {
 #pragma unroll
-            for (int q = 0; q < 4; ++q) wv[q] = weight_at<T, HOMO, PERM>(weights, perm, j + q, w0);
+                for (int q = 0; q < 4; ++q) wv[q] = weight_at<T, HOMO, PERM>(weights, perm, j + q, w0);
+            }
+            f(ix.x, wv[0]);
+            f(ix.y, wv[1]);
+            f(ix.z, wv[2]);
+            f(ix.w, wv[3]);
         }
-        f(ix.x, wv[0]);
-        f(ix.y, wv[1]);
-        f(ix.z, wv[2]);
-        f(ix.w, wv[3]);
+        return;
     }
-    if (gl < e - aend) f(__ldg(indices + aend + gl), weight_at<T, HOMO, PERM>(weights, perm, aend + gl, w0));
+    const int64_t a0 = s & ~(int64_t)3;
+#pragma unroll 2
+    for (int64_t j = a0 + (int64_t)gl * 4; j < e; j += (int64_t)G * 4) {
+        int ixv[4];
+        A wv[4];
+        if (j + 4 <= e) {
+            const int4 ix = ldg_stream((const int4*)(indices + j));
+            ixv[0] = ix.x; ixv[1] = ix.y; ixv[2] = ix.z; ixv[3] = ix.w;
+            if (HOMO) { wv[0] = wv[1] = wv[2] = wv[3] = w0; }
+            else if (PERM == 0) { Vec4<T> v = load4(weights + j); wv[0] = v.v[0]; wv[1] = v.v[1]; wv[2] = v.v[2]; wv[3] = v.v[3]; }
+            else {
+#pragma unroll
+                for (int q = 0; q < 4; ++q) wv[q] = (j + q >= s) ? weight_at<T, HOMO, PERM>(weights, perm, j + q, w0) : A(0);
+            }
+        } else {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const bool ok = (j + q >= s) && (j + q < e);
+                ixv[q] = ok ? __ldg(indices + j + q) : 0;
+                wv[q] = ok ? weight_at<T, HOMO, PERM>(weights, perm, j + q, w0) : A(0);
+            }
+        }
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+            if (j + q >= s && j + q < e) f(ixv[q], wv[q]);
+    }
 }
 
-template <typename T, bool HOMO, int PERM, bool VEC, int G>
+template <typename T, bool HOMO, int PERM, int VEC, int G>
 __device__ __forceinline__ void scatter_segment(int64_t s, int64_t e, int gl,
                                                 const int32_t* __restrict__ indices,
                                                 const T* __restrict__ weights,
@@ -76,7 +106,7 @@ __device__ __forceinline__ void scatter_segment(int64_t s, int64_t e, int gl,
                                             [&](int col, A w) { red_add(out + col, w); });
 }
 
-template <typename T, bool HOMO, int PERM, bool VEC, int LPR, typename Rows>
+template <typename T, bool HOMO, int PERM, int VEC, int LPR, typename Rows>
 __global__ void __launch_bounds__(256) scatter_mv_kernel(Rows rows, const int32_t* __restrict__ indices,
                                                          const T* __restrict__ weights,
                                                          const void* __restrict__ perm,
@@ -127,7 +157,7 @@ __global__ void __launch_bounds__(256) scatter_mv_kernel(Rows rows, const int32_
 // lanes = synapses (32 REDs per instruction); dense masks use lanes = columns (contiguous REDs).
 // ------------------------------------------------------------------------------------------
 
-template <typename T, bool HOMO, int PERM, bool VEC, int MW, typename Rows>
+template <typename T, bool HOMO, int PERM, int VEC, int MW, typename Rows>
 __global__ void __launch_bounds__(256) scatter_mm_kernel(Rows rows, const int32_t* __restrict__ indices,
                                                          const T* __restrict__ weights,
                                                          const void* __restrict__ perm,
@@ -219,7 +249,7 @@ __global__ void __launch_bounds__(256) scatter_mm_kernel(Rows rows, const int32_
 // groups it spikes in (~1.3x at 1 % rates instead of once per output tile), and no synapse is
 // filtered away after being loaded.
 // ------------------------------------------------------------------------------------------
-template <typename T, bool HOMO, int PERM, bool VEC, typename Rows>
+template <typename T, bool HOMO, int PERM, int VEC, typename Rows>
 __global__ void __launch_bounds__(256) scatter_mm_bm_kernel(Rows rows, const int32_t* __restrict__ indices,
                                                             const T* __restrict__ weights,
                                                             const void* __restrict__ perm,
@@ -256,10 +286,19 @@ __global__ void __launch_bounds__(256) scatter_mm_bm_kernel(Rows rows, const int
 // ------------------------------------------------------------------------------------------
 // launch helpers
 // ------------------------------------------------------------------------------------------
+// 0: scalar accesses (unaligned base pointers); 1: masked 128-bit quads (arbitrary row extents);
+// 2: rows start/end on 4-element boundaries (ELL with n_conn % 4 == 0)
+template <typename Rows>
+static inline int vec_mode(const Rows& rows, const ConnArgs& c) {
+    if (!(al16(c.indices) && (c.homo || al16(c.weights)))) return 0;
+    if constexpr (std::is_same<Rows, FcnRows>::value) return (rows.n_conn % 4 == 0) ? 2 : 1;
+    return 1;
+}
+
 template <typename T, bool HOMO, int PERM, typename Rows>
 static int launch_scatter_mv(const Rows& rows, const ConnArgs& c, const Events& ev, int64_t n_src,
                              T* out, cudaStream_t s) {
-    const bool vec = al16(c.indices) && (c.homo || al16(c.weights));
+    const int vec = vec_mode(rows, c);
     const bool narrow = c.avg_row < 40.0;
     const int groups = narrow ? 32 : 8;
     int blocks = (int)std::min<int64_t>(ceil_div(std::max<int64_t>(n_src, 1), groups), kNumSM * 8);
@@ -268,8 +307,9 @@ static int launch_scatter_mv(const Rows& rows, const ConnArgs& c, const Events& 
         rows, c.indices, (const T*)c.weights, c.perm, ev.active_ids, ev.n_active, out, ev.sel_thr)
     {
         ProfileScope prof(s);
-        if (vec) { if (narrow) BE_SC(true, 8); else BE_SC(true, 32); }
-        else { if (narrow) BE_SC(false, 8); else BE_SC(false, 32); }
+        if (vec == 2) { if (narrow) BE_SC(2, 8); else BE_SC(2, 32); }
+        else if (vec == 1) { if (narrow) BE_SC(1, 8); else BE_SC(1, 32); }
+        else { if (narrow) BE_SC(0, 8); else BE_SC(0, 32); }
     }
 #undef BE_SC
     BE_LAUNCH_CHECK("scatter_mv_kernel");
@@ -284,7 +324,7 @@ static int launch_scatter_mm(const Rows& rows, const ConnArgs& c, const Events& 
     int blocks = (int)std::min<int64_t>(ceil_div(std::max<int64_t>(n_src, 1), 8), kNumSM * 8);
     const size_t row_bytes = (size_t)n * sizeof(T);
     const int64_t rows_per_pass = std::max<int64_t>(1, (int64_t)(kL2TileBytes / row_bytes));
-    const bool vec = al16(c.indices) && (c.homo || al16(c.weights));
+    const bool vec = vec_mode(rows, c) != 0;
     ProfileScope prof(s);   // one record for all passes of the call
     for (int64_t lo = 0; lo < n_out; lo += rows_per_pass) {
         const int64_t hi = std::min(n_out, lo + rows_per_pass);
@@ -295,8 +335,8 @@ static int launch_scatter_mm(const Rows& rows, const ConnArgs& c, const Events& 
         scatter_mm_kernel<T, HOMO, PERM, VEC, MW, Rows><<<blocks, 256, 0, s>>>(                     \
             rows, c.indices, (const T*)c.weights, c.perm, ev.active_ids, ev.n_active, ev.packed,    \
             ev.words_per_row, n, out, (int)lo, (int)hi)
-        if (ev.words_per_row <= 2) { if (vec) BE_SMM(true, 2); else BE_SMM(false, 2); }
-        else { if (vec) BE_SMM(true, 8); else BE_SMM(false, 8); }
+        if (ev.words_per_row <= 2) { if (vec) BE_SMM(1, 2); else BE_SMM(0, 2); }
+        else { if (vec) BE_SMM(1, 8); else BE_SMM(0, 8); }
 #undef BE_SMM
     }
     BE_LAUNCH_CHECK("scatter_mm_kernel");
@@ -309,19 +349,17 @@ static int launch_scatter_mm_bm(const Rows& rows, const ConnArgs& c, const Event
     int blocks = (int)std::min<int64_t>(ceil_div(std::max<int64_t>(n_src, 1), 8), kNumSM * 8);
     const size_t col_bytes = (size_t)n_out * sizeof(T);
     const int64_t cols_per_pass = std::max<int64_t>(1, (int64_t)(kL2TileBytes / std::max<size_t>(col_bytes, 1)));
-    const bool vec = al16(c.indices) && (c.homo || al16(c.weights));
+    const int vec = vec_mode(rows, c);
     ProfileScope prof(s);
     for (int64_t lo = 0; lo < n; lo += cols_per_pass) {
         const int64_t hi = std::min(n, lo + cols_per_pass);
         BE_CUDA(cudaMemsetAsync(out + lo * n_out, 0, (size_t)(hi - lo) * col_bytes, s));
-        if (vec)
-            scatter_mm_bm_kernel<T, HOMO, PERM, true, Rows><<<blocks, 256, 0, s>>>(
-                rows, c.indices, (const T*)c.weights, c.perm, ev.active_ids, ev.n_active, ev.packed,
-                ev.words_per_row, n_out, out, (int)lo, (int)hi);
-        else
-            scatter_mm_bm_kernel<T, HOMO, PERM, false, Rows><<<blocks, 256, 0, s>>>(
-                rows, c.indices, (const T*)c.weights, c.perm, ev.active_ids, ev.n_active, ev.packed,
-                ev.words_per_row, n_out, out, (int)lo, (int)hi);
+#define BE_SBM(VEC)                                                                              \
+        scatter_mm_bm_kernel<T, HOMO, PERM, VEC, Rows><<<blocks, 256, 0, s>>>(                       \
+            rows, c.indices, (const T*)c.weights, c.perm, ev.active_ids, ev.n_active, ev.packed,     \
+            ev.words_per_row, n_out, out, (int)lo, (int)hi)
+        if (vec == 2) BE_SBM(2); else if (vec == 1) BE_SBM(1); else BE_SBM(0);
+#undef BE_SBM
     }
     BE_LAUNCH_CHECK("scatter_mm_bm_kernel");
     return BE_B200_OK;
