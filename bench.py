@@ -128,7 +128,16 @@ class FcnWeak(Workload):
                                      dtype=torch.int32, generator=g)
         self.weights = torch.rand((self.n_total, self.conn_local), device=device, generator=g)
         self.pool = spike_pool(torch, self.n_local, rate, 99 + rank, device)     # spikes of the neurons I own
-        self.x = bd.SpikeExchange(self.n_total, device=device)
+        self.exchange_kind = "nccl all_gather"
+        self.x = None
+        if world > 1 and os.environ.get("BE_B200_EXCHANGE", "p2p") == "p2p":
+            try:
+                self.x = bd.P2PSpikeExchange(self.n_total, device=device)
+                self.exchange_kind = "fused pack + NVLink peer-store all-gather (exchange.cu)"
+            except Exception as e:  # pragma: no cover - symmetric memory unavailable: NCCL path
+                sys.stderr.write(f"[bench] P2P exchange unavailable ({type(e).__name__}: {e}); using NCCL\n")
+        if self.x is None:
+            self.x = bd.SpikeExchange(self.n_total, device=device)
         self.proj = bd.PostShardedProjection("fcn", self.n_total, self.n_total, self.x,
                                              weights=self.weights, indices=self.indices)
         self.launches_per_timestep = 2 if world == 1 else 3
@@ -149,7 +158,8 @@ class FcnWeak(Workload):
                                    f"{rate:.0%} spikes/timestep, post-sharded over {world} GPU(s) "
                                    f"({self.n_local} post neurons and {self.conn_local} synapses/pre-neuron per GPU, "
                                    "targets stratified evenly over post blocks), BASELINE configs[4] at 8 GPUs",
-                       "neurons": self.n_total, "synapses_per_neuron": n_conn, "spike_rate": rate}
+                       "neurons": self.n_total, "synapses_per_neuron": n_conn, "spike_rate": rate,
+                       "spike_exchange": self.exchange_kind if world > 1 else "none (single GPU)"}
 
     def timestep(self, t):
         if self.emulate:

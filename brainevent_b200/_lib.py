@@ -63,6 +63,9 @@ _SIGNATURES = {
     "be_b200_binary_densemm": (_I, [_P, _I, _L, _L, _P, _P, _I, _L, _I, _P, _P, _Z, _P]),
     "be_b200_csc_workspace_bytes": (_Z, [_L, _L, _L]),
     "be_b200_csr_to_csc": (_I, [_P, _I, _P, _L, _L, _L, _P, _P, _P, _P, _Z, _P]),
+    "be_b200_exchange_ctl_bytes": (_Z, []),
+    "be_b200_pack_publish": (_I, [_P, _I, _L, _P, _P, _I, _I, _L, _P, _P]),
+    "be_b200_wait_exchange": (_I, [_P, _P, _I, _L, _P, _P, _P]),
     "be_b200_projection_create_csr": (_P, [_P, _I, _P, _P, _L, _L]),
     "be_b200_projection_create_fcn": (_P, [_P, _I, _P, _L, _L, _L]),
     "be_b200_projection_adopt_fcn": (_P, [_P, _I, _P, _L, _L, _L]),

@@ -1,0 +1,146 @@
+// exchange.cu -- fused bit-pack + all-gather of spike words over NVLink peer memory.
+//
+// Net-new relative to the reference (no distributed code there).  The compute
+// step "pack my block of spikes" and the collective "all-gather the packed words" are ONE kernel:
+// every rank packs its own block and stores each 32-bit word straight into every peer's gather
+// buffer (peer pointers from a symmetric-memory rendezvous; NVSwitch gives each pair full
+// bandwidth), then publishes a monotonically increasing step number into a flag slot on each
+// peer with release semantics at system scope.  A one-warp wait kernel on the consumer side
+// acquires the `world` flags before the propagation kernels read the gathered words.  The whole
+// exchange moves N/8 bytes and is latency-bound, so it replaces NCCL's all-gather launch +
+// protocol latency by a single store-and-flag round.
+//
+// Buffers are double-buffered by the parity of the device-side step counter: a rank can run at
+// most one exchange ahead of a peer (its step t+1 needs every peer's step t+1 pack, which follows
+// that peer's step t consumption in stream order), so parity t never overwrites words of step t
+// that a slower peer is still reading.  The wait kernel copies the current half into a fixed
+// local buffer, so consumers (and CUDA graphs) see one static pointer.
+#include "common.cuh"
+
+#include <algorithm>
+
+namespace be {
+
+__device__ __forceinline__ void st_release_sys(uint32_t* p, uint32_t v) {
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* p) {
+    uint32_t v;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+
+struct ExchangeCtl {      // local (non-symmetric) control block, zero-initialised by the caller
+    uint32_t step;        // exchanges completed by this rank
+    uint32_t done;        // blocks of the pack kernel in flight that have finished their stores
+    uint32_t timeout;     // set when a wait gave up (peer never published): surfaced by the host
+    uint32_t pad;
+};
+
+template <int KIND>
+__global__ void __launch_bounds__(256) pack_publish_kernel(const void* __restrict__ spikes, int64_t n_local,
+                                                           uint32_t* const* __restrict__ peer_bufs,
+                                                           uint32_t* const* __restrict__ peer_flags, int world,
+                                                           int rank, int64_t words_per_rank, ExchangeCtl* ctl) {
+    const uint32_t t = ctl->step + 1;      // read by every block before the last one bumps it
+    const int lane = threadIdx.x & 31;
+    const int64_t slot0 = (int64_t)(t & 1u) * words_per_rank * world + (int64_t)rank * words_per_rank;
+    for (int64_t h = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; (h - lane) < 2 * words_per_rank;
+         h += (int64_t)gridDim.x * blockDim.x) {
+        unsigned int m = 0;
+        const int64_t base = h * 16;
+        if (base < n_local) {
+            if (KIND == BE_B200_SPK_BOOL) {
+                if (base + 16 <= n_local) {
+                    const int4 v = ldg_stream((const int4*)((const uint8_t*)spikes + base));
+                    const unsigned int w[4] = {(unsigned)v.x, (unsigned)v.y, (unsigned)v.z, (unsigned)v.w};
+#pragma unroll
+                    for (int q = 0; q < 4; ++q)
+#pragma unroll
+                        for (int b = 0; b < 4; ++b)
+                            if ((w[q] >> (8 * b)) & 0xffu) m |= 1u << (q * 4 + b);
+                } else {
+                    for (int b = 0; b < 16 && base + b < n_local; ++b)
+                        if (((const uint8_t*)spikes)[base + b]) m |= 1u << b;
+                }
+            } else {
+                for (int b = 0; b < 16 && base + b < n_local; ++b)
+                    if (((const float*)spikes)[base + b] > 0.0f) m |= 1u << b;
+            }
+        }
+        const unsigned int hi = __shfl_down_sync(0xffffffffu, m, 1);
+        if ((h & 1) == 0 && (h >> 1) < words_per_rank) {
+            const uint32_t word = m | (hi << 16);
+            for (int p = 0; p < world; ++p) peer_bufs[p][slot0 + (h >> 1)] = word;   // NVLink peer stores
+        }
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const uint32_t prev = atomicAdd(&ctl->done, 1u);
+        if (prev == gridDim.x - 1) {
+            __threadfence_system();
+            for (int p = 0; p < world; ++p) st_release_sys(peer_flags[p] + rank, t);
+            ctl->done = 0u;
+            ctl->step = t;
+        }
+    }
+}
+
+// every block waits until all peers have published this rank's current step, then copies its
+// share of the gathered words (current parity half) into the fixed local buffer
+__global__ void __launch_bounds__(256) wait_copy_kernel(const uint32_t* __restrict__ my_flags,
+                                                        const uint32_t* __restrict__ my_buf, int world,
+                                                        int64_t words_per_rank, uint32_t* __restrict__ dst,
+                                                        ExchangeCtl* ctl) {
+    const uint32_t t = ctl->step;
+    if ((int)threadIdx.x < world) {
+        unsigned long long spins = 0;
+        while ((int32_t)(ld_acquire_sys(my_flags + threadIdx.x) - t) < 0) {
+            if (++spins > (1ull << 26)) { ctl->timeout = 1u; break; }   // bounded: never hang the GPU
+            __nanosleep(32);
+        }
+    }
+    __syncthreads();
+    const int64_t n = words_per_rank * world;
+    const uint32_t* src = my_buf + (int64_t)(t & 1u) * n;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+        dst[i] = __ldcv(src + i);     // peers wrote these words: bypass any stale cached copy
+}
+
+}  // namespace be
+
+using namespace be;
+
+extern "C" size_t be_b200_exchange_ctl_bytes(void) { return sizeof(ExchangeCtl); }
+
+extern "C" int be_b200_pack_publish(const void* spikes_local, int spk_kind, int64_t n_local,
+                                    void* const* peer_bufs, void* const* peer_flags, int world, int rank,
+                                    int64_t words_per_rank, void* ctl, void* stream) {
+    cudaStream_t s = (cudaStream_t)stream;
+    BE_REQUIRE(spikes_local && peer_bufs && peer_flags && ctl, "pack_publish: NULL pointer");
+    BE_REQUIRE(world >= 1 && world <= 32 && rank >= 0 && rank < world, "pack_publish: bad rank/world");
+    BE_REQUIRE(n_local >= 0 && n_local <= words_per_rank * 32, "pack_publish: n_local exceeds the slot");
+    const int blocks = (int)std::max<int64_t>(1, std::min<int64_t>(ceil_div(2 * words_per_rank, 256), kNumSM * 4));
+    if (spk_kind == BE_B200_SPK_BOOL)
+        pack_publish_kernel<BE_B200_SPK_BOOL><<<blocks, 256, 0, s>>>(spikes_local, n_local, (uint32_t* const*)peer_bufs,
+                                                                      (uint32_t* const*)peer_flags, world, rank,
+                                                                      words_per_rank, (ExchangeCtl*)ctl);
+    else if (spk_kind == BE_B200_SPK_F32)
+        pack_publish_kernel<BE_B200_SPK_F32><<<blocks, 256, 0, s>>>(spikes_local, n_local, (uint32_t* const*)peer_bufs,
+                                                                     (uint32_t* const*)peer_flags, world, rank,
+                                                                     words_per_rank, (ExchangeCtl*)ctl);
+    else { set_error("pack_publish: unsupported event kind %d", spk_kind); return BE_B200_EINVAL; }
+    BE_LAUNCH_CHECK("pack_publish_kernel");
+    return BE_B200_OK;
+}
+
+extern "C" int be_b200_wait_exchange(const void* my_flags, const void* my_buf, int world,
+                                     int64_t words_per_rank, uint32_t* gathered_out, void* ctl, void* stream) {
+    BE_REQUIRE(my_flags && my_buf && gathered_out && ctl && world >= 1 && world <= 32, "wait_exchange: bad arguments");
+    const int blocks = (int)std::max<int64_t>(1, std::min<int64_t>(ceil_div(words_per_rank * world, 1024), kNumSM));
+    wait_copy_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>((const uint32_t*)my_flags, (const uint32_t*)my_buf, world,
+                                                              words_per_rank, gathered_out, (ExchangeCtl*)ctl);
+    BE_LAUNCH_CHECK("wait_copy_kernel");
+    return BE_B200_OK;
+}

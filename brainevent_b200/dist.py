@@ -84,6 +84,57 @@ class SpikeExchange:
         return self.gathered[: self.n_words]
 
 
+class P2PSpikeExchange(SpikeExchange):
+    """Fused bit-pack + all-gather over NVLink peer memory (csrc/exchange.cu): every rank stores
+    its packed words directly into all peers' gather buffers and flags completion; no NCCL call
+    on the per-timestep path.  Peer pointers come from a torch symmetric-memory rendezvous
+    (torch is used for the memory mapping only; the kernels are ours)."""
+
+    def __init__(self, n_neurons: int, group=None, device="cuda"):
+        super().__init__(n_neurons, group, device)
+        import torch.distributed._symmetric_memory as symm
+        from . import _lib
+        W, wpr = self.world, self.words_per_rank
+        self.n_buf = 2 * W * wpr
+        self.symm = symm.empty(self.n_buf + 64, dtype=torch.int32, device=device)
+        self.symm.zero_()
+        grp = group if group is not None else dist.group.WORLD
+        self.handle = symm.rendezvous(self.symm, grp)
+        ptrs = [int(p) for p in self.handle.buffer_ptrs]
+        self.peer_bufs = torch.tensor(ptrs, dtype=torch.int64, device=device)
+        self.peer_flags = torch.tensor([p + 4 * self.n_buf for p in ptrs], dtype=torch.int64, device=device)
+        self.ctl = torch.zeros(max(4, _lib.lib().be_b200_exchange_ctl_bytes() // 4), dtype=torch.int32, device=device)
+        self.local = self.bounds[self.rank]
+        torch.cuda.synchronize(device)
+        dist.barrier(group=group)        # every rank's buffer is zeroed before anyone publishes
+
+    def exchange_spikes(self, local_spikes: torch.Tensor) -> torch.Tensor:
+        """bool/uint8/float32 spikes of the neurons this rank owns -> int32[ceil(N/32)] global words."""
+        from . import _lib
+        from ._runtime import ptr, stream_ptr
+        s = local_spikes
+        if s.dtype in (torch.bool, torch.uint8, torch.int8):
+            kind = _lib.SPK_BOOL
+        elif s.dtype == torch.float32:
+            kind = _lib.SPK_F32
+        else:
+            s, kind = (s > 0), _lib.SPK_BOOL
+        s = s.contiguous()
+        L = _lib.lib()
+        dev = s.device
+        me = self.symm
+        _lib.check(L.be_b200_pack_publish(ptr(s), kind, s.numel(), ptr(self.peer_bufs), ptr(self.peer_flags), self.world,
+                                          self.rank, self.words_per_rank, ptr(self.ctl), stream_ptr(dev)), "pack_publish")
+        import ctypes
+        _lib.check(L.be_b200_wait_exchange(ctypes.c_void_p(me.data_ptr() + 4 * self.n_buf), ptr(me), self.world,
+                                           self.words_per_rank, ptr(self.gathered), ptr(self.ctl), stream_ptr(dev)),
+                   "wait_exchange")
+        return self.gathered[: self.n_words]
+
+    def timed_out(self) -> bool:
+        return bool(self.ctl[2].item())
+
+
 class PostShardedProjection:
     """One rank's share of a projection pre[N] -> post[N], partitioned by post block.
 
@@ -127,4 +178,6 @@ class PostShardedProjection:
         raise ValueError(self.kind)
 
     def step(self, local_spikes: torch.Tensor) -> torch.Tensor:
+        if hasattr(self.x, "exchange_spikes"):           # fused pack + peer-memory all-gather
+            return self.propagate(self.x.exchange_spikes(local_spikes))
         return self.propagate(self.x.exchange(self.pack_local(local_spikes)))
