@@ -130,7 +130,7 @@ class FcnWeak(Workload):
         self.pool = spike_pool(torch, self.n_local, rate, 99 + rank, device)     # spikes of the neurons I own
         self.exchange_kind = "nccl all_gather"
         self.x = None
-        if world > 1 and os.environ.get("BE_B200_EXCHANGE", "p2p") == "p2p":
+        if world > 1 and os.environ.get("BE_B200_EXCHANGE", "nccl") == "p2p":
             try:
                 self.x = bd.P2PSpikeExchange(self.n_total, device=device)
                 self.exchange_kind = "fused pack + NVLink peer-store all-gather (exchange.cu)"

@@ -74,9 +74,9 @@ __global__ void __launch_bounds__(256) pack_publish_kernel(const void* __restric
             for (int p = 0; p < world; ++p) peer_bufs[p][slot0 + (h >> 1)] = word;   // NVLink peer stores
         }
     }
-    __threadfence_system();
-    __syncthreads();
+    __syncthreads();                       // this CTA's peer stores are ordered before thread 0's fence
     if (threadIdx.x == 0) {
+        __threadfence_system();            // cumulative: publishes the whole CTA's stores at system scope
         const uint32_t prev = atomicAdd(&ctl->done, 1u);
         if (prev == gridDim.x - 1) {
             __threadfence_system();
