@@ -504,7 +504,7 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default="fcn", choices=["fcn", "coba", "cuba_jitc", "csr_spmm", "jitc_1m"])
+    ap.add_argument("--workload", default="fcn", choices=["fcn", "coba", "cuba_jitc", "csr_spmm", "jitc_1m", "csr_gather", "csr_scatter", "dense_mm", "jitc_1m_gather"])
     ap.add_argument("--timesteps", type=int, default=100, help="simulated timesteps per step")
     ap.add_argument("--no-extra", action="store_true", help="skip the other BASELINE configs at N=1")
     ap.add_argument("--no-graph", action="store_true")
@@ -540,6 +540,14 @@ def main():
         wl = CubaJitc(torch, be, device, corder=True)
     elif args.workload == "csr_spmm":
         wl = CsrSpmm(torch, be, device)
+    elif args.workload == "csr_gather":
+        wl = CsrMv1M(torch, be, device, gather=True, homo=True)
+    elif args.workload == "csr_scatter":
+        wl = CsrMv1M(torch, be, device, gather=False)
+    elif args.workload == "dense_mm":
+        wl = DenseMm(torch, be, device)
+    elif args.workload == "jitc_1m_gather":
+        wl = Jitc1M(torch, be, device, corder=False)
     else:
         wl = Jitc1M(torch, be, device, corder=True)
 

@@ -21,11 +21,13 @@
 #include "common.cuh"
 
 #include <algorithm>
+#include <cstdlib>
 
 namespace be {
 
 constexpr int TC_BM = 128, TC_BK = 32, TC_THREADS = 256, TC_STAGES = 2;   // BN (batch tile) is a template parameter: 64 / 128 / 256
 constexpr int TC_A_PLANE = TC_BM * TC_BK * 2;            // 8 KB: one bf16 plane of the A tile
+constexpr int TC_MAX_KB = 2048;                            // k-blocks per CTA (live map in shared memory)
 constexpr int TC_ITEMS = (TC_BK / 8) * 8 / 8;            // [8 k x 16 m] load items per warp per k-block
 __host__ __device__ constexpr int tc_stage_bytes(int bn) { return 3 * TC_A_PLANE + bn * TC_BK * 2; }
 __host__ __device__ constexpr int tc_smem_bytes(int bn) { return TC_STAGES * tc_stage_bytes(bn) + 1024; }
@@ -81,14 +83,24 @@ __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint6
         : "memory");
 }
 
-__device__ __forceinline__ uint32_t pack_bf16(__nv_bfloat16 a, __nv_bfloat16 b) {
-    return (uint32_t)__bfloat16_as_ushort(a) | ((uint32_t)__bfloat16_as_ushort(b) << 16);
+// (a, b) -> packed bf16x2 planes hi / mid / lo with a = hi.x + mid.x + lo.x (to 2^-24 relative)
+__device__ __forceinline__ uint32_t cvt_bf16x2(float a, float b) {
+    uint32_t r;
+    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(b), "f"(a));   // upper half <- first source operand
+    return r;
+}
+__device__ __forceinline__ void split3(float a, float b, uint32_t& hi, uint32_t& mid, uint32_t& lo) {
+    hi = cvt_bf16x2(a, b);
+    const float ra = a - __uint_as_float(hi << 16), rb = b - __uint_as_float(hi & 0xffff0000u);
+    mid = cvt_bf16x2(ra, rb);
+    const float sa = ra - __uint_as_float(mid << 16), sb = rb - __uint_as_float(mid & 0xffff0000u);
+    lo = cvt_bf16x2(sa, sb);
 }
 
 template <int TC_BN>
 __global__ void __launch_bounds__(TC_THREADS, (TC_BN == 64) ? 3 : 2)
 dense_mm_t_tc_kernel(const float* __restrict__ W, int64_t k, int64_t m, const uint32_t* __restrict__ packed, int wpr,
-                     int64_t n, float* __restrict__ out, int kb_per_split, int split_k) {
+                     int64_t n, float* __restrict__ out, int kb_per_split, int split_k, int lane_map) {
     extern __shared__ __align__(1024) uint8_t smem[];
     __shared__ uint64_t empty_bar[TC_STAGES];
     __shared__ uint64_t done_bar;
@@ -120,50 +132,109 @@ dense_mm_t_tc_kernel(const float* __restrict__ W, int64_t k, int64_t m, const ui
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem_d = tmem_base_s;
 
-    // next k-block >= kb whose TC_BK sources are not all silent in my columns (event-driven skip:
-    // a silent block is dropped before its weights are read); uniform across the CTA
-    auto find_next = [&](int kb) {
-        for (; kb < kb_end; ++kb) {
-            uint32_t my_word = 0;
-            if (tid < WPT * TC_BK) {
-                const int64_t kr = (int64_t)kb * TC_BK + (tid / WPT);
-                const int w = (int)(n0 >> 5) + (tid % WPT);
-                if (kr < k && w < wpr) my_word = __ldg(packed + kr * wpr + w);
-                const int64_t cbase = (int64_t)w * 32;
-                if (cbase + 32 > n) my_word &= (n > cbase) ? ((1u << (n - cbase)) - 1u) : 0u;
-            }
-            if (__syncthreads_or(my_word != 0u)) break;
+    // ---- live-block map (event-driven skip): one pass over this CTA's share of the packed spikes,
+    // all threads in parallel, result in shared memory; a silent k-block is then dropped before its
+    // weights are read, without any global-memory latency inside the main loop
+    __shared__ uint8_t s_live[TC_MAX_KB];
+    const int n_kb = kb_end - kb_begin;
+    for (int i = tid; i < n_kb; i += TC_THREADS) s_live[i] = 0;
+    __syncthreads();
+    for (int item = tid; item < n_kb * TC_BK; item += TC_THREADS) {
+        const int64_t kr = (int64_t)kb_begin * TC_BK + item;
+        if (kr >= k) continue;
+        uint32_t any = 0;
+#pragma unroll
+        for (int w = 0; w < WPT; ++w) {
+            const int wi = (int)(n0 >> 5) + w;
+            if (wi >= wpr) break;
+            uint32_t word = __ldg(packed + kr * wpr + wi);
+            const int64_t cbase = (int64_t)wi * 32;
+            if (cbase + 32 > n) word &= (n > cbase) ? ((1u << (n - cbase)) - 1u) : 0u;
+            any |= word;
         }
+        if (any) s_live[item / TC_BK] = 1;
+    }
+    __syncthreads();
+    auto find_next = [&](int kb) {
+        while (kb < kb_end && !s_live[kb - kb_begin]) ++kb;
         return kb;
     };
-    // each warp streams TC_ITEMS [8 k x 16 m] patches of the tile: lane = (k8 = lane/4, quad = lane%4)
-    auto load_tile = [&](int kb, float4 (&wv)[TC_ITEMS]) {
+    // each warp streams TC_ITEMS [8 k x 16 m] patches of the tile: lane = (k8 = lane/4, quad = lane%4);
+    // the spike words this thread will expand into the B tile are fetched with the same batch of loads.
+    // Per-thread offsets are loop-invariant; interior tiles (the common case) take a path without
+    // any bounds checks.
+    constexpr int B_CELLS = TC_BK * (TC_BN / 8) / TC_THREADS;      // (k, n-octet) cells per thread
+    const int k8_l = lane_map ? (lane & 7) : (lane >> 2);
+    const int quad_l = lane_map ? (lane >> 3) : (lane & 3);
+    int64_t a_goff[TC_ITEMS];     // element offset of my float4 inside a k-block of W
+    uint32_t a_soff[TC_ITEMS];    // byte offset of my 4 elements inside an A plane
+#pragma unroll
+    for (int i = 0; i < TC_ITEMS; ++i) {
+        const int item = warp * TC_ITEMS + i;              // (kk, mq) = (item / 8, item % 8)
+        const int kk = item >> 3, mq = item & 7;
+        const int m_local = mq * 16 + quad_l * 4;
+        a_goff[i] = (int64_t)(kk * 8 + k8_l) * m + m0 + m_local;
+        a_soff[i] = (uint32_t)((kk * 16 + (m_local >> 3)) * 128 + k8_l * 16 + (m_local & 7) * 2);
+    }
+    int b_k[B_CELLS], b_sh[B_CELLS];
+    int64_t b_goff[B_CELLS];
+    uint32_t b_soff[B_CELLS];
+#pragma unroll
+    for (int i = 0; i < B_CELLS; ++i) {
+        const int cell = tid + i * TC_THREADS;              // k8 fastest: 8 lanes fill one 128-byte core matrix
+        const int k_local = (cell / (8 * (TC_BN / 8))) * 8 + (cell & 7), ni = (cell >> 3) % (TC_BN / 8);
+        const int64_t c0 = n0 + ni * 8;
+        b_k[i] = k_local;
+        b_sh[i] = (int)(c0 & 31);
+        b_goff[i] = (int64_t)k_local * wpr + (c0 >> 5);
+        b_soff[i] = (uint32_t)(((k_local >> 3) * (TC_BN / 8) + ni) * 128 + (k_local & 7) * 16);
+    }
+    const bool m_interior = (m0 + TC_BM <= m);
+    const bool n_interior = (n0 + TC_BN <= n);
+    auto load_tile = [&](int kb, float4 (&wv)[TC_ITEMS], uint32_t (&bw)[B_CELLS]) {
         const int64_t k0 = (int64_t)kb * TC_BK;
+        const float* wbase = W + k0 * m;
+        const uint32_t* pbase = packed + k0 * wpr;
+        if (m_interior && n_interior && k0 + TC_BK <= k) {
+#pragma unroll
+            for (int i = 0; i < TC_ITEMS; ++i) wv[i] = __ldg(reinterpret_cast<const float4*>(wbase + a_goff[i]));
+#pragma unroll
+            for (int i = 0; i < B_CELLS; ++i) bw[i] = (__ldg(pbase + b_goff[i]) >> b_sh[i]) & 0xffu;
+            return;
+        }
 #pragma unroll
         for (int i = 0; i < TC_ITEMS; ++i) {
-            const int item = warp * TC_ITEMS + i;          // (kk, mq) = (item / 8, item % 8)
-            const int64_t kr = k0 + (item >> 3) * 8 + (lane >> 2);
-            const int64_t mc = m0 + (item & 7) * 16 + (lane & 3) * 4;
-            if (kr < k && mc + 3 < m) wv[i] = __ldg(reinterpret_cast<const float4*>(W + kr * m + mc));
-            else {
-                float t[4];
+            const int item = warp * TC_ITEMS + i;
+            const int64_t kr = k0 + (item >> 3) * 8 + k8_l;
+            const int64_t mc = m0 + (item & 7) * 16 + quad_l * 4;
+            float t[4];
 #pragma unroll
-                for (int q = 0; q < 4; ++q) t[q] = (kr < k && mc + q < m) ? __ldg(W + kr * m + mc + q) : 0.0f;
-                wv[i] = make_float4(t[0], t[1], t[2], t[3]);
+            for (int q = 0; q < 4; ++q) t[q] = (kr < k && mc + q < m) ? __ldg(W + kr * m + mc + q) : 0.0f;
+            wv[i] = make_float4(t[0], t[1], t[2], t[3]);
+        }
+#pragma unroll
+        for (int i = 0; i < B_CELLS; ++i) {
+            const int64_t kr = k0 + b_k[i];
+            const int64_t c0 = n0 + (int64_t)(((tid + i * TC_THREADS) >> 3) % (TC_BN / 8)) * 8;
+            uint32_t bits = 0;
+            if (kr < k && c0 < n) {
+                bits = (__ldg(pbase + b_goff[i]) >> b_sh[i]) & 0xffu;
+                if (c0 + 8 > n) bits &= (1u << (n - c0)) - 1u;
             }
+            bw[i] = bits;
         }
     };
 
     int n_issued = 0;      // k-blocks that actually reached the tensor core (uniform across the CTA)
     float4 cur[TC_ITEMS], nxt[TC_ITEMS];
+    uint32_t cur_b[B_CELLS], nxt_b[B_CELLS];
     int kb = find_next(kb_begin);
-    if (kb < kb_end) load_tile(kb, cur);
+    if (kb < kb_end) load_tile(kb, cur, cur_b);
     while (kb < kb_end) {
-        const int64_t k0 = (int64_t)kb * TC_BK;
         // software pipeline: the next live block's weights are in flight while this one is
         // converted, staged and multiplied
         const int kb_next = find_next(kb + 1);
-        if (kb_next < kb_end) load_tile(kb_next, nxt);
+        if (kb_next < kb_end) load_tile(kb_next, nxt, nxt_b);
 
         const int stage = n_issued % TC_STAGES;
         uint8_t* sA = smem + stage * TC_STAGE_BYTES;
@@ -172,42 +243,23 @@ dense_mm_t_tc_kernel(const float* __restrict__ W, int64_t k, int64_t m, const ui
         // ---- A: split into bf16 hi/mid/lo planes, MN-major core matrices ------------------------
 #pragma unroll
         for (int i = 0; i < TC_ITEMS; ++i) {
-            const int item = warp * TC_ITEMS + i;
-            const int kk = item >> 3, mq = item & 7;
-            const int k8 = lane >> 2;
-            const int m_local = mq * 16 + (lane & 3) * 4;
-            const uint32_t off = (uint32_t)((kk * 16 + (m_local >> 3)) * 128 + k8 * 16 + (m_local & 7) * 2);
-            const float w4[4] = {cur[i].x, cur[i].y, cur[i].z, cur[i].w};
-            __nv_bfloat16 hi[4], mid[4], lo[4];
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-                hi[q] = __float2bfloat16_rn(w4[q]);
-                const float r1 = w4[q] - __bfloat162float(hi[q]);
-                mid[q] = __float2bfloat16_rn(r1);
-                const float r2 = r1 - __bfloat162float(mid[q]);
-                lo[q] = __float2bfloat16_rn(r2);
-            }
-            *reinterpret_cast<uint2*>(sA + off) = make_uint2(pack_bf16(hi[0], hi[1]), pack_bf16(hi[2], hi[3]));
-            *reinterpret_cast<uint2*>(sA + TC_A_PLANE + off) = make_uint2(pack_bf16(mid[0], mid[1]), pack_bf16(mid[2], mid[3]));
-            *reinterpret_cast<uint2*>(sA + 2 * TC_A_PLANE + off) = make_uint2(pack_bf16(lo[0], lo[1]), pack_bf16(lo[2], lo[3]));
+            // error-free 3-way split, two elements per cvt.rn.bf16x2.f32
+            uint32_t hi[2], mid[2], lo[2];
+            split3(cur[i].x, cur[i].y, hi[0], mid[0], lo[0]);
+            split3(cur[i].z, cur[i].w, hi[1], mid[1], lo[1]);
+            *reinterpret_cast<uint2*>(sA + a_soff[i]) = make_uint2(hi[0], hi[1]);
+            *reinterpret_cast<uint2*>(sA + TC_A_PLANE + a_soff[i]) = make_uint2(mid[0], mid[1]);
+            *reinterpret_cast<uint2*>(sA + 2 * TC_A_PLANE + a_soff[i]) = make_uint2(lo[0], lo[1]);
         }
-        // ---- B: 0/1 bf16 from the spike bits: TC_BK x 8 (k, n-octet) cells ------------------------
-        for (int cell = tid; cell < TC_BK * (TC_BN / 8); cell += TC_THREADS) {
-            const int k_local = cell / (TC_BN / 8), ni = cell % (TC_BN / 8);
-            const int64_t kr = k0 + k_local;
-            const int64_t c0 = n0 + ni * 8;
-            uint32_t bits = 0;
-            if (kr < k && c0 < n) {
-                const uint32_t word = __ldg(packed + kr * wpr + (c0 >> 5));
-                bits = (word >> (c0 & 31)) & 0xffu;
-                if (c0 + 8 > n) bits &= (1u << (n - c0)) - 1u;
-            }
+        // ---- B: 0/1 bf16 from the prefetched spike bits ---------------------------------------------
+#pragma unroll
+        for (int i = 0; i < B_CELLS; ++i) {
+            const uint32_t bits = cur_b[i];
             uint32_t v[4];
 #pragma unroll
             for (int q = 0; q < 4; ++q)
                 v[q] = ((bits >> (2 * q)) & 1u ? 0x3f80u : 0u) | ((bits >> (2 * q + 1)) & 1u ? 0x3f800000u : 0u);
-            const uint32_t off = (uint32_t)(((k_local >> 3) * (TC_BN / 8) + ni) * 128 + (k_local & 7) * 16);
-            *reinterpret_cast<uint4*>(sB + off) = make_uint4(v[0], v[1], v[2], v[3]);
+            *reinterpret_cast<uint4*>(sB + b_soff[i]) = make_uint4(v[0], v[1], v[2], v[3]);
         }
         // generic-proxy writes -> visible to the tensor core (async proxy)
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -230,6 +282,8 @@ dense_mm_t_tc_kernel(const float* __restrict__ W, int64_t k, int64_t m, const ui
         kb = kb_next;
 #pragma unroll
         for (int i = 0; i < TC_ITEMS; ++i) cur[i] = nxt[i];
+#pragma unroll
+        for (int i = 0; i < B_CELLS; ++i) cur_b[i] = nxt_b[i];
     }
 
     // ---- drain + epilogue ---------------------------------------------------------------------
@@ -283,11 +337,14 @@ dense_mm_t_tc_kernel(const float* __restrict__ W, int64_t k, int64_t m, const ui
 int launch_dense_mm_t_tc(const float* W, int64_t k, int64_t m, const uint32_t* packed, int wpr, int64_t n,
                          float* out, cudaStream_t s) {
     if (m == 0 || n == 0) return BE_B200_OK;
+    const char* lm = getenv("BE_B200_TC_LANEMAP");
+    const int lane_map = lm ? (lm[0] != '0') : 0;   // 0: row-quad lanes (measured faster), 1: half-warp per core matrix
     // widest batch tile that the batch fills: W is read once per batch tile
     const int bn = n > 128 ? 256 : (n > 64 ? 128 : 64);
     const int total_kb = (int)ceil_div(k, TC_BK);
     const int64_t tiles = ceil_div(m, TC_BM) * ceil_div(n, bn);
     int split_k = (int)std::max<int64_t>(1, std::min<int64_t>({(int64_t)total_kb, (6 * kNumSM) / std::max<int64_t>(tiles, 1), (int64_t)32}));
+    split_k = std::max(split_k, (int)ceil_div(std::max(total_kb, 1), TC_MAX_KB));
     const int kb_per_split = (int)ceil_div(std::max(total_kb, 1), split_k);
     split_k = (int)ceil_div(std::max(total_kb, 1), kb_per_split);
     if (split_k > 1) BE_CUDA(cudaMemsetAsync(out, 0, (size_t)(m * n) * sizeof(float), s));
@@ -298,7 +355,7 @@ int launch_dense_mm_t_tc(const float* W, int64_t k, int64_t m, const uint32_t* p
         dim3 grid((unsigned)ceil_div(m, TC_BM), (unsigned)split_k, (unsigned)ceil_div(n, BN));                 \
         ProfileScope prof(s);                                                                                  \
         dense_mm_t_tc_kernel<BN><<<grid, TC_THREADS, tc_smem_bytes(BN), s>>>(W, k, m, packed, wpr, n, out,     \
-                                                                            kb_per_split, split_k);           \
+                                                                            kb_per_split, split_k, lane_map); \
     } while (0)
     if (bn == 64) BE_TC_LAUNCH(64); else if (bn == 128) BE_TC_LAUNCH(128); else BE_TC_LAUNCH(256);
 #undef BE_TC_LAUNCH
