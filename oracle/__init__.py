@@ -322,17 +322,19 @@ def binary_fcnmm(weights, indices, matrix, *, shape, transpose=False):
 # ----------------------------------------------------------------------------------------------
 # JITC
 # ----------------------------------------------------------------------------------------------
-def _jit_mv(kind, p0, p1, prob, vector, seed, shape, transpose, corder, dtype):
+def _jit_mv(kind, p0, p1, prob, vector, seed, shape, transpose, corder, dtype, rows=None):
     clen = conn_length(prob)
     act = active_mask(vector)
     out_len = shape[1] if transpose else shape[0]
     vec_len = shape[0] if transpose else shape[1]
     assert act.shape[0] == vec_len
     chunk = normalize_chunk_size(shape[1])
-    out = np.zeros(out_len, dtype)
+    r0, rn = (0, out_len) if rows is None else rows
+    assert rows is None or corder, "row subsampling is defined for the gather orientation only"
+    out = np.zeros(rn if corder else out_len, dtype)
     getattr(lib(), "ora_jitmv" + _sfx(dtype))(
         kind, _scalar(dtype, p0), _scalar(dtype, p1), _u32(clen), _u32(seed), _p(act),
-        _i64(vec_len), _i64(out_len), _i64(chunk), int(bool(corder)), _p(out))
+        _i64(vec_len), _i64(out_len), _i64(chunk), int(bool(corder)), _i64(r0), _i64(rn), _p(out))
     return out
 
 
@@ -352,9 +354,9 @@ def _jit_mm(kind, p0, p1, prob, B, seed, shape, transpose, corder, dtype):
 
 
 def binary_jitsmv(weight, prob, vector, seed, *, shape, transpose=False, corder=True,
-                  dtype=np.float32):
-    """_jit_scalar/binary.py:44."""
-    return _jit_mv(0, weight, 0.0, prob, vector, seed, shape, transpose, corder, dtype)
+                  dtype=np.float32, rows=None):
+    """_jit_scalar/binary.py:44.  rows=(offset, count): gather orientation, row subsample."""
+    return _jit_mv(0, weight, 0.0, prob, vector, seed, shape, transpose, corder, dtype, rows)
 
 
 def binary_jitsmm(weight, prob, B, seed, *, shape, transpose=False, corder=True, dtype=np.float32):
@@ -363,9 +365,9 @@ def binary_jitsmm(weight, prob, B, seed, *, shape, transpose=False, corder=True,
 
 
 def binary_jitnmv(w_loc, w_scale, prob, vector, seed, *, shape, transpose=False, corder=True,
-                  dtype=np.float32):
+                  dtype=np.float32, rows=None):
     """_jit_normal/binary.py:44."""
-    return _jit_mv(1, w_loc, w_scale, prob, vector, seed, shape, transpose, corder, dtype)
+    return _jit_mv(1, w_loc, w_scale, prob, vector, seed, shape, transpose, corder, dtype, rows)
 
 
 def binary_jitnmm(w_loc, w_scale, prob, B, seed, *, shape, transpose=False, corder=True,
@@ -375,9 +377,9 @@ def binary_jitnmm(w_loc, w_scale, prob, B, seed, *, shape, transpose=False, cord
 
 
 def binary_jitumv(w_low, w_high, prob, vector, seed, *, shape, transpose=False, corder=True,
-                  dtype=np.float32):
+                  dtype=np.float32, rows=None):
     """_jit_uniform/binary.py:44."""
-    return _jit_mv(2, w_low, w_high, prob, vector, seed, shape, transpose, corder, dtype)
+    return _jit_mv(2, w_low, w_high, prob, vector, seed, shape, transpose, corder, dtype, rows)
 
 
 def binary_jitumm(w_low, w_high, prob, B, seed, *, shape, transpose=False, corder=True,

@@ -390,3 +390,98 @@ def test_rate_selected_scatter_or_gather(G, homo, rate):
         a = (be.BinaryArray(t(v)) @ csr).cpu().numpy()
         b = (be.BinaryArray(t(v)) @ csr).cpu().numpy()
         np.testing.assert_array_equal(a, b)
+
+
+# ---- BASELINE.json sizes ---------------------------------------------------------------------
+def test_baseline_c2_cuba_400k_jitc_scalar(G):
+    """configs[1]: JITCScalarR (320000, 400000) and (80000, 400000), prob 2e-4, seed 42, 0.24 % spikes.
+    Scatter orientation: the FULL result against the oracle.  Gather orientation (the class default):
+    4000 output rows against the oracle's row-subsampled walk, plus gather == scatter-of-the-other
+    -orientation is NOT expected (different matrices), so each is pinned on its own."""
+    import brainevent_b200 as be
+    for n_pre, w in ((320_000, 1.62), (80_000, -9.0)):
+        shape = (n_pre, 400_000)
+        spk = cases.spikes(n_pre, n_pre, 0.0024)
+        t = torch.as_tensor(spk, device="cuda")
+        sc = (be.BinaryArray(t) @ be.JITCScalarR((w, 2e-4, 42), shape=shape, corder=True)).cpu().numpy()
+        ref = O.binary_jitsmv(w, 2e-4, spk, 42, shape=shape, transpose=True, corder=False)
+        np.testing.assert_allclose(sc, ref, rtol=RTOL, atol=1e-5)
+        assert np.count_nonzero(ref) > 10_000
+        ga = (be.BinaryArray(t) @ be.JITCScalarR((w, 2e-4, 42), shape=shape, corder=False)).cpu().numpy()
+        for r0 in (0, 123_456, 396_000):
+            refg = O.binary_jitsmv(w, 2e-4, spk, 42, shape=shape, transpose=True, corder=True, rows=(r0, 4000))
+            np.testing.assert_allclose(ga[r0:r0 + 4000], refg, rtol=RTOL, atol=1e-5)
+
+
+def test_baseline_c4_jitc_1m_normal_uniform(G):
+    """configs[3]: 1M x 1M, prob 1e-3, seed 123, Normal(1, 0.1) and Uniform(0, 1): scatter in full
+    at 0.1 % spikes, gather on row subsamples at 1 %; connectivity index-for-index on sampled rows."""
+    import brainevent_b200 as be
+    n, prob, seed = 1_000_000, 1e-3, 123
+    shape = (n, n)
+    spk_lo, spk_hi = cases.spikes(1, n, 0.001), cases.spikes(2, n, 0.01)
+    for cls, ofn, params in ((be.JITCNormalR, O.binary_jitnmv, (1.0, 0.1)), (be.JITCUniformR, O.binary_jitumv, (0.0, 1.0))):
+        sc = (be.BinaryArray(torch.as_tensor(spk_lo, device="cuda")) @ cls((*params, prob, seed), shape=shape, corder=True)).cpu().numpy()
+        ref = ofn(*params, prob, spk_lo, seed, shape=shape, transpose=True, corder=False)
+        np.testing.assert_allclose(sc, ref, rtol=RTOL, atol=2e-5)
+        ga = (be.BinaryArray(torch.as_tensor(spk_hi, device="cuda")) @ cls((*params, prob, seed), shape=shape, corder=False)).cpu().numpy()
+        for r0 in (0, 500_000, 998_000):
+            refg = ofn(*params, prob, spk_hi, seed, shape=shape, transpose=True, corder=True, rows=(r0, 2000))
+            np.testing.assert_allclose(ga[r0:r0 + 2000], refg, rtol=RTOL, atol=2e-5)
+    chunk = O.normalize_chunk_size(n)
+    counts, cols = be.jitc_row_connections(prob, seed, (777_000, 64), n, chunk, stride=32, cap=2048)
+    counts, cols = counts.cpu().numpy(), cols.cpu().numpy()
+    for i in (0, 17, 63):
+        oc = O.jitc_row_connections(seed, O.conn_length(prob), 777_000 + i, n, chunk, 32)
+        assert counts[i] == oc.size and 800 < oc.size < 1200
+        np.testing.assert_array_equal(cols[i, :counts[i]], oc)
+
+
+def test_baseline_c3_spmm_batch64(G):
+    """configs[2]: 1M x 1M CSR, 100 nnz/row, batch 64: checksum + per-column equivalence with the
+    matvec on the same matrix (size-independent properties; the CPU oracle would need minutes)."""
+    import brainevent_b200 as be
+    n, nnz, batch = 1_000_000, 100, 64
+    g = torch.Generator(device="cuda").manual_seed(3)
+    indptr = torch.arange(0, (n + 1) * nnz, nnz, device="cuda", dtype=torch.int32)
+    indices = torch.randint(0, n, (n * nnz,), device="cuda", dtype=torch.int32, generator=g)
+    w = torch.rand(n * nnz, device="cuda", generator=g)
+    B = torch.rand((n, batch), device="cuda", generator=g) < 0.01
+    Y = be.binary_csrmm(w, indices, indptr, B, shape=(n, n), transpose=True)
+    assert tuple(Y.shape) == (n, batch)
+    for c in (0, 31, 32, 63):
+        y = be.binary_csrmv(w, indices, indptr, B[:, c].contiguous(), shape=(n, n), transpose=True)
+        torch.testing.assert_close(Y[:, c], y, rtol=1e-4, atol=1e-4)
+    rows_w = w.view(n, nnz).double().sum(1)
+    expect = (B.double() * rows_w[:, None]).sum(0)
+    torch.testing.assert_close(Y.double().sum(0), expect, rtol=1e-6, atol=1e-2)
+    # gather direction on the same operands: csr @ B against per-column matvecs
+    Z = be.binary_csrmm(w, indices, indptr, B, shape=(n, n), transpose=False)
+    for c in (5, 40):
+        z = be.binary_csrmv(w, indices, indptr, B[:, c].contiguous(), shape=(n, n), transpose=False)
+        torch.testing.assert_close(Z[:, c], z, rtol=1e-5, atol=1e-5)
+
+
+def test_baseline_c5_fcn_shard(G):
+    """configs[4]: one GPU's shard of the 10M x 1000 network post-sharded over 8 GPUs
+    (10M pre rows x 125 local synapses, packed global spikes): checksum + linearity + a 2000-row
+    slice against the oracle."""
+    import brainevent_b200 as be
+    n_total, n_local, conn = 10_000_000, 1_250_016, 125
+    g = torch.Generator(device="cuda").manual_seed(9)
+    idx = torch.randint(0, n_local, (n_total, conn), device="cuda", dtype=torch.int32, generator=g)
+    w = torch.rand((n_total, conn), device="cuda", generator=g)
+    s1 = torch.rand(n_total, device="cuda", generator=g) < 0.01
+    s2 = (torch.rand(n_total, device="cuda", generator=g) < 0.01) & ~s1
+    f = lambda s: be.binary_fcnmv(w, idx, be.BitPackedBinary(s), shape=(n_total, n_local), transpose=True)
+    y1, y2, y12 = f(s1), f(s2), f(s1 | s2)
+    torch.testing.assert_close(y12, y1 + y2, rtol=1e-4, atol=1e-4)
+    expect = w[s1].double().sum()
+    assert abs(y1.double().sum().item() - expect.item()) <= 1e-6 * expect.item() + 1e-2
+    torch.testing.assert_close(f(s1), be.binary_fcnmv(w, idx, s1, shape=(n_total, n_local), transpose=True), rtol=1e-4, atol=1e-4)
+    # exact check on a slice: only pre rows [0, 2000) active
+    s3 = torch.zeros(n_total, dtype=torch.bool, device="cuda")
+    s3[:2000] = s1[:2000] | s2[:2000] | (torch.arange(2000, device="cuda") % 7 == 0)
+    ref = O.binary_fcnmv(w[:2000].cpu().numpy(), idx[:2000].cpu().numpy(), s3[:2000].cpu().numpy(),
+                         shape=(2000, n_local), transpose=True)
+    np.testing.assert_allclose(f(s3).cpu().numpy(), ref, rtol=RTOL, atol=1e-5)
