@@ -485,3 +485,50 @@ def test_baseline_c5_fcn_shard(G):
     ref = O.binary_fcnmv(w[:2000].cpu().numpy(), idx[:2000].cpu().numpy(), s3[:2000].cpu().numpy(),
                          shape=(2000, n_local), transpose=True)
     np.testing.assert_allclose(f(s3).cpu().numpy(), ref, rtol=RTOL, atol=1e-5)
+
+
+@pytest.mark.parametrize("dt", ["float64", "float16", "bfloat16"])
+def test_other_weight_dtypes(G, dt):
+    """Weight/output dtypes f64, f16, bf16 (ref: include/brainevent/tensor.h:42-59): same kernels,
+    accumulation in f32 (f64 for f64), result in the weight dtype."""
+    import brainevent_b200 as be
+    tdt = getattr(torch, dt)
+    tol = dict(float64=1e-12, float16=3e-2, bfloat16=1e-1)[dt]
+    def T(x):
+        return torch.as_tensor(x, device="cuda")
+    def W(x):       # weights rounded to the target dtype, plus their exact float64 values for the oracle
+        w = torch.as_tensor(x, device="cuda").to(tdt)
+        return w, w.double().cpu().numpy()
+    def close(got, ref):
+        assert got.dtype == tdt
+        np.testing.assert_allclose(got.double().cpu().numpy(), ref, rtol=tol, atol=tol)
+    f = cases.fcn_case(60, 900, 700, 20)
+    w, w64 = W(f["weights"])
+    for tr in (True, False):
+        s = cases.spikes(61, 900 if tr else 700, 0.1)
+        close(be.binary_fcnmv(w, T(f["indices"]), T(s), shape=(900, 700), transpose=tr),
+              O.binary_fcnmv(w64, f["indices"], s, shape=(900, 700), transpose=tr))
+        B = cases.spikes(62, 900 if tr else 700, 0.05, batch=40)
+        close(be.binary_fcnmm(w, T(f["indices"]), T(B), shape=(900, 700), transpose=tr),
+              O.binary_fcnmm(w64, f["indices"], B, shape=(900, 700), transpose=tr))
+    c = cases.csr_case(63, 800, 600, 15, 0.1, ragged=True)
+    w, w64 = W(c["data"])
+    B = cases.spikes(64, 800, 0.05, batch=64)
+    close(be.binary_csrmm(w, T(c["indices"]), T(c["indptr"]), T(B), shape=c["shape"], transpose=True),
+          O.binary_csrmm(w64, c["indices"], c["indptr"], B, shape=c["shape"], transpose=True))
+    # JITC: parameters in the weight dtype
+    v = cases.spikes(65, 500, 0.2)
+    for corder in (False, True):
+        p0, p0_64 = W(np.array([1.5]))
+        close(be.binary_jitsmv(p0, 0.05, T(v), 3, shape=(500, 640), transpose=True, corder=corder),
+              O.binary_jitsmv(float(p0_64[0]), 0.05, v, 3, shape=(500, 640), transpose=True, corder=corder, dtype=np.float64))
+        (a, a64), (b, b64) = W(np.array([1.0])), W(np.array([0.25]))
+        close(be.binary_jitumv(a, b + a, 0.05, T(v), 3, shape=(500, 640), transpose=True, corder=corder),
+              O.binary_jitumv(float(a64[0]), float((b + a).double().cpu()[0]), 0.05, v, 3, shape=(500, 640), transpose=True,
+                              corder=corder, dtype=np.float64))
+    Wd, Wd64 = W(np.random.default_rng(66).standard_normal((300, 260)))
+    for tr in (True, False):
+        s = cases.spikes(67, 300 if tr else 260, 0.1)
+        close(be.binary_densemv(Wd, T(s), transpose=tr), O.binary_densemv(Wd64, s, transpose=tr))
+        B = cases.spikes(68, 300 if tr else 260, 0.1, batch=70)
+        close(be.binary_densemm(Wd, T(B), transpose=tr), O.binary_densemm(Wd64, B, transpose=tr))
