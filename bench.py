@@ -107,6 +107,13 @@ def spike_pool(torch, n, rate, seed, device):
     return torch.rand((POOL, n), device=device, generator=g) < rate
 
 
+def fcn_workload_text(n_total, n_conn, rate, shards):
+    return (f"FixedNumPerPre {n_total} neurons x {n_conn} synapses/neuron, fp32 hetero weights, "
+            f"{rate:.0%} spikes/timestep, post-sharded over {shards} GPU(s) "
+            f"({n_total // shards} post neurons and {n_conn // shards} synapses/pre-neuron per GPU, "
+            "targets stratified evenly over post blocks), BASELINE configs[4] at 8 GPUs")
+
+
 class FcnWeak(Workload):
     """FixedNumPerPre, post-sharded, weak scaling (configs[4] at N = 8)."""
     name = "fcn_perpre_postsharded"
@@ -154,10 +161,7 @@ class FcnWeak(Workload):
         self.active_per_timestep = float(per_t.mean().item())
         self.events_per_timestep = self.active_per_timestep * self.conn_local          # per rank
         self.extra_bytes_per_timestep = 4.0 * self.active_per_timestep
-        self.config = {"workload": f"FixedNumPerPre {self.n_total} neurons x {n_conn} synapses/neuron, fp32 hetero weights, "
-                                   f"{rate:.0%} spikes/timestep, post-sharded over {world} GPU(s) "
-                                   f"({self.n_local} post neurons and {self.conn_local} synapses/pre-neuron per GPU, "
-                                   "targets stratified evenly over post blocks), BASELINE configs[4] at 8 GPUs",
+        self.config = {"workload": fcn_workload_text(self.n_total, n_conn, rate, shards),
                        "neurons": self.n_total, "synapses_per_neuron": n_conn, "spike_rate": rate,
                        "spike_exchange": self.exchange_kind if world > 1 else "none (single GPU)"}
 
@@ -411,12 +415,26 @@ def kernel_profile(torch, L, wl, T, kernels_per_timestep_filter=None):
     return ms
 
 
+def measured_traffic(wl):
+    """DRAM bytes per launch of the dominant kernel from the committed ncu capture (None if this
+    workload has not been captured)."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+            t = json.load(f)
+        key = wl.name + ("_shard8" if getattr(wl, "emulate", 0) == 8 else "")
+        if getattr(wl, "world", 1) > 1:
+            return None
+        return t[key]["bytes_per_launch"] if key in t else None
+    except Exception:
+        return None
+
+
 def roofline(wl, kernel_ms, peak_gbs, peak_src, kernels_per_timestep=1):
     per_launch_bytes = wl.algorithmic_bytes_per_timestep() / kernels_per_timestep
     avg_ms = float(np.mean(kernel_ms)) if len(kernel_ms) else float("nan")
     achieved = per_launch_bytes / (avg_ms * 1e-3) / 1e9 if avg_ms > 0 else float("nan")
     return {"bound": "hbm", "kernel": wl.dominant_kernel, "achieved": round(achieved, 1), "peak": peak_gbs,
-            "unit": "GB/s", "frac": round(achieved / peak_gbs, 4), "traffic": None,
+            "unit": "GB/s", "frac": round(achieved / peak_gbs, 4), "traffic": measured_traffic(wl),
             "peak_source": peak_src, "algorithmic_bytes_per_launch": round(per_launch_bytes),
             "kernel_ms_avg": round(avg_ms, 5), "kernel_launches_timed": int(len(kernel_ms))}
 
@@ -457,8 +475,10 @@ def run_reference(args):
     line = {"impl": "reference", "metric": "synaptic events/sec", "value": value, "unit": "events/s",
             "n_gpus": args.gpus, "steps": K, "warmup": W, "ms_per_step": 1e3 * total_t / K,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "FixedNumPerPre x 1000 synapses/neuron, fp32 hetero weights, 1% spikes/timestep "
-                                   "(same projection as the GPU arm; bounded sample of the pre rows)"},
+            "config": {"workload": fcn_workload_text(FCN_NEURONS_PER_GPU * max(args.gpus, 1), FCN_CONN, RATE, max(args.gpus, 1)),
+                       "neurons": FCN_NEURONS_PER_GPU * max(args.gpus, 1), "synapses_per_neuron": FCN_CONN, "spike_rate": RATE,
+                       "reference_arm": "reference algorithm (oracle port of _fcn/binary.py:156-253) on the host CPU, bounded "
+                                        "sample of the pre rows of the same projection"},
             "cpu_baseline": {"value": value, "unit": "events/s", "cores": 1, "kind": "port", "sample": sample},
             "e2e": {"value": value, "unit": "events/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
