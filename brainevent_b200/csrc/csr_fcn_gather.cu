@@ -31,10 +31,38 @@ __global__ void __launch_bounds__(SMEM ? 1024 : 256) gather_mv_kernel(Rows rows,
     if (sel_thr >= 0 && *sel_n_active <= sel_thr) return;   // the scatter variant owns this call
     extern __shared__ __align__(16) uint32_t s_bits[];
     if (SMEM) {
+        // TMA bulk copy (cp.async.bulk, SASS UBLKCP) of the packed spike vector into shared memory:
+        // one thread issues <= 32 KB chunks against an mbarrier, everybody waits on its phase
+        __shared__ uint64_t s_bar;
+        const uint32_t bar = (uint32_t)__cvta_generic_to_shared(&s_bar);
         const int64_t n16 = n_words >> 2;
-        for (int64_t i = threadIdx.x; i < n16; i += blockDim.x)
-            reinterpret_cast<int4*>(s_bits)[i] = __ldg(reinterpret_cast<const int4*>(packed) + i);
+        if (threadIdx.x == 0) {
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar));
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            const uint32_t total = (uint32_t)(n16 * 16);
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(total) : "memory");
+            const uint32_t dst0 = (uint32_t)__cvta_generic_to_shared(s_bits);
+            for (uint32_t off = 0; off < total; off += 32768u) {
+                const uint32_t sz = min(32768u, total - off);
+                asm volatile(
+                    "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                    ::"r"(dst0 + off), "l"((const char*)packed + off), "r"(sz), "r"(bar)
+                    : "memory");
+            }
+        }
         for (int64_t i = (n16 << 2) + threadIdx.x; i < n_words; i += blockDim.x) s_bits[i] = __ldg(packed + i);
+        {
+            uint32_t done = 0;
+            while (!done)
+                asm volatile(
+                    "{\n\t.reg .pred p;\n\t"
+                    "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0;\n\t"
+                    "selp.u32 %0, 1, 0, p;\n\t}"
+                    : "=r"(done) : "r"(bar) : "memory");
+        }
         __syncthreads();
     }
     auto bit = [&](int idx) -> bool {
