@@ -15,6 +15,9 @@ from ._event import (BinaryArray, BitPackedBinary, CompactBinary, EventRepresent
                      binary_2d_compact_only_p_call, bitpack)
 from ._fcn import (FixedNumConn, FixedNumPerPost, FixedNumPerPre, binary_fcnmm, binary_fcnmm_p,
                    binary_fcnmm_p_call, binary_fcnmv, binary_fcnmv_p, binary_fcnmv_p_call)
+from ._float import (csrmm, csrmm_p, csrmm_p_call, csrmv, csrmv_p, csrmv_p_call, fcnmm, fcnmm_p, fcnmm_p_call,
+                     fcnmv, fcnmv_p, fcnmv_p_call, jitnmm, jitnmm_p, jitnmv, jitnmv_p, jitsmm, jitsmm_p, jitsmv,
+                     jitsmv_p, jitumm, jitumm_p, jitumv, jitumv_p)
 from ._jitc import (JITCMatrix, JITCNormalC, JITCNormalR, JITCScalarC, JITCScalarR, JITCUniformC,
                     JITCUniformR, binary_jitnmm, binary_jitnmm_p, binary_jitnmv, binary_jitnmv_p,
                     binary_jitsmm, binary_jitsmm_p, binary_jitsmv, binary_jitsmv_p, binary_jitumm,

@@ -195,6 +195,23 @@ def csr_to_csc_index(csr_indptr, csr_indices, *, shape):
 # ---------------------------------------------------------------------------------------------
 # matrix classes (routing only)
 # ---------------------------------------------------------------------------------------------
+def _float_matmul(data, indices, indptr, other, a_shape, transpose, backend, left=None):
+    """Plain (non-event) operand: route to csrmv / csrmm (ref: _csr/main.py:1678-1700, :1756-1776).
+    `left`: whether the matrix is the left factor (defaults to `not transpose`, the CSR case); a
+    right-hand 2-D operand [b, rows] is transposed around the kernel call."""
+    from ._float import csrmm, csrmv
+    other = as_tensor(other, device=data.device)
+    if left is None:
+        left = not transpose
+    if other.ndim == 1:
+        return csrmv(data, indices, indptr, other, shape=a_shape, transpose=transpose, backend=backend)
+    if other.ndim == 2:
+        if left:
+            return csrmm(data, indices, indptr, other, shape=a_shape, transpose=transpose, backend=backend)
+        return csrmm(data, indices, indptr, other.t(), shape=a_shape, transpose=transpose, backend=backend).t()
+    raise NotImplementedError(f"matmul with object of shape {tuple(other.shape)}")
+
+
 class _Compressed:
     def __init__(self, args, *, shape, backend=None):
         data, indices, indptr = args
@@ -246,8 +263,7 @@ class CSR(_Compressed):
                 return binary_csrmm(self.data, self.indices, self.indptr, other, shape=self.shape,
                                     transpose=False, backend=self.backend)
             raise NotImplementedError(f"matmul with object of shape {other.shape}")
-        raise NotImplementedError("brainevent_b200 implements the event-driven path only: wrap the "
-                                  "operand in BinaryArray / BitPackedBinary / CompactBinary")
+        return _float_matmul(self.data, self.indices, self.indptr, other, self.shape, False, self.backend)
 
     def __rmatmul__(self, other):
         # other @ csr (ref: _csr/main.py:1731-1776)
@@ -267,8 +283,7 @@ class CSR(_Compressed):
                                  transpose=True, backend=self.backend)
                 return r.t()
             raise NotImplementedError(f"matmul with object of shape {other.shape}")
-        raise NotImplementedError("brainevent_b200 implements the event-driven path only: wrap the "
-                                  "operand in BinaryArray / BitPackedBinary / CompactBinary")
+        return _float_matmul(self.data, self.indices, self.indptr, other, self.shape, True, self.backend)
 
 
 class CSC(_Compressed):
@@ -299,7 +314,7 @@ class CSC(_Compressed):
                 return binary_csrmm(self.data, self.indices, self.indptr, other, shape=self.shape[::-1],
                                     transpose=True, backend=self.backend)
             raise NotImplementedError(f"matmul with object of shape {other.shape}")
-        raise NotImplementedError("brainevent_b200 implements the event-driven path only")
+        return _float_matmul(self.data, self.indices, self.indptr, other, self.shape[::-1], True, self.backend, left=True)
 
     def __rmatmul__(self, other):
         # other @ csc: gather over the stored (transposed) rows
@@ -314,4 +329,4 @@ class CSC(_Compressed):
                                  shape=self.shape[::-1], transpose=False, backend=self.backend)
                 return r.t()
             raise NotImplementedError(f"matmul with object of shape {other.shape}")
-        raise NotImplementedError("brainevent_b200 implements the event-driven path only")
+        return _float_matmul(self.data, self.indices, self.indptr, other, self.shape[::-1], False, self.backend, left=False)

@@ -158,8 +158,18 @@ class FixedNumConn:
                     return self._binary_matmat(other.value.t(), transpose_W).t()
                 return self._binary_matmat(other, transpose_W)
             raise NotImplementedError(f"matmul with object of shape {other.shape}")
-        raise NotImplementedError("brainevent_b200 implements the event-driven path only: wrap the "
-                                  "operand in BinaryArray / BitPackedBinary / CompactBinary")
+        # plain (non-event) operand (ref: _fcn/main.py FixedPreNumConn/FixedPostNumConn __matmul__)
+        from ._float import fcnmm, fcnmv
+        other = as_tensor(other, device=self.data.device)
+        a_shape, ell_transpose = self._a_shape, self._ell_transpose(transpose_W)
+        if other.ndim == 1:
+            return fcnmv(self.data, self.indices, other, shape=a_shape, transpose=ell_transpose, backend=self.backend)
+        if other.ndim == 2:
+            if transpose_W:
+                return fcnmm(self.data, self.indices, other.t(), shape=a_shape, transpose=ell_transpose,
+                             backend=self.backend).t()
+            return fcnmm(self.data, self.indices, other, shape=a_shape, transpose=ell_transpose, backend=self.backend)
+        raise NotImplementedError(f"matmul with object of shape {tuple(other.shape)}")
 
     def __matmul__(self, other):
         return self._dispatch(other, transpose_W=False)

@@ -196,18 +196,27 @@ class JITCMatrix:
         return self._dev[key]
 
     def _call(self, other, shape, transpose, corder):
-        if not isinstance(other, _EVENT_TYPES):
-            raise NotImplementedError("brainevent_b200 implements the event-driven path only: wrap the "
-                                      "operand in BinaryArray / BitPackedBinary / CompactBinary")
         if other.ndim not in (1, 2):
             raise NotImplementedError(f"matmul with object of shape {other.shape}")
         return other.ndim == 2
 
     def _run(self, x, shape, transpose, corder, matmat):
+        if not isinstance(x, _EVENT_TYPES):
+            return self._run_float(x, shape, transpose, corder, matmat)
         prim = type(self)._prims[1 if matmat else 0]
         ev = event_args(x)
         vals, clen, seed = self._device_params(ev.device)
         res = _jit_p_call(prim, vals, clen, ev, seed, shape, transpose, corder, self.backend, matmat)[0]
+        return maybe_decimal(res, split_mantissa_unit(self.params[0])[1])
+
+
+    def _run_float(self, x, shape, transpose, corder, matmat):
+        """plain (non-event) operand: jit?mv / jit?mm (ref: _jit_scalar/main.py:941-1066)."""
+        from . import _float
+        prim = _float.JIT_FLOAT_PRIMS[type(self)._family][1 if matmat else 0]
+        x = as_tensor(x)
+        vals, clen, seed = self._device_params(x.device)
+        res = _float._jit_p_call(prim, vals, clen, x, seed, shape, transpose, corder, self.backend, matmat)[0]
         return maybe_decimal(res, split_mantissa_unit(self.params[0])[1])
 
 
@@ -219,9 +228,11 @@ class _JITC_R(JITCMatrix):
 
     def __rmatmul__(self, other):
         if self._call(other, None, None, None):
+            if not isinstance(other, _EVENT_TYPES):
+                return self._run(as_tensor(other).t(), self.shape, True, not self.corder, True).t()
             if not isinstance(other, BinaryArray):
                 raise NotImplementedError("2-D packed events must be packed along the batch axis")
-            return self._run(other.value.t(), self.shape, True, not self.corder, True).t()
+            return self._run(BinaryArray(other.value.t()), self.shape, True, not self.corder, True).t()
         return self._run(other, self.shape, True, not self.corder, False)
 
 
@@ -234,9 +245,11 @@ class _JITC_C(JITCMatrix):
 
     def __rmatmul__(self, other):
         if self._call(other, None, None, None):
+            if not isinstance(other, _EVENT_TYPES):
+                return self._run(as_tensor(other).t(), self.shape[::-1], False, not self.corder, True).t()
             if not isinstance(other, BinaryArray):
                 raise NotImplementedError("2-D packed events must be packed along the batch axis")
-            return self._run(other.value.t(), self.shape[::-1], False, not self.corder, True).t()
+            return self._run(BinaryArray(other.value.t()), self.shape[::-1], False, not self.corder, True).t()
         return self._run(other, self.shape[::-1], False, not self.corder, False)
 
 
@@ -245,7 +258,8 @@ def _cls(name, base, prims, n_params, doc):
         *params, prob, seed = data
         assert len(params) == n_params, f"{name} expects ({', '.join(['w'] * n_params)}, prob, seed)"
         base.__init__(self, params, prob, seed, shape=shape, corder=corder, backend=backend)
-    return type(name, (base,), {"__init__": __init__, "_prims": prims, "__doc__": doc})
+    family = {"S": "scalar", "N": "normal", "U": "uniform"}[name[4]]
+    return type(name, (base,), {"__init__": __init__, "_prims": prims, "_family": family, "__doc__": doc})
 
 
 JITCScalarR = _cls("JITCScalarR", _JITC_R, (binary_jitsmv_p, binary_jitsmm_p), 1, "JITCScalarR((weight, prob, seed), shape=...)")

@@ -327,6 +327,142 @@ __global__ void __launch_bounds__(256) jit_mm_scatter_kernel(JitParams jp, const
 }
 
 // ------------------------------------------------------------------------------------------
+// float (non-event) twins (ref _jit_scalar/float.py:805-912, :1298-1405 and the
+// normal/uniform analogues): same walks, a value vector / matrix instead of spike bits.
+// ------------------------------------------------------------------------------------------
+template <typename T, int KIND>
+__global__ void __launch_bounds__(256) jit_mv_val_gather_kernel(JitParams jp, const T* __restrict__ x,
+                                                                int64_t vec_len, int64_t chunk_size,
+                                                                int64_t out_len, T* __restrict__ out) {
+    using A = typename Acc<T>::type;
+    A p0, p1; uint32_t cl, seed;
+    load_params<T, KIND>(jp, p0, p1, cl, seed);
+    const uint32_t lane = threadIdx.x & 31;
+    const int n_chunks = (int)ceil_div(vec_len, chunk_size);
+    for (int64_t rr = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5); rr < out_len; rr += (int64_t)gridDim.x * 8) {
+        const uint32_t row = (uint32_t)rr;
+        A acc = A(0);
+        for (int c = 0; c < n_chunks; ++c) {
+            const int64_t cs = (int64_t)c * chunk_size;
+            const uint32_t width = (uint32_t)min(chunk_size, vec_len - cs);
+            const uint32_t qmax = lane_qmax<32>(width, lane);
+            uint32_t s = rng_init(seed, row, (uint32_t)c, lane);
+            uint32_t q = rng_initial_q(s, cl);
+            const T* xp = x + cs + lane;
+            while (q < qmax) {
+                const A xv = to_acc<T>(__ldg(xp + 32 * (int64_t)q));
+                if (KIND == BE_B200_JIT_SCALAR) acc += xv;
+                else acc += jit_weight<KIND, A>(p0, p1, seed, row, (uint32_t)(cs + lane + 32 * (int64_t)q)) * xv;
+                s = rng_next(s);
+                q += 1U + __umulhi(s, cl - 1U);
+            }
+        }
+        acc = warp_sum(acc);
+        if (KIND == BE_B200_JIT_SCALAR) acc *= p0;
+        if (lane == 0) out[rr] = from_acc<T>(acc);
+    }
+}
+
+template <typename T, int KIND>
+__global__ void __launch_bounds__(256) jit_mv_val_scatter_kernel(JitParams jp, const T* __restrict__ x,
+                                                                 int64_t vec_len, int64_t out_len,
+                                                                 int64_t chunk_size, T* __restrict__ out) {
+    using A = typename Acc<T>::type;
+    A p0, p1; uint32_t cl, seed;
+    load_params<T, KIND>(jp, p0, p1, cl, seed);
+    const uint32_t lane = threadIdx.x & 31;
+    const int n_chunks = (int)ceil_div(out_len, chunk_size);
+    const int64_t n_tasks = vec_len * n_chunks;
+    for (int64_t t = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5); t < n_tasks; t += (int64_t)gridDim.x * 8) {
+        const int64_t r = t / n_chunks;
+        const int c = (int)(t - r * n_chunks);
+        const A xv = to_acc<T>(__ldg(x + r));
+        if (xv == A(0)) continue;     // ref: `if v == 0.: continue`
+        const int64_t cs = (int64_t)c * chunk_size;
+        const uint32_t width = (uint32_t)min(chunk_size, out_len - cs);
+        const uint32_t qmax = lane_qmax<32>(width, lane);
+        const uint32_t row = (uint32_t)r;
+        uint32_t s = rng_init(seed, row, (uint32_t)c, lane);
+        uint32_t q = rng_initial_q(s, cl);
+        const int64_t b0 = cs + lane;
+        while (q < qmax) {
+            const int64_t j = b0 + 32 * (int64_t)q;
+            red_add(out + j, jit_weight<KIND, A>(p0, p1, seed, row, (uint32_t)j) * xv);
+            s = rng_next(s);
+            q += 1U + __umulhi(s, cl - 1U);
+        }
+    }
+}
+
+// mm: lanes 0..3 walk the four residue streams of one (row, chunk), every connection is broadcast
+// and applied by all lanes (= 32 columns of X / out, contiguous segments).
+template <typename T, int KIND, bool GATHER>
+__global__ void __launch_bounds__(256) jit_mm_val_kernel(JitParams jp, const T* __restrict__ X,
+                                                         int64_t n_rows, int64_t walk_len, int64_t n,
+                                                         int64_t chunk_size, T* __restrict__ out) {
+    using A = typename Acc<T>::type;
+    A p0, p1; uint32_t cl, seed;
+    load_params<T, KIND>(jp, p0, p1, cl, seed);
+    const uint32_t lane = threadIdx.x & 31;
+    const int n_chunks = (int)ceil_div(walk_len, chunk_size);
+    const int64_t n_ct = ceil_div(n, (int64_t)32);
+    // gather: one warp owns (row, column tile) and loops over the chunks; scatter: (row, chunk, tile)
+    const int64_t n_tasks = GATHER ? n_rows * n_ct : n_rows * n_ct * n_chunks;
+    for (int64_t t = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5); t < n_tasks; t += (int64_t)gridDim.x * 8) {
+        int64_t rr, ct;
+        int c_lo, c_hi;
+        if (GATHER) { rr = t / n_ct; ct = t - rr * n_ct; c_lo = 0; c_hi = n_chunks; }
+        else {
+            const int64_t rc = t / n_ct;
+            ct = t - rc * n_ct;
+            rr = rc / n_chunks;
+            c_lo = (int)(rc - rr * n_chunks);
+            c_hi = c_lo + 1;
+        }
+        const uint32_t row = (uint32_t)rr;
+        const int64_t col = ct * 32 + lane;
+        const bool ok = col < n;
+        A acc = A(0);
+        A xrow = A(0);
+        if (!GATHER && ok) xrow = to_acc<T>(__ldg(X + rr * n + col));
+        for (int c = c_lo; c < c_hi; ++c) {
+            const int64_t cs = (int64_t)c * chunk_size;
+            const uint32_t width = (uint32_t)min(chunk_size, walk_len - cs);
+            uint32_t s = 0, q = 0, qmax = 0;
+            if (lane < 4) {
+                qmax = lane_qmax<4>(width, lane);
+                s = rng_init(seed, row, (uint32_t)c, lane);
+                q = rng_initial_q(s, cl);
+            }
+            uint32_t live = __ballot_sync(0xffffffffu, q < qmax);
+            while (live) {
+                int64_t my_j = 0;
+                A my_w = A(1);
+                if (q < qmax) {
+                    my_j = cs + lane + 4 * (int64_t)q;
+                    if (KIND != BE_B200_JIT_SCALAR || !GATHER) my_w = jit_weight<KIND, A>(p0, p1, seed, row, (uint32_t)my_j);
+                    s = rng_next(s);
+                    q += 1U + __umulhi(s, cl - 1U);
+                }
+                uint32_t m = live;
+                while (m) {
+                    const int tt = __ffs(m) - 1;
+                    m &= m - 1;
+                    const A wv = __shfl_sync(0xffffffffu, my_w, tt);
+                    const int64_t j = __shfl_sync(0xffffffffu, my_j, tt);
+                    if (ok) {
+                        if (GATHER) acc += wv * to_acc<T>(__ldg(X + j * n + col));
+                        else if (xrow != A(0)) red_add(out + j * n + col, xrow * wv);
+                    }
+                }
+                live = __ballot_sync(0xffffffffu, q < qmax);
+            }
+        }
+        if (GATHER && ok) out[rr * n + col] = from_acc<T>(KIND == BE_B200_JIT_SCALAR ? acc * p0 : acc);
+    }
+}
+
+// ------------------------------------------------------------------------------------------
 // connectivity dump (parity instrument): per generated row, count and the first `cap` columns
 // in the reference's walk order (chunk-major, then lane, then ascending within the lane).
 // ------------------------------------------------------------------------------------------
@@ -428,6 +564,52 @@ static int run_jit_mm(const JitParams& jp, const Events& ev, int64_t vec_len, in
         default: ::be::set_error("unknown JITC kind %d", (int)(kind)); return BE_B200_EINVAL;    \
     }
 
+template <typename T, int KIND>
+static int run_jit_val(const JitParams& jp, const T* x, int64_t vec_len, int64_t out_len, int64_t n,
+                       int64_t chunk_size, bool corder, T* out, cudaStream_t s) {
+    if (out_len == 0) return BE_B200_OK;
+    const int64_t width = std::max<int64_t>(n, 1);
+    if (!corder || vec_len == 0) BE_CUDA(cudaMemsetAsync(out, 0, (size_t)(out_len * width) * sizeof(T), s));
+    if (vec_len == 0) return BE_B200_OK;
+    const int64_t walk = corder ? vec_len : out_len;
+    const int64_t n_chunks = ceil_div(walk, chunk_size);
+    const int64_t n_ct = ceil_div(width, (int64_t)32);
+    int64_t tasks;
+    if (n == 0) tasks = corder ? out_len : vec_len * n_chunks;
+    else tasks = corder ? out_len * n_ct : vec_len * n_chunks * n_ct;
+    const int blocks = (int)std::min<int64_t>(ceil_div(std::max<int64_t>(tasks, 1), 8), (int64_t)kNumSM * 32);
+    {
+        ProfileScope prof(s);
+        if (n == 0) {
+            if (corder) jit_mv_val_gather_kernel<T, KIND><<<blocks, 256, 0, s>>>(jp, x, vec_len, chunk_size, out_len, out);
+            else jit_mv_val_scatter_kernel<T, KIND><<<blocks, 256, 0, s>>>(jp, x, vec_len, out_len, chunk_size, out);
+        } else {
+            if (corder) jit_mm_val_kernel<T, KIND, true><<<blocks, 256, 0, s>>>(jp, x, out_len, vec_len, n, chunk_size, out);
+            else jit_mm_val_kernel<T, KIND, false><<<blocks, 256, 0, s>>>(jp, x, vec_len, out_len, n, chunk_size, out);
+        }
+    }
+    BE_LAUNCH_CHECK("jit_val_kernel");
+    return BE_B200_OK;
+}
+
+static int jit_val_entry(int kind, const void* p0, const void* p1, int w_dtype, const int32_t* clen,
+                         const int32_t* seed, const void* x, int64_t vec_len, int64_t out_len, int64_t n,
+                         int64_t chunk_size, int corder, void* out, void* stream) {
+    cudaStream_t s = (cudaStream_t)stream;
+    BE_REQUIRE(p0 && clen && seed && out, "jit: NULL pointer");
+    BE_REQUIRE(kind == BE_B200_JIT_SCALAR || p1, "jit: p1 is NULL");
+    BE_REQUIRE(x || vec_len == 0, "jit: operand is NULL");
+    BE_REQUIRE(vec_len >= 0 && out_len >= 0 && vec_len < (1ll << 31) && out_len < (1ll << 31), "jit: shape out of range");
+    BE_REQUIRE(chunk_size >= 1, "jit: chunk_size must be positive");
+    JitParams jp{p0, p1, clen, seed};
+    BE_DISPATCH_WT(w_dtype, T, {
+        BE_DISPATCH_KIND(kind, K, {
+            return run_jit_val<T, K>(jp, (const T*)x, vec_len, out_len, n, chunk_size, corder != 0, (T*)out, s);
+        });
+    });
+    return BE_B200_OK;
+}
+
 }  // namespace be
 
 using namespace be;
@@ -502,4 +684,17 @@ extern "C" int be_b200_jitc_row_connections(const int32_t* clen, const int32_t* 
     else jit_conn_dump_kernel<4><<<blocks, 128, 0, s>>>(clen, seed, row_begin, n_rows, k, chunk_size, counts, cols, cap);
     BE_LAUNCH_CHECK("jit_conn_dump_kernel");
     return BE_B200_OK;
+}
+
+extern "C" int be_b200_jitmv(int kind, const void* p0, const void* p1, int w_dtype, const int32_t* clen,
+                             const int32_t* seed, const void* x, int64_t vec_len, int64_t out_len,
+                             int64_t chunk_size, int corder, void* out, void* stream) {
+    return jit_val_entry(kind, p0, p1, w_dtype, clen, seed, x, vec_len, out_len, 0, chunk_size, corder, out, stream);
+}
+
+extern "C" int be_b200_jitmm(int kind, const void* p0, const void* p1, int w_dtype, const int32_t* clen,
+                             const int32_t* seed, const void* X, int64_t vec_len, int64_t out_len, int64_t n,
+                             int64_t chunk_size, int corder, void* out, void* stream) {
+    BE_REQUIRE(n >= 1, "jitmm: n must be >= 1");
+    return jit_val_entry(kind, p0, p1, w_dtype, clen, seed, X, vec_len, out_len, n, chunk_size, corder, out, stream);
 }

@@ -170,6 +170,34 @@ int be_b200_jitc_row_connections(const int32_t* clen, const int32_t* seed, int64
                                  int64_t n_rows, int64_t k, int64_t chunk_size, int stride,
                                  int32_t* counts, int32_t* cols, int64_t cap, void* stream);
 
+/* ---- float (non-event) products through the same connectivity: the callers either side of the
+ *      event path.  x / X hold VALUES in the weight dtype; X is [rows, n] row-major
+ *      and out is [rows_out, n] row-major.  No workspace.
+ *      ref: _csr/float.py:49 csrmv, :559 csrmm (_csr/float_csrmv.cu, float_csrmm.cu);
+ *           _fcn/float.py:33 fcnmv, :136 fcnmm (_fcn/float_fcnmv.cu, float_fcnmm.cu);
+ *           _jit_scalar/float.py:159 jitsmv, :1024 jitsmm and the normal/uniform analogues
+ *           (float_jitsmv.cu, float_jitsmm.cu, ... next to each family's float.py). */
+int be_b200_csrmv(const void* weights, int w_dtype, int homo, const int32_t* indices,
+                  const void* indptr, int indptr_is64, const void* x, int64_t m, int64_t k,
+                  int64_t nse, int transpose, void* out, void* stream);
+int be_b200_csrmm(const void* weights, int w_dtype, int homo, const int32_t* indices,
+                  const void* indptr, int indptr_is64, const void* X, int64_t m, int64_t k,
+                  int64_t nse, int64_t n, int transpose, void* out, void* stream);
+/* indices [n_rows, n_conn]; transpose=1: x[n_rows] -> out[n_other]; transpose=0: x[n_other] -> out[n_rows] */
+int be_b200_fcnmv(const void* weights, int w_dtype, int homo, const int32_t* indices,
+                  int64_t n_rows, int64_t n_conn, const void* x, int64_t n_other, int transpose,
+                  void* out, void* stream);
+int be_b200_fcnmm(const void* weights, int w_dtype, int homo, const int32_t* indices,
+                  int64_t n_rows, int64_t n_conn, const void* X, int64_t n_other, int64_t n,
+                  int transpose, void* out, void* stream);
+/* same parameter meaning as be_b200_binary_jitmv / _jitmm without windows */
+int be_b200_jitmv(int kind, const void* p0, const void* p1, int w_dtype, const int32_t* clen,
+                  const int32_t* seed, const void* x, int64_t vec_len, int64_t out_len,
+                  int64_t chunk_size, int corder, void* out, void* stream);
+int be_b200_jitmm(int kind, const void* p0, const void* p1, int w_dtype, const int32_t* clen,
+                  const int32_t* seed, const void* X, int64_t vec_len, int64_t out_len, int64_t n,
+                  int64_t chunk_size, int corder, void* out, void* stream);
+
 /* ---- dense event ops (ref: _dense/binary.py:79 binary_densemv, :487 binary_densemm;
  *      _dense/binary_densemv.cu, binary_densemm.cu) --------------------------------------------
  * W row-major [rows, cols].  transpose=1: events[rows] -> out[cols]; transpose=0: events[cols]

@@ -414,3 +414,108 @@ def binary_densemm(weights, spikes, *, transpose):
     getattr(lib(), "ora_densemm" + _sfx(W.dtype))(
         _p(W), _i64(rows), _i64(cols), _p(act), _i64(n), int(bool(transpose)), _p(out))
     return out
+
+
+# ----------------------------------------------------------------------------------------------
+# float (non-event) operators -- SURVEY 8(f)-1
+# ----------------------------------------------------------------------------------------------
+def csrmv(data, indices, indptr, v, *, shape, transpose=False):
+    """_csr/float.py:49."""
+    data, homo, indices, indptr, _ = _csr_common(data, indices, indptr, None)
+    m, k = shape
+    x = _c(v, data.dtype)
+    assert x.shape[0] == (m if transpose else k)
+    out = np.zeros(k if transpose else m, data.dtype)
+    getattr(lib(), "ora_csrmv_val" + _sfx(data.dtype))(
+        _p(data), homo, _p(indices), _p(indptr), _p(x), _i64(m), _i64(k), int(bool(transpose)), _p(out))
+    return out
+
+
+def csrmm(data, indices, indptr, B, *, shape, transpose=False):
+    """_csr/float.py:559."""
+    data, homo, indices, indptr, _ = _csr_common(data, indices, indptr, None)
+    m, k = shape
+    X = _c(B, data.dtype)
+    n = X.shape[1]
+    assert X.shape[0] == (m if transpose else k)
+    out = np.zeros((k if transpose else m, n), data.dtype)
+    getattr(lib(), "ora_csrmm_val" + _sfx(data.dtype))(
+        _p(data), homo, _p(indices), _p(indptr), _p(X), _i64(m), _i64(k), _i64(n), int(bool(transpose)), _p(out))
+    return out
+
+
+def _fcn_as_csr(weights, indices):
+    weights = _c(np.atleast_1d(weights))
+    indices = _c(indices, np.int32)
+    n_rows, n_conn = indices.shape
+    indptr = np.arange(n_rows + 1, dtype=np.int64) * n_conn
+    return (weights if weights.size == 1 else weights.reshape(-1)), indices.reshape(-1), indptr
+
+
+def fcnmv(weights, indices, vector, *, shape, transpose=False):
+    """_fcn/float.py:33 (ELL == CSR with a regular indptr)."""
+    w, ix, ip = _fcn_as_csr(weights, indices)
+    return csrmv(w, ix, ip, vector, shape=shape, transpose=transpose)
+
+
+def fcnmm(weights, indices, matrix, *, shape, transpose=False):
+    """_fcn/float.py:136."""
+    w, ix, ip = _fcn_as_csr(weights, indices)
+    return csrmm(w, ix, ip, matrix, shape=shape, transpose=transpose)
+
+
+def _jit_mv_val(kind, p0, p1, prob, vector, seed, shape, transpose, corder, dtype):
+    clen = conn_length(prob)
+    x = _c(vector, dtype)
+    out_len = shape[1] if transpose else shape[0]
+    vec_len = shape[0] if transpose else shape[1]
+    assert x.shape[0] == vec_len
+    chunk = normalize_chunk_size(shape[1])
+    out = np.zeros(out_len, dtype)
+    getattr(lib(), "ora_jitmv_val" + _sfx(dtype))(
+        kind, _scalar(dtype, p0), _scalar(dtype, p1), _u32(clen), _u32(seed), _p(x),
+        _i64(vec_len), _i64(out_len), _i64(chunk), int(bool(corder)), _p(out))
+    return out
+
+
+def jitsmv(weight, prob, vector, seed, *, shape, transpose=False, corder=True, dtype=np.float32):
+    """_jit_scalar/float.py:159."""
+    return _jit_mv_val(0, weight, 0.0, prob, vector, seed, shape, transpose, corder, dtype)
+
+
+def jitnmv(w_loc, w_scale, prob, vector, seed, *, shape, transpose=False, corder=True, dtype=np.float32):
+    """_jit_normal/float.py (jitnmv)."""
+    return _jit_mv_val(1, w_loc, w_scale, prob, vector, seed, shape, transpose, corder, dtype)
+
+
+def jitumv(w_low, w_high, prob, vector, seed, *, shape, transpose=False, corder=True, dtype=np.float32):
+    """_jit_uniform/float.py (jitumv)."""
+    return _jit_mv_val(2, w_low, w_high, prob, vector, seed, shape, transpose, corder, dtype)
+
+
+def _jit_mm_val(kind, p0, p1, prob, B, seed, shape, transpose, corder, dtype):
+    clen = conn_length(prob)
+    X = _c(B, dtype)
+    n = X.shape[1]
+    out_len = shape[1] if transpose else shape[0]
+    vec_len = shape[0] if transpose else shape[1]
+    assert X.shape[0] == vec_len
+    chunk = normalize_chunk_size(shape[1])
+    out = np.zeros((out_len, n), dtype)
+    getattr(lib(), "ora_jitmm_val" + _sfx(dtype))(
+        kind, _scalar(dtype, p0), _scalar(dtype, p1), _u32(clen), _u32(seed), _p(X),
+        _i64(vec_len), _i64(out_len), _i64(n), _i64(chunk), int(bool(corder)), _p(out))
+    return out
+
+
+def jitsmm(weight, prob, B, seed, *, shape, transpose=False, corder=True, dtype=np.float32):
+    """_jit_scalar/float.py:1298."""
+    return _jit_mm_val(0, weight, 0.0, prob, B, seed, shape, transpose, corder, dtype)
+
+
+def jitnmm(w_loc, w_scale, prob, B, seed, *, shape, transpose=False, corder=True, dtype=np.float32):
+    return _jit_mm_val(1, w_loc, w_scale, prob, B, seed, shape, transpose, corder, dtype)
+
+
+def jitumm(w_low, w_high, prob, B, seed, *, shape, transpose=False, corder=True, dtype=np.float32):
+    return _jit_mm_val(2, w_low, w_high, prob, B, seed, shape, transpose, corder, dtype)

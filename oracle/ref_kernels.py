@@ -202,3 +202,68 @@ def binary_densemm(weights, spikes, *, transpose):
                                        weight_info=SDS(W.shape, W.dtype), transpose=transpose,
                                        outs=[SDS((out_m, s.shape[1]), W.dtype)])
     return _first(k(W, s))
+
+
+# -- float (non-event) operators ------------------------------------------------------------------
+def csrmv(data, indices, indptr, v, *, shape, transpose=False):
+    m = R.ref_module("_csr.float")
+    data = np.atleast_1d(data)
+    v = np.ascontiguousarray(v)
+    out_n = shape[1] if transpose else shape[0]
+    k = m._csrmv_numba_kernel_generator(weight_info=SDS(data.shape, data.dtype), transpose=transpose,
+                                        outs=[SDS((out_n,), data.dtype)])
+    return _first(k(data, indices, indptr, v))
+
+
+def csrmm(data, indices, indptr, B, *, shape, transpose=False):
+    m = R.ref_module("_csr.float")
+    data = np.atleast_1d(data)
+    B = np.ascontiguousarray(B)
+    out_n = shape[1] if transpose else shape[0]
+    k = m._csrmm_numba_kernel_generator(weight_info=SDS(data.shape, data.dtype), transpose=transpose,
+                                        outs=[SDS((out_n, B.shape[1]), data.dtype)])
+    return _first(k(data, indices, indptr, B))
+
+
+def _jit_float(modname, gen, params, prob, x, seed, shape, transpose, corder, dtype):
+    m = R.ref_module(modname)
+    x = np.ascontiguousarray(x)
+    out_n = shape[1] if transpose else shape[0]
+    is_mm = x.ndim == 2
+    oshape = (out_n, x.shape[1]) if is_mm else (out_n,)
+    k = getattr(m, gen)(corder=corder, shape=tuple(shape), outs=[SDS(oshape, dtype)], transpose=transpose,
+                        **{"B_info" if is_mm else "vector_info": SDS(x.shape, x.dtype)})
+    clen = np.asarray([conn_length(prob)], np.int32)
+    seed = np.asarray([seed], np.int32)
+    ps = [np.asarray([p], dtype) for p in params]
+    if modname.startswith("_jit_scalar"):
+        return _first(k(*ps, clen, x, seed, None))
+    return _first(k(*ps, clen, x, seed))
+
+
+def jitsmv(weight, prob, vector, seed, *, shape, transpose=False, corder=True, dtype=np.float32):
+    return _jit_float("_jit_scalar.float", "_jitsmv_numba_kernel", [weight], prob, vector, seed, shape, transpose, corder, dtype)
+
+
+def jitnmv(w_loc, w_scale, prob, vector, seed, *, shape, transpose=False, corder=True, dtype=np.float32):
+    return _jit_float("_jit_normal.float", "_jitnmv_numba_kernel_generator", [w_loc, w_scale], prob, vector, seed, shape,
+                      transpose, corder, dtype)
+
+
+def jitumv(w_low, w_high, prob, vector, seed, *, shape, transpose=False, corder=True, dtype=np.float32):
+    return _jit_float("_jit_uniform.float", "_jitumv_numba_kernel_generator", [w_low, w_high], prob, vector, seed, shape,
+                      transpose, corder, dtype)
+
+
+def jitsmm(weight, prob, B, seed, *, shape, transpose=False, corder=True, dtype=np.float32):
+    return _jit_float("_jit_scalar.float", "_jitsmm_numba_kernel", [weight], prob, B, seed, shape, transpose, corder, dtype)
+
+
+def jitnmm(w_loc, w_scale, prob, B, seed, *, shape, transpose=False, corder=True, dtype=np.float32):
+    return _jit_float("_jit_normal.float", "_jitnmm_numba_kernel_generator", [w_loc, w_scale], prob, B, seed, shape,
+                      transpose, corder, dtype)
+
+
+def jitumm(w_low, w_high, prob, B, seed, *, shape, transpose=False, corder=True, dtype=np.float32):
+    return _jit_float("_jit_uniform.float", "_jitumm_numba_kernel_generator", [w_low, w_high], prob, B, seed, shape,
+                      transpose, corder, dtype)

@@ -132,7 +132,15 @@ def golden_ops():
     save("ops", **out)
 
 
+def golden_float_ops():
+    """float (non-event) operators: every case of golden_cases.float_op_cases() through the
+    reference's numba kernels."""
+    from tests import golden_cases
+    save("float_ops", **{tag: fn(RK) for tag, fn, _ in golden_cases.float_op_cases()})
+
+
 if __name__ == "__main__":
     golden_rng()
     golden_connectivity()
     golden_ops()
+    golden_float_ops()

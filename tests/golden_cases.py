@@ -63,3 +63,38 @@ def op_cases():
         B = cases.spikes(16, k, 0.2, batch=7)
         yield (f"dense_t{int(tr)}_mv", (lambda api, v=v, tr=tr: api.binary_densemv(W, v, transpose=tr)), 1e-5)
         yield (f"dense_t{int(tr)}_mm", (lambda api, B=B, tr=tr: api.binary_densemm(W, B, transpose=tr)), 1e-5)
+
+
+def _fvals(seed, n, batch=None, density=0.7):
+    rng = np.random.default_rng(seed)
+    shape = (n,) if batch is None else (n, batch)
+    return (rng.standard_normal(shape) * (rng.random(shape) < density)).astype(np.float32)
+
+
+def float_op_cases():
+    """(tag, fn(api) -> ndarray, atol) for tests/golden/float_ops.npz: the float (non-event)
+    operators, generated from the reference's numba kernels (make_golden.py::golden_float_ops)."""
+    for homo in (False, True):
+        c = cases.csr_case(20, 300, 200, 9, 0.1, homo=homo, ragged=True)
+        m, k = c["shape"]
+        for tr in (False, True):
+            tag = f"csr_h{int(homo)}_t{int(tr)}"
+            v = _fvals(21, m if tr else k)
+            B = _fvals(22, m if tr else k, batch=13)
+            yield (tag + "_mv", (lambda api, c=c, v=v, tr=tr: api.csrmv(
+                c["data"], c["indices"], c["indptr"], v, shape=c["shape"], transpose=tr)), 2e-5)
+            yield (tag + "_mm", (lambda api, c=c, B=B, tr=tr: api.csrmm(
+                c["data"], c["indices"], c["indptr"], B, shape=c["shape"], transpose=tr)), 2e-5)
+    shape, prob, seed = (230, 310), 0.05, 4321
+    for fam, params in [("s", (1.5,)), ("n", (1.0, 0.1)), ("u", (-0.5, 1.0))]:
+        atol = 3e-4 if fam == "n" else 2e-5   # normal: fastmath reference build, see op_cases()
+        for tr in (False, True):
+            for co in (False, True):
+                tag = f"jit{fam}_t{int(tr)}_c{int(co)}"
+                vec_len = shape[0] if tr else shape[1]
+                v = _fvals(23, vec_len, density=0.6)
+                B = _fvals(24, vec_len, batch=6, density=0.6)
+                yield (tag + "_mv", (lambda api, fam=fam, params=params, v=v, tr=tr, co=co: getattr(
+                    api, f"jit{fam}mv")(*params, prob, v, seed, shape=shape, transpose=tr, corder=co)), atol)
+                yield (tag + "_mm", (lambda api, fam=fam, params=params, B=B, tr=tr, co=co: getattr(
+                    api, f"jit{fam}mm")(*params, prob, B, seed, shape=shape, transpose=tr, corder=co)), atol)

@@ -111,3 +111,44 @@ def bitpack(arr, axis=0):
 def csr_to_csc_index(indptr, indices, shape):
     a, b, c = be.csr_to_csc_index(_t(indptr), _t(indices), shape=shape)
     return _np(a).astype(np.int64), _np(b), _np(c).astype(np.int64)
+
+
+# ---- float (non-event) operators ----------------------------------------------------------------
+def csrmv(data, indices, indptr, v, *, shape, transpose=False):
+    return _np(be.csrmv(_t(np.atleast_1d(data)), _t(indices), _t(indptr), _t(v), shape=shape, transpose=transpose))
+
+
+def csrmm(data, indices, indptr, B, *, shape, transpose=False):
+    return _np(be.csrmm(_t(np.atleast_1d(data)), _t(indices), _t(indptr), _t(B), shape=shape, transpose=transpose))
+
+
+def fcnmv(weights, indices, v, *, shape, transpose=False):
+    return _np(be.fcnmv(_t(np.atleast_1d(weights)), _t(indices), _t(v), shape=shape, transpose=transpose))
+
+
+def fcnmm(weights, indices, B, *, shape, transpose=False):
+    return _np(be.fcnmm(_t(np.atleast_1d(weights)), _t(indices), _t(B), shape=shape, transpose=transpose))
+
+
+def jitsmv(w, prob, v, seed, *, shape, transpose=False, corder=True, dtype=np.float32):
+    return _jit(be.jitsmv, [w], prob, v, seed, shape, transpose, corder, dtype)
+
+
+def jitsmm(w, prob, B, seed, *, shape, transpose=False, corder=True, dtype=np.float32):
+    return _jit(be.jitsmm, [w], prob, B, seed, shape, transpose, corder, dtype)
+
+
+def jitnmv(loc, scale, prob, v, seed, *, shape, transpose=False, corder=True, dtype=np.float32):
+    return _jit(be.jitnmv, [loc, scale], prob, v, seed, shape, transpose, corder, dtype)
+
+
+def jitnmm(loc, scale, prob, B, seed, *, shape, transpose=False, corder=True, dtype=np.float32):
+    return _jit(be.jitnmm, [loc, scale], prob, B, seed, shape, transpose, corder, dtype)
+
+
+def jitumv(lo, hi, prob, v, seed, *, shape, transpose=False, corder=True, dtype=np.float32):
+    return _jit(be.jitumv, [lo, hi], prob, v, seed, shape, transpose, corder, dtype)
+
+
+def jitumm(lo, hi, prob, B, seed, *, shape, transpose=False, corder=True, dtype=np.float32):
+    return _jit(be.jitumm, [lo, hi], prob, B, seed, shape, transpose, corder, dtype)

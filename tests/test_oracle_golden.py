@@ -126,3 +126,9 @@ def test_compaction_fixture():
 def test_ops_fixture(tag, fn, atol):
     g = golden_cases.load("ops")
     np.testing.assert_allclose(fn(O), g[tag], rtol=RTOL, atol=atol)
+
+
+@pytest.mark.parametrize("tag,fn,atol", list(golden_cases.float_op_cases()), ids=lambda x: x if isinstance(x, str) else "")
+def test_float_ops_fixture(tag, fn, atol):
+    g = golden_cases.load("float_ops")
+    np.testing.assert_allclose(fn(O), g[tag], rtol=1e-5, atol=atol)

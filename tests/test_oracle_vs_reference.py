@@ -158,3 +158,55 @@ def test_dense(RK, transpose, float_spikes):
     B = cases.spikes(16, k, 0.2, float_spikes, batch=7)
     np.testing.assert_allclose(O.binary_densemm(W, B, transpose=transpose),
                                RK.binary_densemm(W, B, transpose=transpose), rtol=RTOL, atol=1e-5)
+
+
+# ---- float (non-event) operators: SURVEY 8(f)-1 ------------------------------------------------
+@pytest.mark.parametrize("homo", [False, True])
+@pytest.mark.parametrize("transpose", [False, True])
+def test_float_csr(RK, homo, transpose):
+    c = cases.csr_case(40, 300, 200, 9, 0.1, homo=homo, ragged=True)
+    m, k = c["shape"]
+    rng = np.random.default_rng(41)
+    x = (rng.standard_normal(m if transpose else k) * (rng.random(m if transpose else k) < 0.7)).astype(np.float32)
+    np.testing.assert_allclose(O.csrmv(c["data"], c["indices"], c["indptr"], x, shape=c["shape"], transpose=transpose),
+                               RK.csrmv(c["data"], c["indices"], c["indptr"], x, shape=c["shape"], transpose=transpose),
+                               rtol=1e-5, atol=1e-5)
+    X = rng.standard_normal((m if transpose else k, 7)).astype(np.float32)
+    np.testing.assert_allclose(O.csrmm(c["data"], c["indices"], c["indptr"], X, shape=c["shape"], transpose=transpose),
+                               RK.csrmm(c["data"], c["indices"], c["indptr"], X, shape=c["shape"], transpose=transpose),
+                               rtol=1e-5, atol=1e-5)
+
+
+@pytest.mark.parametrize("fam,params", JIT)
+@pytest.mark.parametrize("transpose", [False, True])
+@pytest.mark.parametrize("corder", [False, True])
+def test_float_jitc(RK, fam, params, transpose, corder):
+    shape, prob, seed = (230, 310), 0.05, 99
+    rng = np.random.default_rng(42)
+    n = shape[0] if transpose else shape[1]
+    x = (rng.standard_normal(n) * (rng.random(n) < 0.6)).astype(np.float32)
+    kw = dict(shape=shape, transpose=transpose, corder=corder)
+    a = getattr(RK, f"jit{fam}mv")(*params, prob, x, seed, **kw)
+    b = getattr(O, f"jit{fam}mv")(*params, prob, x, seed, **kw)
+    np.testing.assert_allclose(b, a, rtol=1e-5, atol=3e-4 if fam == "n" else 2e-5)
+    assert np.abs(a).sum() > 0
+    X = rng.standard_normal((n, 6)).astype(np.float32)
+    a = getattr(RK, f"jit{fam}mm")(*params, prob, X, seed, **kw)
+    b = getattr(O, f"jit{fam}mm")(*params, prob, X, seed, **kw)
+    np.testing.assert_allclose(b, a, rtol=1e-5, atol=3e-4 if fam == "n" else 2e-5)
+    assert np.abs(a).sum() > 0
+
+
+def test_float_fcn_matches_dense():
+    # the reference FCN float ops are jnp formulas (_fcn/float.py:33-260): compare with dense algebra
+    f = cases.fcn_case(43, 120, 90, 7)
+    rng = np.random.default_rng(44)
+    dense = np.zeros((120, 90), np.float64)
+    for i in range(120):
+        for j in range(7):
+            dense[i, f["indices"][i, j]] += f["weights"][i, j]
+    x1, x0 = rng.standard_normal(120).astype(np.float32), rng.standard_normal(90).astype(np.float32)
+    np.testing.assert_allclose(O.fcnmv(f["weights"], f["indices"], x1, shape=(120, 90), transpose=True), x1 @ dense, rtol=1e-4, atol=1e-4)
+    np.testing.assert_allclose(O.fcnmv(f["weights"], f["indices"], x0, shape=(120, 90), transpose=False), dense @ x0, rtol=1e-4, atol=1e-4)
+    X1 = rng.standard_normal((120, 5)).astype(np.float32)
+    np.testing.assert_allclose(O.fcnmm(f["weights"], f["indices"], X1, shape=(120, 90), transpose=True), dense.T @ X1, rtol=1e-4, atol=1e-4)
