@@ -21,7 +21,8 @@ from ._float import (csrmm, csrmm_p, csrmm_p_call, csrmv, csrmv_p, csrmv_p_call,
 from ._jitc import (JITCMatrix, JITCNormalC, JITCNormalR, JITCScalarC, JITCScalarR, JITCUniformC,
                     JITCUniformR, binary_jitnmm, binary_jitnmm_p, binary_jitnmv, binary_jitnmv_p,
                     binary_jitsmm, binary_jitsmm_p, binary_jitsmv, binary_jitsmv_p, binary_jitumm,
-                    binary_jitumm_p, binary_jitumv, binary_jitumv_p, jitc_row_connections)
+                    binary_jitumm_p, binary_jitumv, binary_jitumv_p, jitc_row_connections, jitn_to_csr,
+                    jits_to_csr, jitu_to_csr)
 from ._op import (KernelEntry, XLACustomKernel, get_all_primitive_names, get_primitives_by_tags,
                   get_registry)
 

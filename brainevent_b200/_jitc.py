@@ -168,6 +168,110 @@ def jitc_row_connections(prob, seed, rows, k, chunk_size, stride=MV_STRIDE, devi
 
 
 # ---------------------------------------------------------------------------------------------
+# JITC -> CSR materialisation (ref: _jit_scalar/csr.py:488 jits_to_csr, _jit_normal/csr.py:465,
+# _jit_uniform/csr.py)
+# ---------------------------------------------------------------------------------------------
+MM_STRIDE = 4
+
+
+def _normalize_matrix_mode(matrix_mode):
+    if matrix_mode not in ("mv", "mm"):
+        raise ValueError(f"matrix_mode must be 'mv' or 'mm', got {matrix_mode!r}")
+    return matrix_mode
+
+
+def _jit_to_csr(kind, params, prob, seed, shape, corder, matrix_mode, device):
+    from ._csr import CSR
+    n_rows, n_cols = int(shape[0]), int(shape[1])
+    stride = MV_STRIDE if _normalize_matrix_mode(matrix_mode) == "mv" else MM_STRIDE
+    units = [split_mantissa_unit(p)[1] for p in params]
+    p0 = _param(split_mantissa_unit(params[0])[0], device, None)
+    p1 = _param(split_mantissa_unit(params[1])[0], device, p0.dtype) if len(params) > 1 else None
+    dev = p0.device
+    if n_rows == 0 or n_cols == 0 or float(prob) == 0.0:
+        return CSR((torch.zeros(0, dtype=p0.dtype, device=dev), torch.zeros(0, dtype=torch.int32, device=dev),
+                    torch.zeros(n_rows + 1, dtype=torch.int32, device=dev)), shape=(n_rows, n_cols))
+    clen, seed_t = _initialize_conn_length(prob, dev), _initialize_seed(seed, dev)
+    chunk = _normalize_chunk_size(n_cols)
+    L = _lib.lib()
+    ws = torch.empty(L.be_b200_jitc_csr_workspace_bytes(n_rows, 0), dtype=torch.uint8, device=dev)
+    indptr = torch.empty(n_rows + 1, dtype=torch.int64, device=dev)
+    _lib.check(L.be_b200_jitc_csr_count(ptr(clen), ptr(seed_t), n_rows, n_cols, chunk, stride, int(bool(corder)),
+                                        ptr(indptr), ptr(ws), ws.numel(), stream_ptr(dev)), "jitc_csr_count")
+    nnz = int(indptr[-1].item())      # the one host read-back, as in the reference (csr.py:530)
+    indices = torch.empty(nnz, dtype=torch.int32, device=dev)
+    data = torch.empty(nnz, dtype=p0.dtype, device=dev)
+    if nnz:
+        ws = torch.empty(L.be_b200_jitc_csr_workspace_bytes(n_rows, nnz), dtype=torch.uint8, device=dev)
+        _lib.check(L.be_b200_jitc_csr_fill(_KIND[kind], ptr(p0), ptr(p1), wt_code(p0.dtype), ptr(clen), ptr(seed_t),
+                                           n_rows, n_cols, chunk, stride, int(bool(corder)), ptr(indptr), nnz,
+                                           ptr(indices), ptr(data), ptr(ws), ws.numel(), stream_ptr(dev)),
+                   "jitc_csr_fill")
+    if nnz < 2 ** 31:
+        indptr = indptr.to(torch.int32)
+    return CSR((maybe_decimal(data, units[0]), indices, indptr), shape=(n_rows, n_cols))
+
+
+def jits_to_csr(weight, prob, seed, *, shape, corder, matrix_mode, backend=None, device="cuda"):
+    """CSR of the matrix jitsmv ('mv') / jitsmm ('mm') applies with transpose=False
+    (ref: _jit_scalar/csr.py:488)."""
+    return _jit_to_csr("scalar", (weight,), prob, seed, shape, corder, matrix_mode, device)
+
+
+def jitn_to_csr(w_loc, w_scale, prob, seed, *, shape, corder, matrix_mode, backend=None, device="cuda"):
+    """ref: _jit_normal/csr.py:465."""
+    return _jit_to_csr("normal", (w_loc, w_scale), prob, seed, shape, corder, matrix_mode, device)
+
+
+def jitu_to_csr(w_low, w_high, prob, seed, *, shape, corder, matrix_mode, backend=None, device="cuda"):
+    """ref: _jit_uniform/csr.py."""
+    return _jit_to_csr("uniform", (w_low, w_high), prob, seed, shape, corder, matrix_mode, device)
+
+
+class _ModeView:
+    """`mat.mv` / `mat.mm`: the mv (stride 32) and mm (stride 4) kernels draw different matrices,
+    so materialisation names the one it wants (ref: _jit_scalar/main.py:40-86)."""
+    __slots__ = ("_mat", "_mode")
+
+    def __init__(self, mat, mode):
+        self._mat, self._mode = mat, mode
+
+    def _generated(self, device):
+        m = self._mat
+        gen_shape, gen_transpose = m._materialize_params()
+        # the products of a column-oriented class run the generator with transpose=True: its rows
+        # are then the generated matrix's COLUMNS for corder=True (and its rows for corder=False),
+        # i.e. the materialisation with the opposite corder
+        corder = (not m.corder) if gen_transpose else m.corder
+        g = _jit_to_csr(type(m)._family, m.params, m.prob, m.seed, gen_shape, corder, self._mode, device)
+        return g, gen_transpose
+
+    def tocsr(self, device="cuda"):
+        from ._csr import CSR, csr_to_csc_index
+        g, gen_transpose = self._generated(device)
+        if not gen_transpose:
+            return g
+        # column-oriented classes generate the transpose: CSR(M) = CSC mirror of the generated CSR
+        indptr, indices, perm = csr_to_csc_index(g.indptr, g.indices, shape=g.shape)
+        return CSR((g.data[perm.long()], indices, indptr), shape=self._mat.shape)
+
+    def tocsc(self, device="cuda"):
+        from ._csr import CSC, csr_to_csc_index
+        g, gen_transpose = self._generated(device)
+        if gen_transpose:
+            return g.T          # the generated CSR compresses the columns of the logical matrix
+        indptr, indices, perm = csr_to_csc_index(g.indptr, g.indices, shape=g.shape)
+        return CSC((g.data[perm.long()], indices, indptr), shape=g.shape)
+
+    def todense(self, device="cuda"):
+        g, gen_transpose = self._generated(device)
+        return g.todense().t() if gen_transpose else g.todense()
+
+    def __repr__(self):
+        return f"{type(self._mat).__name__}.{self._mode}"
+
+
+# ---------------------------------------------------------------------------------------------
 # matrix classes
 # ---------------------------------------------------------------------------------------------
 class JITCMatrix:
@@ -183,6 +287,20 @@ class JITCMatrix:
         self.backend = backend
 
         self._dev = {}
+
+    @property
+    def mv(self):
+        return _ModeView(self, "mv")
+
+    @property
+    def mm(self):
+        return _ModeView(self, "mm")
+
+    def tocsr(self):
+        raise NotImplementedError("tocsr() is ambiguous for JITC matrices: the mv and mm kernels draw different "
+                                  "matrices. Use mat.mv.tocsr() or mat.mm.tocsr().")
+
+    todense = tocsr
 
     def _device_params(self, device):
         """weight parameters, clen and seed as one-element device tensors, created once per device
@@ -223,6 +341,9 @@ class JITCMatrix:
 class _JITC_R(JITCMatrix):
     """Row-oriented: the generated matrix has the logical shape (ref: _jit_scalar/main.py:885-1066)."""
 
+    def _materialize_params(self):
+        return self.shape, False
+
     def __matmul__(self, other):
         return self._run(other, self.shape, False, self.corder, self._call(other, None, None, None))
 
@@ -239,6 +360,9 @@ class _JITC_R(JITCMatrix):
 class _JITC_C(JITCMatrix):
     """Column-oriented: the generator is invoked with shape[::-1] (ref: _jit_scalar/main.py:1392-1593),
     so R and C of the same logical shape draw different matrices."""
+
+    def _materialize_params(self):
+        return self.shape[::-1], True
 
     def __matmul__(self, other):
         return self._run(other, self.shape[::-1], True, self.corder, self._call(other, None, None, None))

@@ -64,6 +64,9 @@ _SIGNATURES = {
     "be_b200_fcnmm": (_I, [_P, _I, _I, _P, _L, _L, _P, _L, _L, _I, _P, _P]),
     "be_b200_jitmv": (_I, [_I, _P, _P, _I, _P, _P, _P, _L, _L, _L, _I, _P, _P]),
     "be_b200_jitmm": (_I, [_I, _P, _P, _I, _P, _P, _P, _L, _L, _L, _L, _I, _P, _P]),
+    "be_b200_jitc_csr_workspace_bytes": (_Z, [_L, _L]),
+    "be_b200_jitc_csr_count": (_I, [_P, _P, _L, _L, _L, _I, _I, _P, _P, _Z, _P]),
+    "be_b200_jitc_csr_fill": (_I, [_I, _P, _P, _I, _P, _P, _L, _L, _L, _I, _I, _P, _L, _P, _P, _P, _Z, _P]),
     "be_b200_jitc_row_connections": (_I, [_P, _P, _L, _L, _L, _L, _I, _P, _P, _L, _P]),
     "be_b200_binary_densemv": (_I, [_P, _I, _L, _L, _P, _P, _I, _I, _P, _P, _Z, _P]),
     "be_b200_binary_densemm": (_I, [_P, _I, _L, _L, _P, _P, _I, _L, _I, _P, _P, _Z, _P]),

@@ -198,6 +198,24 @@ int be_b200_jitmm(int kind, const void* p0, const void* p1, int w_dtype, const i
                   const int32_t* seed, const void* X, int64_t vec_len, int64_t out_len, int64_t n,
                   int64_t chunk_size, int corder, void* out, void* stream);
 
+/* ---- JITC -> CSR materialisation (ref: _jit_scalar/csr.py:488 jits_to_csr with its count (:112)
+ *      and fill (:310) passes, _jit_normal/csr.py:465, _jit_uniform/csr.py; csr.cu next to each).
+ *      The result is the canonical CSR (columns ascending inside every row) of the [n_rows, n_cols]
+ *      matrix that jit?mv (stride 32) or jit?mm (stride 4) applies with transpose=0 and the given
+ *      corder.  count writes int64 indptr[n_rows+1] (indptr[n_rows] = nnz); the host reads nnz,
+ *      allocates indices[nnz] / data[nnz] and calls fill with the same parameters.  One workspace
+ *      (256-byte aligned, be_b200_jitc_csr_workspace_bytes(n_rows, nnz); nnz = 0 for the count
+ *      pass) serves both. ------------------------------------------------------------------------ */
+size_t be_b200_jitc_csr_workspace_bytes(int64_t n_rows, int64_t nnz);
+int be_b200_jitc_csr_count(const int32_t* clen, const int32_t* seed, int64_t n_rows, int64_t n_cols,
+                           int64_t chunk_size, int stride, int corder, int64_t* indptr,
+                           void* workspace, size_t workspace_bytes, void* stream);
+int be_b200_jitc_csr_fill(int kind, const void* p0, const void* p1, int w_dtype, const int32_t* clen,
+                          const int32_t* seed, int64_t n_rows, int64_t n_cols, int64_t chunk_size,
+                          int stride, int corder, const int64_t* indptr, int64_t nnz,
+                          int32_t* indices, void* data, void* workspace, size_t workspace_bytes,
+                          void* stream);
+
 /* ---- dense event ops (ref: _dense/binary.py:79 binary_densemv, :487 binary_densemm;
  *      _dense/binary_densemv.cu, binary_densemm.cu) --------------------------------------------
  * W row-major [rows, cols].  transpose=1: events[rows] -> out[cols]; transpose=0: events[cols]

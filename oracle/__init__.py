@@ -519,3 +519,47 @@ def jitnmm(w_loc, w_scale, prob, B, seed, *, shape, transpose=False, corder=True
 
 def jitumm(w_low, w_high, prob, B, seed, *, shape, transpose=False, corder=True, dtype=np.float32):
     return _jit_mm_val(2, w_low, w_high, prob, B, seed, shape, transpose, corder, dtype)
+
+
+# ----------------------------------------------------------------------------------------------
+# JITC -> CSR materialisation -- SURVEY 8(f)-2
+# ----------------------------------------------------------------------------------------------
+def _jit_to_csr(kind, p0, p1, prob, seed, shape, corder, matrix_mode, dtype):
+    """(data, indices, indptr) column-sorted, like jits_to_csr (_jit_scalar/csr.py:488-570)."""
+    n_rows, n_cols = int(shape[0]), int(shape[1])
+    stride = {"mv": 32, "mm": 4}[matrix_mode]
+    clen = conn_length(prob)
+    chunk = normalize_chunk_size(n_cols)
+    counts = np.zeros(n_rows, np.int64)
+    if n_rows and n_cols:
+        lib().ora_jit_csr_count(_u32(clen), _u32(seed), _i64(n_rows), _i64(n_cols), _i64(chunk), stride,
+                                int(bool(corder)), _p(counts))
+    indptr = np.zeros(n_rows + 1, np.int64)
+    np.cumsum(counts, out=indptr[1:])
+    nnz = int(indptr[-1])
+    indices = np.zeros(nnz, np.int32)
+    data = np.zeros(nnz, dtype)
+    if nnz:
+        cursor = np.zeros(n_rows, np.int64)
+        getattr(lib(), "ora_jit_csr_fill" + _sfx(dtype))(
+            kind, _scalar(dtype, p0), _scalar(dtype, p1), _u32(clen), _u32(seed), _i64(n_rows), _i64(n_cols),
+            _i64(chunk), stride, int(bool(corder)), _p(indptr), _p(cursor), _p(indices), _p(data))
+        seg = np.repeat(np.arange(n_rows, dtype=np.int64), counts)
+        order = np.lexsort((indices, seg))
+        indices, data = indices[order], data[order]
+    return data, indices, indptr
+
+
+def jits_to_csr(weight, prob, seed, *, shape, corder, matrix_mode, dtype=np.float32):
+    """_jit_scalar/csr.py:488."""
+    return _jit_to_csr(0, weight, 0.0, prob, seed, shape, corder, matrix_mode, dtype)
+
+
+def jitn_to_csr(w_loc, w_scale, prob, seed, *, shape, corder, matrix_mode, dtype=np.float32):
+    """_jit_normal/csr.py:465."""
+    return _jit_to_csr(1, w_loc, w_scale, prob, seed, shape, corder, matrix_mode, dtype)
+
+
+def jitu_to_csr(w_low, w_high, prob, seed, *, shape, corder, matrix_mode, dtype=np.float32):
+    """_jit_uniform/csr.py."""
+    return _jit_to_csr(2, w_low, w_high, prob, seed, shape, corder, matrix_mode, dtype)

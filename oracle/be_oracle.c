@@ -192,6 +192,25 @@ void ora_csr_to_csc(const int64_t* indptr, const int32_t* indices, int64_t m, in
 /* ------------------------------------------------------------------------------------------
  * typed operators, instantiated for f32 and f64
  * ---------------------------------------------------------------------------------------- */
+/* ---- JITC -> CSR materialisation  (_jit_scalar/csr.py:112-205 count, :310-411 fill; the normal
+ * and uniform modules are the same walk with per-entry weights) --------------------------------
+ * corder=1: generator row == CSR row, walk over the n_cols columns.
+ * corder=0: generator rows are the n_cols COLUMNS, the walk runs over the n_rows CSR rows.
+ * chunk_size always comes from n_cols (the reference's quirk, csr.py:135).  counts is
+ * int64[n_rows]. */
+void ora_jit_csr_count(uint32_t clen, uint32_t seed0, int64_t n_rows, int64_t n_cols,
+                       int64_t chunk_size, int stride, int corder, int64_t* counts) {
+    uint32_t cl = clen < 2U ? 2U : clen;
+    for (int64_t r = 0; r < n_rows; ++r) counts[r] = 0;
+    if (corder) {
+        for (int64_t row = 0; row < n_rows; ++row)
+            ORA_WALK_ROW(seed0, cl, row, n_cols, chunk_size, stride, { (void)j; counts[row] += 1; });
+    } else {
+        for (int64_t row = 0; row < n_cols; ++row)
+            ORA_WALK_ROW(seed0, cl, row, n_rows, chunk_size, stride, { counts[j] += 1; });
+    }
+}
+
 #define T float
 #define SFX(name) name##_f32
 #include "be_oracle_ops.inc"

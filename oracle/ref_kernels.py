@@ -7,7 +7,7 @@ signature as its counterpart in oracle/__init__.py, so tests can compare them ca
 import numpy as np
 
 from . import ref_shim as R
-from . import conn_length
+from . import conn_length, normalize_chunk_size
 
 SDS = R.SDS
 available = R.available
@@ -267,3 +267,45 @@ def jitnmm(w_loc, w_scale, prob, B, seed, *, shape, transpose=False, corder=True
 def jitumm(w_low, w_high, prob, B, seed, *, shape, transpose=False, corder=True, dtype=np.float32):
     return _jit_float("_jit_uniform.float", "_jitumm_numba_kernel_generator", [w_low, w_high], prob, B, seed, shape,
                       transpose, corder, dtype)
+
+
+# -- JITC -> CSR materialisation ---------------------------------------------------------------------
+def _jit_to_csr(modname, fam, params, prob, seed, shape, corder, matrix_mode, dtype):
+    """count + fill through the reference's numba kernels, with the orchestration of
+    jits_to_csr (_jit_scalar/csr.py:488-570: row sums, exclusive offsets, lexsort) in numpy."""
+    m = R.ref_module(modname)
+    n_rows, n_cols = int(shape[0]), int(shape[1])
+    chunk = normalize_chunk_size(n_cols)
+    n_chunks = -(-n_cols // chunk)
+    clen = np.asarray([conn_length(prob)], np.int32)
+    seed = np.asarray([seed], np.int32)
+    ps = [np.asarray([p], dtype) for p in params]
+    kw = dict(shape=(n_rows, n_cols), corder=corder, matrix_mode=matrix_mode)
+    cshape = (n_rows, n_chunks) if corder else (n_rows,)
+    cc = _first(getattr(m, f"_jit{fam}_csr_count_numba_kernel")(outs=[SDS(cshape, np.int32)], **kw)(*ps, clen, seed))
+    row_counts = cc.sum(axis=1).astype(np.int64) if corder else cc.astype(np.int64)
+    indptr = np.concatenate([[0], np.cumsum(row_counts)]).astype(np.int64)
+    nnz = int(indptr[-1])
+    if corder:
+        offsets = (indptr[:-1, None] + np.cumsum(cc, axis=1) - cc).astype(np.int32)
+    else:
+        offsets = indptr.astype(np.int32)
+    outs = [SDS((nnz,), np.int32), SDS((nnz,), dtype)]
+    if not corder:
+        outs.append(SDS((n_rows,), np.int32))
+    res = getattr(m, f"_jit{fam}_csr_fill_numba_kernel")(outs=outs, **kw)(*ps, clen, seed, offsets)
+    indices, data = res[0], res[1]
+    order = np.lexsort((indices, np.repeat(np.arange(n_rows), row_counts)))
+    return data[order], indices[order], indptr
+
+
+def jits_to_csr(weight, prob, seed, *, shape, corder, matrix_mode, dtype=np.float32):
+    return _jit_to_csr("_jit_scalar.csr", "s", [weight], prob, seed, shape, corder, matrix_mode, dtype)
+
+
+def jitn_to_csr(w_loc, w_scale, prob, seed, *, shape, corder, matrix_mode, dtype=np.float32):
+    return _jit_to_csr("_jit_normal.csr", "n", [w_loc, w_scale], prob, seed, shape, corder, matrix_mode, dtype)
+
+
+def jitu_to_csr(w_low, w_high, prob, seed, *, shape, corder, matrix_mode, dtype=np.float32):
+    return _jit_to_csr("_jit_uniform.csr", "u", [w_low, w_high], prob, seed, shape, corder, matrix_mode, dtype)

@@ -136,7 +136,11 @@ def golden_float_ops():
     """float (non-event) operators: every case of golden_cases.float_op_cases() through the
     reference's numba kernels."""
     from tests import golden_cases
-    save("float_ops", **{tag: fn(RK) for tag, fn, _ in golden_cases.float_op_cases()})
+    out = {tag: fn(RK) for tag, fn, _ in golden_cases.float_op_cases()}
+    for tag, fn, _ in golden_cases.to_csr_cases():
+        data, indices, indptr = fn(RK)
+        out[tag + "_data"], out[tag + "_indices"], out[tag + "_indptr"] = data, indices, indptr
+    save("float_ops", **out)
 
 
 if __name__ == "__main__":

@@ -98,3 +98,14 @@ def float_op_cases():
                     api, f"jit{fam}mv")(*params, prob, v, seed, shape=shape, transpose=tr, corder=co)), atol)
                 yield (tag + "_mm", (lambda api, fam=fam, params=params, B=B, tr=tr, co=co: getattr(
                     api, f"jit{fam}mm")(*params, prob, B, seed, shape=shape, transpose=tr, corder=co)), atol)
+
+
+def to_csr_cases():
+    """(tag, fn(api) -> (data, indices, indptr), atol): JITC -> CSR materialisation."""
+    shape, prob, seed = (230, 310), 0.05, 2468
+    for fam, params in [("s", (1.5,)), ("n", (1.0, 0.1)), ("u", (-0.5, 1.0))]:
+        for co in (False, True):
+            for mode in ("mv", "mm"):
+                yield (f"tocsr_{fam}_c{int(co)}_{mode}", (lambda api, fam=fam, params=params, co=co, mode=mode: getattr(
+                    api, f"jit{fam}_to_csr")(*params, prob, seed, shape=shape, corder=co, matrix_mode=mode)),
+                    3e-4 if fam == "n" else 1e-6)

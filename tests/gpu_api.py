@@ -152,3 +152,22 @@ def jitumv(lo, hi, prob, v, seed, *, shape, transpose=False, corder=True, dtype=
 
 def jitumm(lo, hi, prob, B, seed, *, shape, transpose=False, corder=True, dtype=np.float32):
     return _jit(be.jitumm, [lo, hi], prob, B, seed, shape, transpose, corder, dtype)
+
+
+def _to_csr(fn, params, prob, seed, shape, corder, matrix_mode, dtype):
+    td = torch.float32 if np.dtype(dtype) == np.float32 else torch.float64
+    ps = [torch.tensor([p], dtype=td, device=DEV) for p in params]
+    c = fn(*ps, prob, seed, shape=shape, corder=corder, matrix_mode=matrix_mode)
+    return _np(c.data), _np(c.indices), _np(c.indptr).astype(np.int64)
+
+
+def jits_to_csr(w, prob, seed, *, shape, corder, matrix_mode, dtype=np.float32):
+    return _to_csr(be.jits_to_csr, [w], prob, seed, shape, corder, matrix_mode, dtype)
+
+
+def jitn_to_csr(loc, scale, prob, seed, *, shape, corder, matrix_mode, dtype=np.float32):
+    return _to_csr(be.jitn_to_csr, [loc, scale], prob, seed, shape, corder, matrix_mode, dtype)
+
+
+def jitu_to_csr(lo, hi, prob, seed, *, shape, corder, matrix_mode, dtype=np.float32):
+    return _to_csr(be.jitu_to_csr, [lo, hi], prob, seed, shape, corder, matrix_mode, dtype)

@@ -132,3 +132,12 @@ def test_ops_fixture(tag, fn, atol):
 def test_float_ops_fixture(tag, fn, atol):
     g = golden_cases.load("float_ops")
     np.testing.assert_allclose(fn(O), g[tag], rtol=1e-5, atol=atol)
+
+
+def test_jitc_to_csr_fixture():
+    g = golden_cases.load("float_ops")
+    for tag, fn, atol in golden_cases.to_csr_cases():
+        data, indices, indptr = fn(O)
+        np.testing.assert_array_equal(indptr, g[tag + "_indptr"])
+        np.testing.assert_array_equal(indices, g[tag + "_indices"])
+        np.testing.assert_allclose(data, g[tag + "_data"], rtol=1e-6, atol=atol)

@@ -210,3 +210,22 @@ def test_float_fcn_matches_dense():
     np.testing.assert_allclose(O.fcnmv(f["weights"], f["indices"], x0, shape=(120, 90), transpose=False), dense @ x0, rtol=1e-4, atol=1e-4)
     X1 = rng.standard_normal((120, 5)).astype(np.float32)
     np.testing.assert_allclose(O.fcnmm(f["weights"], f["indices"], X1, shape=(120, 90), transpose=True), dense.T @ X1, rtol=1e-4, atol=1e-4)
+
+
+# ---- JITC -> CSR materialisation: SURVEY 8(f)-2 -----------------------------------------------------
+@pytest.mark.parametrize("fam,params", JIT)
+@pytest.mark.parametrize("corder", [False, True])
+@pytest.mark.parametrize("mode", ["mv", "mm"])
+def test_jitc_to_csr(RK, fam, params, corder, mode):
+    shape, prob, seed = (230, 310), 0.05, 77
+    a = getattr(RK, f"jit{fam}_to_csr")(*params, prob, seed, shape=shape, corder=corder, matrix_mode=mode)
+    b = getattr(O, f"jit{fam}_to_csr")(*params, prob, seed, shape=shape, corder=corder, matrix_mode=mode)
+    np.testing.assert_array_equal(b[2], a[2])
+    np.testing.assert_array_equal(b[1], a[1])
+    np.testing.assert_allclose(b[0], a[0], rtol=1e-6, atol=3e-4 if fam == "n" else 1e-6)
+    assert a[1].size > 0
+    # the CSR is the matrix the mv operator applies (same orientation rule as jits(), csr.py:500-504)
+    if mode == "mv":
+        x = np.random.default_rng(5).standard_normal(shape[1]).astype(np.float32)
+        y = getattr(O, f"jit{fam}mv")(*params, prob, x, seed, shape=shape, transpose=False, corder=corder)
+        np.testing.assert_allclose(O.csrmv(b[0], b[1], b[2], x, shape=shape), y, rtol=1e-4, atol=1e-4)
