@@ -23,6 +23,9 @@ from ._jitc import (JITCMatrix, JITCNormalC, JITCNormalR, JITCScalarC, JITCScala
                     binary_jitsmm, binary_jitsmm_p, binary_jitsmv, binary_jitsmv_p, binary_jitumm,
                     binary_jitumm_p, binary_jitumv, binary_jitumv_p, jitc_row_connections, jitn_to_csr,
                     jits_to_csr, jitu_to_csr)
+from ._plasticity import (update_csc_on_binary_post, update_csc_on_binary_pre, update_csr_on_binary_post,
+                          update_csr_on_binary_pre, update_dense_on_binary_post, update_dense_on_binary_pre,
+                          update_fixed_post_conn_on_binary_pre, update_fixed_pre_conn_on_binary_post)
 from ._op import (KernelEntry, XLACustomKernel, get_all_primitive_names, get_primitives_by_tags,
                   get_registry)
 

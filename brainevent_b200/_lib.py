@@ -40,6 +40,7 @@ def build(verbose: bool = False, jobs: int = 8) -> str:
 
 
 _P, _I, _L, _Z = ctypes.c_void_p, ctypes.c_int, ctypes.c_int64, ctypes.c_size_t
+_D = ctypes.c_double
 
 _SIGNATURES = {
     "be_b200_last_error": (ctypes.c_char_p, []),
@@ -67,6 +68,9 @@ _SIGNATURES = {
     "be_b200_jitc_csr_workspace_bytes": (_Z, [_L, _L]),
     "be_b200_jitc_csr_count": (_I, [_P, _P, _L, _L, _L, _I, _I, _P, _P, _Z, _P]),
     "be_b200_jitc_csr_fill": (_I, [_I, _P, _P, _I, _P, _P, _L, _L, _L, _I, _I, _P, _L, _P, _P, _P, _Z, _P]),
+    "be_b200_plasticity_rows": (_I, [_P, _I, _P, _P, _I, _L, _P, _I, _P, _P, _I, _P, _L, _L, _L, _D, _D, _P, _Z, _P]),
+    "be_b200_plasticity_dense": (_I, [_P, _I, _L, _L, _P, _P, _I, _P, _I, _D, _D, _P, _Z, _P]),
+    "be_b200_clip": (_I, [_P, _I, _L, _D, _D, _P]),
     "be_b200_jitc_row_connections": (_I, [_P, _P, _L, _L, _L, _L, _I, _P, _P, _L, _P]),
     "be_b200_binary_densemv": (_I, [_P, _I, _L, _L, _P, _P, _I, _I, _P, _P, _Z, _P]),
     "be_b200_binary_densemm": (_I, [_P, _I, _L, _L, _P, _P, _I, _L, _I, _P, _P, _Z, _P]),

@@ -222,10 +222,11 @@ struct ProfileScope {
 // it is zeroed by the compaction kernel itself when one is launched (no separate memset node),
 // otherwise by cudaMemsetAsync.  `ordered_ids=false` lets the id list be block-ordered only
 // (one atomic per tile instead of the look-back chain) -- fine for scatter consumers.
+// `nonzero`: float spikes are active when != 0 (plasticity, encoders) instead of > 0 (operators).
 int prepare_events_1d(const void* spikes, const void* aux, int spk_kind, int64_t n,
                       bool need_ids, bool need_packed, void* workspace, size_t workspace_bytes,
                       cudaStream_t stream, Events* ev, void* zero_ptr = nullptr,
-                      size_t zero_bytes = 0, bool ordered_ids = true);
+                      size_t zero_bytes = 0, bool ordered_ids = true, bool nonzero = false);
 int prepare_events_2d(const void* spikes, const void* aux, int spk_kind, int64_t n, int64_t batch,
                       bool need_ids, void* workspace, size_t workspace_bytes, cudaStream_t stream,
                       Events* ev);

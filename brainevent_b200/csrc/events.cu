@@ -450,7 +450,7 @@ int compact_2d_any(const void* spikes, int spk_kind, int64_t n, int64_t batch, b
 
 int prepare_events_1d(const void* spikes, const void* aux, int spk_kind, int64_t n, bool need_ids,
                       bool need_packed, void* workspace, size_t workspace_bytes, cudaStream_t s,
-                      Events* ev, void* zero_ptr, size_t zero_bytes, bool ordered_ids) {
+                      Events* ev, void* zero_ptr, size_t zero_bytes, bool ordered_ids, bool nonzero) {
     int rc = check_ws(workspace, workspace_bytes, n, 1);
     if (rc) return rc;
     Workspace ws = ws_carve(workspace, n, 1);
@@ -475,11 +475,11 @@ int prepare_events_1d(const void* spikes, const void* aux, int spk_kind, int64_t
     }
     ev->packed = ws.packed;
     if (need_ids)
-        return compact_1d_any(spikes, spk_kind, n, false, ws, ws.active_ids, nullptr,
+        return compact_1d_any(spikes, spk_kind, n, nonzero, ws, ws.active_ids, nullptr,
                               need_packed ? ws.packed : nullptr, s, zero_ptr, zero_bytes, ordered_ids);
     if (need_packed && n > 0) {
-        if (spk_kind == BE_B200_SPK_BOOL) return launch_bitpack<BE_B200_SPK_BOOL>(spikes, n, false, ws.packed, s);
-        if (spk_kind == BE_B200_SPK_F32) return launch_bitpack<BE_B200_SPK_F32>(spikes, n, false, ws.packed, s);
+        if (spk_kind == BE_B200_SPK_BOOL) return launch_bitpack<BE_B200_SPK_BOOL>(spikes, n, nonzero, ws.packed, s);
+        if (spk_kind == BE_B200_SPK_F32) return launch_bitpack<BE_B200_SPK_F32>(spikes, n, nonzero, ws.packed, s);
         set_error("unsupported event kind %d", spk_kind);
         return BE_B200_EINVAL;
     }

@@ -216,6 +216,29 @@ int be_b200_jitc_csr_fill(int kind, const void* p0, const void* p1, int w_dtype,
                           int32_t* indices, void* data, void* workspace, size_t workspace_bytes,
                           void* stream);
 
+/* ---- spike-triggered additive plasticity.  In place on `weights`:
+ *      for every ACTIVE row r and stored slot j of r:
+ *          w[slot(j)] = clamp(w[slot(j)] + trace[indices[j]], w_min, w_max),  slot(j) = perm ? perm[j] : j
+ *      Pass -INFINITY / +INFINITY for an absent bound.  n_conn >= 0 selects fixed-number (ELL) rows
+ *      and ignores indptr.  Events follow the be_b200_binary_* convention (length n_rows).
+ *      ref: _csr/plasticity_binary.py:45 update_csr_on_binary_pre (rows = pre, perm = NULL),
+ *           :477 update_csr_on_binary_post (rows = post over the CSC mirror, perm = weight_indices),
+ *           _fcn/plasticity_binary.py:207/:269 (ELL rows), plasticity_binary_on_{pre,post}.cu,
+ *           plasticity_row_driven.cu.  The reference clips the whole array afterwards: be_b200_clip.
+ *      dense (ref: _dense/plasticity_binary.py:42, :360): W [rows, cols] row-major; on_post=0:
+ *      W[i,:] += trace[cols] for active i (events length rows); on_post=1: W[:,j] += trace[rows]
+ *      for active j (events length cols). ------------------------------------------------------- */
+int be_b200_plasticity_rows(void* weights, int w_dtype, const int32_t* indices, const void* indptr,
+                            int indptr_is64, int64_t n_conn, const void* perm, int perm_is64,
+                            const void* spikes, const void* aux, int spk_kind, const void* trace,
+                            int64_t n_rows, int64_t n_trace, int64_t nse, double w_min, double w_max,
+                            void* workspace, size_t workspace_bytes, void* stream);
+int be_b200_plasticity_dense(void* W, int w_dtype, int64_t rows, int64_t cols, const void* spikes,
+                             const void* aux, int spk_kind, const void* trace, int on_post,
+                             double w_min, double w_max, void* workspace, size_t workspace_bytes,
+                             void* stream);
+int be_b200_clip(void* w, int w_dtype, int64_t n, double w_min, double w_max, void* stream);
+
 /* ---- dense event ops (ref: _dense/binary.py:79 binary_densemv, :487 binary_densemm;
  *      _dense/binary_densemv.cu, binary_densemm.cu) --------------------------------------------
  * W row-major [rows, cols].  transpose=1: events[rows] -> out[cols]; transpose=0: events[cols]

@@ -563,3 +563,55 @@ def jitn_to_csr(w_loc, w_scale, prob, seed, *, shape, corder, matrix_mode, dtype
 def jitu_to_csr(w_low, w_high, prob, seed, *, shape, corder, matrix_mode, dtype=np.float32):
     """_jit_uniform/csr.py."""
     return _jit_to_csr(2, w_low, w_high, prob, seed, shape, corder, matrix_mode, dtype)
+
+
+# ----------------------------------------------------------------------------------------------
+# spike-triggered additive plasticity -- SURVEY 8(f)-4 (plain numpy restatements)
+# ----------------------------------------------------------------------------------------------
+def _clip(w, w_min, w_max):
+    if w_min is None and w_max is None:
+        return w
+    return np.clip(w, w_min, w_max).astype(w.dtype)
+
+
+def update_csr_on_binary_pre(weight, indices, indptr, pre_spike, post_trace, w_min=None, w_max=None, *, shape):
+    """_csr/plasticity_binary.py:176-204: out_w[i_start:i_end] += post_trace[indices[i_start:i_end]]."""
+    w = np.array(weight, copy=True)
+    act = active_mask(pre_spike, True)
+    for i in np.nonzero(act)[0]:
+        s, e = int(indptr[i]), int(indptr[i + 1])
+        w[s:e] += np.asarray(post_trace, w.dtype)[indices[s:e]]
+    return _clip(w, w_min, w_max)
+
+
+def update_csr_on_binary_post(weight, indices, indptr, weight_indices, pre_trace, post_spike, w_min=None, w_max=None,
+                              *, shape):
+    """_csr/plasticity_binary.py:621-654: out_w[weight_indices[seg]] += pre_trace[indices[seg]]."""
+    w = np.array(weight, copy=True)
+    act = active_mask(post_spike, True)
+    for i in np.nonzero(act)[0]:
+        s, e = int(indptr[i]), int(indptr[i + 1])
+        w[weight_indices[s:e]] += np.asarray(pre_trace, w.dtype)[indices[s:e]]
+    return _clip(w, w_min, w_max)
+
+
+def fcn_plasticity_row(data, indices, spike, trace, w_min=None, w_max=None):
+    """_fcn/plasticity_binary.py:81-109: out[r, k] += trace[indices[r, k]] for firing rows r."""
+    w = np.array(data, copy=True)
+    act = active_mask(spike, True).astype(bool)
+    w[act] += np.asarray(trace, w.dtype)[indices[act]]
+    return _clip(w, w_min, w_max)
+
+
+def update_dense_on_binary_pre(weight, pre_spike, post_trace, w_min=None, w_max=None):
+    """_dense/plasticity_binary.py:144-164."""
+    w = np.array(weight, copy=True)
+    w[active_mask(pre_spike, True).astype(bool)] += np.asarray(post_trace, w.dtype)[None, :]
+    return _clip(w, w_min, w_max)
+
+
+def update_dense_on_binary_post(weight, pre_trace, post_spike, w_min=None, w_max=None):
+    """_dense/plasticity_binary.py:462-482."""
+    w = np.array(weight, copy=True)
+    w[:, active_mask(post_spike, True).astype(bool)] += np.asarray(pre_trace, w.dtype)[:, None]
+    return _clip(w, w_min, w_max)

@@ -309,3 +309,40 @@ def jitn_to_csr(w_loc, w_scale, prob, seed, *, shape, corder, matrix_mode, dtype
 
 def jitu_to_csr(w_low, w_high, prob, seed, *, shape, corder, matrix_mode, dtype=np.float32):
     return _jit_to_csr("_jit_uniform.csr", "u", [w_low, w_high], prob, seed, shape, corder, matrix_mode, dtype)
+
+
+# -- plasticity: the numba kernels add into an aliased copy of the weights; the shim hands them a
+#    zero buffer, so updated = weight + returned delta (the update is purely additive) -----------------
+def update_csr_on_binary_pre(weight, indices, indptr, pre_spike, post_trace, *, shape):
+    m = R.ref_module("_csr.plasticity_binary")
+    spk = _spk(pre_spike)
+    k = m._csr_on_pre_numba_kernel_generator(spike_info=SDS(spk.shape, spk.dtype), outs=[SDS(weight.shape, weight.dtype)])
+    return weight + _first(k(weight, indices, indptr, spk, post_trace))
+
+
+def update_csr_on_binary_post(weight, indices, indptr, weight_indices, pre_trace, post_spike, *, shape):
+    m = R.ref_module("_csr.plasticity_binary")
+    spk = _spk(post_spike)
+    k = m._csr2csc_on_post_numba_kernel_generator(spike_info=SDS(spk.shape, spk.dtype), outs=[SDS(weight.shape, weight.dtype)])
+    return weight + _first(k(weight, indices, indptr, weight_indices, pre_trace, spk))
+
+
+def fcn_plasticity_row(data, indices, spike, trace):
+    m = R.ref_module("_fcn.plasticity_binary")
+    spk = _spk(spike)
+    k = m._fcn_plasticity_row_numba_kernel(spike_info=SDS(spk.shape, spk.dtype), outs=[SDS(data.shape, data.dtype)])
+    return data + _first(k(data, indices, spk, trace))
+
+
+def update_dense_on_binary_pre(weight, pre_spike, post_trace):
+    m = R.ref_module("_dense.plasticity_binary")
+    spk = _spk(pre_spike)
+    k = m._dense_on_pre_numba_kernel(spike_info=SDS(spk.shape, spk.dtype), outs=[SDS(weight.shape, weight.dtype)])
+    return weight + _first(k(weight, spk, post_trace))
+
+
+def update_dense_on_binary_post(weight, pre_trace, post_spike):
+    m = R.ref_module("_dense.plasticity_binary")
+    spk = _spk(post_spike)
+    k = m._dense_on_post_numba_kernel(spike_info=SDS(spk.shape, spk.dtype), outs=[SDS(weight.shape, weight.dtype)])
+    return weight + _first(k(weight, pre_trace, spk))

@@ -140,6 +140,8 @@ def golden_float_ops():
     for tag, fn, _ in golden_cases.to_csr_cases():
         data, indices, indptr = fn(RK)
         out[tag + "_data"], out[tag + "_indices"], out[tag + "_indptr"] = data, indices, indptr
+    for tag, fn in golden_cases.plasticity_cases():
+        out[tag] = fn(RK)
     save("float_ops", **out)
 
 

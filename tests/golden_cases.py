@@ -109,3 +109,28 @@ def to_csr_cases():
                 yield (f"tocsr_{fam}_c{int(co)}_{mode}", (lambda api, fam=fam, params=params, co=co, mode=mode: getattr(
                     api, f"jit{fam}_to_csr")(*params, prob, seed, shape=shape, corder=co, matrix_mode=mode)),
                     3e-4 if fam == "n" else 1e-6)
+
+
+def plasticity_cases():
+    """(tag, fn(api) -> ndarray): spike-triggered weight updates without clipping (the reference
+    kernels do not clip; clipping is a separate whole-array pass)."""
+    rng = np.random.default_rng(30)
+    c = cases.csr_case(31, 300, 200, 9, 0.1, homo=False, ragged=True)
+    m, k = c["shape"]
+    tr_pre, tr_post = rng.standard_normal(m).astype(np.float32), rng.standard_normal(k).astype(np.float32)
+    from oracle import csr_to_csc_index
+    cp, ci, perm = csr_to_csc_index(c["indptr"], c["indices"], shape=c["shape"])
+    f = cases.fcn_case(32, 250, 180, 11)
+    tr_f = rng.standard_normal(180).astype(np.float32)
+    W = rng.standard_normal((90, 130)).astype(np.float32)
+    for fs in (False, True):
+        pre, post = cases.spikes(33, m, 0.2, fs), cases.spikes(34, k, 0.2, fs)
+        yield (f"plast_csr_pre_f{int(fs)}", lambda api, pre=pre: api.update_csr_on_binary_pre(
+            c["data"], c["indices"], c["indptr"], pre, tr_post, shape=c["shape"]))
+        yield (f"plast_csr_post_f{int(fs)}", lambda api, post=post: api.update_csr_on_binary_post(
+            c["data"], ci, cp, perm, tr_pre, post, shape=c["shape"]))
+        spk = cases.spikes(35, 250, 0.2, fs)
+        yield (f"plast_fcn_f{int(fs)}", lambda api, spk=spk: api.fcn_plasticity_row(f["weights"], f["indices"], spk, tr_f))
+        sp, so = cases.spikes(36, 90, 0.2, fs), cases.spikes(37, 130, 0.2, fs)
+        yield (f"plast_dense_pre_f{int(fs)}", lambda api, sp=sp: api.update_dense_on_binary_pre(W, sp, tr_post[:130]))
+        yield (f"plast_dense_post_f{int(fs)}", lambda api, so=so: api.update_dense_on_binary_post(W, tr_pre[:90], so))

@@ -171,3 +171,29 @@ def jitn_to_csr(loc, scale, prob, seed, *, shape, corder, matrix_mode, dtype=np.
 
 def jitu_to_csr(lo, hi, prob, seed, *, shape, corder, matrix_mode, dtype=np.float32):
     return _to_csr(be.jitu_to_csr, [lo, hi], prob, seed, shape, corder, matrix_mode, dtype)
+
+
+# ---- plasticity -----------------------------------------------------------------------------------
+def update_csr_on_binary_pre(weight, indices, indptr, pre_spike, post_trace, w_min=None, w_max=None, *, shape):
+    return _np(be.update_csr_on_binary_pre(_t(weight), _t(indices), _t(indptr), _t(pre_spike), _t(post_trace), w_min,
+                                           w_max, shape=shape))
+
+
+def update_csr_on_binary_post(weight, indices, indptr, weight_indices, pre_trace, post_spike, w_min=None, w_max=None,
+                              *, shape):
+    return _np(be.update_csr_on_binary_post(_t(weight), _t(indices), _t(indptr), _t(weight_indices), _t(pre_trace),
+                                            _t(post_spike), w_min, w_max, shape=shape))
+
+
+def fcn_plasticity_row(data, indices, spike, trace, w_min=None, w_max=None):
+    n_rows = indices.shape[0]
+    return _np(be.update_fixed_post_conn_on_binary_pre(_t(data), _t(indices), _t(spike), _t(trace), w_min, w_max,
+                                                       shape=(n_rows, trace.shape[0])))
+
+
+def update_dense_on_binary_pre(weight, pre_spike, post_trace, w_min=None, w_max=None):
+    return _np(be.update_dense_on_binary_pre(_t(weight), _t(pre_spike), _t(post_trace), w_min, w_max))
+
+
+def update_dense_on_binary_post(weight, pre_trace, post_spike, w_min=None, w_max=None):
+    return _np(be.update_dense_on_binary_post(_t(weight), _t(pre_trace), _t(post_spike), w_min, w_max))

@@ -141,3 +141,8 @@ def test_jitc_to_csr_fixture():
         np.testing.assert_array_equal(indptr, g[tag + "_indptr"])
         np.testing.assert_array_equal(indices, g[tag + "_indices"])
         np.testing.assert_allclose(data, g[tag + "_data"], rtol=1e-6, atol=atol)
+
+
+@pytest.mark.parametrize("tag,fn", list(golden_cases.plasticity_cases()), ids=lambda x: x if isinstance(x, str) else "")
+def test_plasticity_fixture(tag, fn):
+    np.testing.assert_allclose(fn(O), golden_cases.load("float_ops")[tag], rtol=1e-6, atol=1e-6)

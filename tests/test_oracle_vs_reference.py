@@ -229,3 +229,27 @@ def test_jitc_to_csr(RK, fam, params, corder, mode):
         x = np.random.default_rng(5).standard_normal(shape[1]).astype(np.float32)
         y = getattr(O, f"jit{fam}mv")(*params, prob, x, seed, shape=shape, transpose=False, corder=corder)
         np.testing.assert_allclose(O.csrmv(b[0], b[1], b[2], x, shape=shape), y, rtol=1e-4, atol=1e-4)
+
+
+# ---- plasticity: SURVEY 8(f)-4 ------------------------------------------------------------------------
+@pytest.mark.parametrize("float_spikes", [False, True])
+def test_plasticity(RK, float_spikes):
+    rng = np.random.default_rng(90)
+    c = cases.csr_case(91, 300, 200, 9, 0.1, homo=False, ragged=True)
+    m, k = c["shape"]
+    pre, post = cases.spikes(92, m, 0.2, float_spikes), cases.spikes(93, k, 0.2, float_spikes)
+    tr_pre, tr_post = rng.standard_normal(m).astype(np.float32), rng.standard_normal(k).astype(np.float32)
+    np.testing.assert_allclose(O.update_csr_on_binary_pre(c["data"], c["indices"], c["indptr"], pre, tr_post, shape=c["shape"]),
+                               RK.update_csr_on_binary_pre(c["data"], c["indices"], c["indptr"], pre, tr_post, shape=c["shape"]), rtol=1e-6, atol=1e-6)
+    cp, ci, perm = O.csr_to_csc_index(c["indptr"], c["indices"], shape=c["shape"])
+    np.testing.assert_allclose(O.update_csr_on_binary_post(c["data"], ci, cp, perm, tr_pre, post, shape=c["shape"]),
+                               RK.update_csr_on_binary_post(c["data"], ci, cp, perm, tr_pre, post, shape=c["shape"]), rtol=1e-6, atol=1e-6)
+    f = cases.fcn_case(94, 250, 180, 11)
+    spk = cases.spikes(95, 250, 0.2, float_spikes)
+    tr = rng.standard_normal(180).astype(np.float32)
+    np.testing.assert_allclose(O.fcn_plasticity_row(f["weights"], f["indices"], spk, tr),
+                               RK.fcn_plasticity_row(f["weights"], f["indices"], spk, tr), rtol=1e-6, atol=1e-6)
+    W = rng.standard_normal((90, 130)).astype(np.float32)
+    sp, so = cases.spikes(96, 90, 0.2, float_spikes), cases.spikes(97, 130, 0.2, float_spikes)
+    np.testing.assert_allclose(O.update_dense_on_binary_pre(W, sp, tr_post[:130]), RK.update_dense_on_binary_pre(W, sp, tr_post[:130]), rtol=1e-6, atol=1e-6)
+    np.testing.assert_allclose(O.update_dense_on_binary_post(W, tr_pre[:90], so), RK.update_dense_on_binary_post(W, tr_pre[:90], so), rtol=1e-6, atol=1e-6)
