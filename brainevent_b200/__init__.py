@@ -23,6 +23,10 @@ from ._jitc import (JITCMatrix, JITCNormalC, JITCNormalR, JITCScalarC, JITCScala
                     binary_jitsmm, binary_jitsmm_p, binary_jitsmv, binary_jitsmv_p, binary_jitumm,
                     binary_jitumm_p, binary_jitumv, binary_jitumv_p, jitc_row_connections, jitn_to_csr,
                     jits_to_csr, jitu_to_csr)
+from ._encode import (binary_2d_csc_encode_p, binary_2d_csc_encode_p_call, binary_2d_csr_encode_p,
+                      binary_2d_csr_encode_p_call, binary_2d_csr_fill_p_call, binary_2d_csr_row_count_p_call,
+                      binary_2d_pair_stream_encode_p, binary_2d_pair_stream_encode_p_call,
+                      binary_2d_row_sparse_encode_p, binary_2d_row_sparse_encode_p_call)
 from ._plasticity import (update_csc_on_binary_post, update_csc_on_binary_pre, update_csr_on_binary_post,
                           update_csr_on_binary_pre, update_dense_on_binary_post, update_dense_on_binary_pre,
                           update_fixed_post_conn_on_binary_pre, update_fixed_pre_conn_on_binary_post)

@@ -68,6 +68,10 @@ _SIGNATURES = {
     "be_b200_jitc_csr_workspace_bytes": (_Z, [_L, _L]),
     "be_b200_jitc_csr_count": (_I, [_P, _P, _L, _L, _L, _I, _I, _P, _P, _Z, _P]),
     "be_b200_jitc_csr_fill": (_I, [_I, _P, _P, _I, _P, _P, _L, _L, _L, _I, _I, _P, _L, _P, _P, _P, _Z, _P]),
+    "be_b200_binary_2d_pair_stream_encode": (_I, [_P, _I, _L, _L, _P, _P, _P, _Z, _P]),
+    "be_b200_binary_2d_csr_encode": (_I, [_P, _I, _L, _L, _P, _P, _P, _Z, _P]),
+    "be_b200_binary_2d_csc_encode": (_I, [_P, _I, _L, _L, _P, _P, _P, _P, _Z, _P]),
+    "be_b200_binary_2d_row_sparse_encode": (_I, [_P, _I, _L, _L, _L, _P, _P, _P]),
     "be_b200_plasticity_rows": (_I, [_P, _I, _P, _P, _I, _L, _P, _I, _P, _P, _I, _P, _L, _L, _L, _D, _D, _P, _Z, _P]),
     "be_b200_plasticity_dense": (_I, [_P, _I, _L, _L, _P, _P, _I, _P, _I, _D, _D, _P, _Z, _P]),
     "be_b200_clip": (_I, [_P, _I, _L, _D, _D, _P]),

@@ -216,6 +216,32 @@ int be_b200_jitc_csr_fill(int kind, const void* p0, const void* p1, int w_dtype,
                           int32_t* indices, void* data, void* workspace, size_t workspace_bytes,
                           void* stream);
 
+/* ---- dense 2-D spike matrix -> sparse event layouts (ref: _event/compact.py
+ *      binary_2d_pair_stream_encode :706, binary_2d_row_sparse_encode :875, binary_2d_csr_encode :1180,
+ *      binary_2d_csc_encode :1265 and _event/compact.cu).  spikes [n_src, n_batch] row-major, kind
+ *      BOOL or F32 (active when != 0); n_src * n_batch < 2^31.  Outputs have the reference's static
+ *      capacity and zero-filled tails; order is row-major (column-major for CSC) like the numba
+ *      kernels.  workspace: be_b200_workspace_bytes(n_src * n_batch, 1), zero on first use.
+ *        pair_stream int32 [n_src*n_batch, 2] (row, col), n_pairs int32[1]
+ *        csr: indices int32 [n_src*n_batch] (batch column ids), indptr int32 [n_src + 1]
+ *        csc: indices int32 [n_src*n_batch] (source row ids), indptr int32 [n_batch + 1];
+ *             scratch = n_src*n_batch bytes
+ *        row_sparse: spike_indices int32 [n_src, row_size] of 1-based column ids, zero padded;
+ *             max_row_nnz int32[1] receives the largest row count (the host raises if > row_size,
+ *             as the reference validates before launching) --------------------------------------- */
+int be_b200_binary_2d_pair_stream_encode(const void* spikes, int spk_kind, int64_t n_src, int64_t n_batch,
+                                         int32_t* pair_stream, int32_t* n_pairs, void* workspace,
+                                         size_t workspace_bytes, void* stream);
+int be_b200_binary_2d_csr_encode(const void* spikes, int spk_kind, int64_t n_src, int64_t n_batch,
+                                 int32_t* indices, int32_t* indptr, void* workspace,
+                                 size_t workspace_bytes, void* stream);
+int be_b200_binary_2d_csc_encode(const void* spikes, int spk_kind, int64_t n_src, int64_t n_batch,
+                                 int32_t* indices, int32_t* indptr, void* scratch, void* workspace,
+                                 size_t workspace_bytes, void* stream);
+int be_b200_binary_2d_row_sparse_encode(const void* spikes, int spk_kind, int64_t n_src, int64_t n_batch,
+                                        int64_t row_size, int32_t* spike_indices, int32_t* max_row_nnz,
+                                        void* stream);
+
 /* ---- spike-triggered additive plasticity.  In place on `weights`:
  *      for every ACTIVE row r and stored slot j of r:
  *          w[slot(j)] = clamp(w[slot(j)] + trace[indices[j]], w_min, w_max),  slot(j) = perm ? perm[j] : j

@@ -615,3 +615,47 @@ def update_dense_on_binary_post(weight, pre_trace, post_spike, w_min=None, w_max
     w = np.array(weight, copy=True)
     w[:, active_mask(post_spike, True).astype(bool)] += np.asarray(pre_trace, w.dtype)[:, None]
     return _clip(w, w_min, w_max)
+
+
+# ----------------------------------------------------------------------------------------------
+# dense 2-D spikes -> sparse event layouts -- SURVEY 8(f)-3 (plain numpy restatements)
+# ----------------------------------------------------------------------------------------------
+def binary_2d_pair_stream_encode(spikes):
+    """_event/compact.py:634-670 -> (pair_stream int32 [n*b, 2], n_pairs int32 [1]); row-major order."""
+    act = active_mask(spikes, True).astype(bool)
+    r, c = np.nonzero(act)
+    out = np.zeros((act.size, 2), np.int32)
+    out[:r.size, 0], out[:r.size, 1] = r, c
+    return out, np.asarray([r.size], np.int32)
+
+
+def binary_2d_row_sparse_encode(spikes, row_size):
+    """_event/compact.py:792-826 -> int32 [n_src, row_size], 1-based column ids, zero padded."""
+    act = active_mask(spikes, True).astype(bool)
+    out = np.zeros((act.shape[0], row_size), np.int32)
+    for r in range(act.shape[0]):
+        cols = np.nonzero(act[r])[0]
+        out[r, :cols.size] = cols + 1
+    return out
+
+
+def binary_2d_csr_encode(spikes):
+    """_event/compact.py:962-1217 -> (indices int32 [n*b] zero-filled tail, indptr int32 [n_src+1])."""
+    act = active_mask(spikes, True).astype(bool)
+    r, c = np.nonzero(act)
+    indices = np.zeros(act.size, np.int32)
+    indices[:c.size] = c
+    indptr = np.zeros(act.shape[0] + 1, np.int32)
+    np.cumsum(act.sum(axis=1), out=indptr[1:])
+    return indices, indptr
+
+
+def binary_2d_csc_encode(spikes):
+    """_event/compact.py:1220-1262 -> (row ids int32 [n*b] zero-filled tail, indptr int32 [n_batch+1])."""
+    act = active_mask(spikes, True).astype(bool)
+    c, r = np.nonzero(act.T)
+    indices = np.zeros(act.size, np.int32)
+    indices[:r.size] = r
+    indptr = np.zeros(act.shape[1] + 1, np.int32)
+    np.cumsum(act.sum(axis=0), out=indptr[1:])
+    return indices, indptr

@@ -346,3 +346,33 @@ def update_dense_on_binary_post(weight, pre_trace, post_spike):
     spk = _spk(post_spike)
     k = m._dense_on_post_numba_kernel(spike_info=SDS(spk.shape, spk.dtype), outs=[SDS(weight.shape, weight.dtype)])
     return weight + _first(k(weight, pre_trace, spk))
+
+
+# -- 2-D spike encoders ----------------------------------------------------------------------------------
+def binary_2d_pair_stream_encode(spikes):
+    m = R.ref_module("_event.compact")
+    s = _spk(spikes)
+    n = s.size
+    k = m._binary_2d_pair_stream_encode_numba_kernel(spikes_info=SDS(s.shape, s.dtype),
+                                                     outs=[SDS((n, 2), np.int32), SDS((1,), np.int32)])
+    o = k(s)
+    return o[0], o[1]
+
+
+def binary_2d_row_sparse_encode(spikes, row_size):
+    m = R.ref_module("_event.compact")
+    s = _spk(spikes)
+    k = m._binary_2d_row_sparse_encode_numba_kernel(spikes_info=SDS(s.shape, s.dtype), row_size=row_size,
+                                                    outs=[SDS((s.shape[0], row_size), np.int32)])
+    return _first(k(s))
+
+
+def binary_2d_csr_encode(spikes):
+    m = R.ref_module("_event.compact")
+    s = _spk(spikes)
+    counts = _first(m._binary_2d_csr_row_count_numba_kernel(spikes_info=SDS(s.shape, s.dtype),
+                                                            outs=[SDS((s.shape[0],), np.int32)])(s))
+    indptr = np.concatenate([[0], np.cumsum(counts)]).astype(np.int32)
+    indices = _first(m._binary_2d_csr_fill_numba_kernel(spikes_info=SDS(s.shape, s.dtype), indptr_info=SDS(indptr.shape, indptr.dtype),
+                                                        outs=[SDS((s.size,), np.int32)])(s, indptr))
+    return indices, indptr

@@ -142,6 +142,9 @@ def golden_float_ops():
         out[tag + "_data"], out[tag + "_indices"], out[tag + "_indptr"] = data, indices, indptr
     for tag, fn in golden_cases.plasticity_cases():
         out[tag] = fn(RK)
+    for tag, fn in golden_cases.encoder_cases():
+        for i, arr in enumerate(fn(RK)):
+            out[f"{tag}_{i}"] = arr
     save("float_ops", **out)
 
 

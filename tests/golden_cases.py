@@ -134,3 +134,12 @@ def plasticity_cases():
         sp, so = cases.spikes(36, 90, 0.2, fs), cases.spikes(37, 130, 0.2, fs)
         yield (f"plast_dense_pre_f{int(fs)}", lambda api, sp=sp: api.update_dense_on_binary_pre(W, sp, tr_post[:130]))
         yield (f"plast_dense_post_f{int(fs)}", lambda api, so=so: api.update_dense_on_binary_post(W, tr_pre[:90], so))
+
+
+def encoder_cases():
+    """(tag, fn(api) -> tuple of ndarrays): dense 2-D spikes -> sparse layouts."""
+    for fs in (False, True):
+        spk = cases.spikes(40, 300, 0.05, fs, batch=70)
+        yield (f"enc_pair_f{int(fs)}", lambda api, spk=spk: tuple(api.binary_2d_pair_stream_encode(spk)))
+        yield (f"enc_rowsparse_f{int(fs)}", lambda api, spk=spk: (api.binary_2d_row_sparse_encode(spk, 40),))
+        yield (f"enc_csr_f{int(fs)}", lambda api, spk=spk: tuple(api.binary_2d_csr_encode(spk)))

@@ -197,3 +197,23 @@ def update_dense_on_binary_pre(weight, pre_spike, post_trace, w_min=None, w_max=
 
 def update_dense_on_binary_post(weight, pre_trace, post_spike, w_min=None, w_max=None):
     return _np(be.update_dense_on_binary_post(_t(weight), _t(pre_trace), _t(post_spike), w_min, w_max))
+
+
+# ---- 2-D spike encoders ------------------------------------------------------------------------------
+def binary_2d_pair_stream_encode(spikes):
+    p, n = be.binary_2d_pair_stream_encode_p_call(_t(spikes))
+    return _np(p), _np(n)
+
+
+def binary_2d_row_sparse_encode(spikes, row_size):
+    return _np(be.binary_2d_row_sparse_encode_p_call(_t(spikes), row_size=row_size)[0])
+
+
+def binary_2d_csr_encode(spikes):
+    i, p = be.binary_2d_csr_encode_p_call(_t(spikes))
+    return _np(i), _np(p)
+
+
+def binary_2d_csc_encode(spikes):
+    i, p = be.binary_2d_csc_encode_p_call(_t(spikes))
+    return _np(i), _np(p)

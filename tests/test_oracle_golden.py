@@ -146,3 +146,10 @@ def test_jitc_to_csr_fixture():
 @pytest.mark.parametrize("tag,fn", list(golden_cases.plasticity_cases()), ids=lambda x: x if isinstance(x, str) else "")
 def test_plasticity_fixture(tag, fn):
     np.testing.assert_allclose(fn(O), golden_cases.load("float_ops")[tag], rtol=1e-6, atol=1e-6)
+
+
+@pytest.mark.parametrize("tag,fn", list(golden_cases.encoder_cases()), ids=lambda x: x if isinstance(x, str) else "")
+def test_encoder_fixture(tag, fn):
+    g = golden_cases.load("float_ops")
+    for i, arr in enumerate(fn(O)):
+        np.testing.assert_array_equal(arr, g[f"{tag}_{i}"])

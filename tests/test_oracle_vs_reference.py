@@ -253,3 +253,20 @@ def test_plasticity(RK, float_spikes):
     sp, so = cases.spikes(96, 90, 0.2, float_spikes), cases.spikes(97, 130, 0.2, float_spikes)
     np.testing.assert_allclose(O.update_dense_on_binary_pre(W, sp, tr_post[:130]), RK.update_dense_on_binary_pre(W, sp, tr_post[:130]), rtol=1e-6, atol=1e-6)
     np.testing.assert_allclose(O.update_dense_on_binary_post(W, tr_pre[:90], so), RK.update_dense_on_binary_post(W, tr_pre[:90], so), rtol=1e-6, atol=1e-6)
+
+
+# ---- 2-D spike encoders: SURVEY 8(f)-3 -------------------------------------------------------------------
+@pytest.mark.parametrize("float_spikes", [False, True])
+def test_encoders(RK, float_spikes):
+    spk = cases.spikes(120, 300, 0.05, float_spikes, batch=70)
+    a, b = O.binary_2d_pair_stream_encode(spk), RK.binary_2d_pair_stream_encode(spk)
+    np.testing.assert_array_equal(a[0], b[0]); np.testing.assert_array_equal(a[1], b[1])
+    np.testing.assert_array_equal(O.binary_2d_row_sparse_encode(spk, 40), RK.binary_2d_row_sparse_encode(spk, 40))
+    a, b = O.binary_2d_csr_encode(spk), RK.binary_2d_csr_encode(spk)
+    np.testing.assert_array_equal(a[0], b[0]); np.testing.assert_array_equal(a[1], b[1])
+    # the CSC encoder is a jnp formula in the reference (_event/compact.py:1220-1262): check by definition
+    idx, ptr_ = O.binary_2d_csc_encode(spk)
+    act = spk != 0
+    for col in (0, 13, 69):
+        np.testing.assert_array_equal(idx[ptr_[col]:ptr_[col + 1]], np.nonzero(act[:, col])[0])
+    assert ptr_[-1] == act.sum() and not idx[ptr_[-1]:].any()
