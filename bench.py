@@ -581,7 +581,7 @@ def main():
         host_spk = [torch.empty(n_in, dtype=torch.uint8).pin_memory() for _ in range(POOL)]
         for i in range(POOL):
             host_spk[i].copy_(wl.pool[i].to(torch.uint8))
-        host_out = [torch.empty(n_out, dtype=torch.float32).pin_memory() for _ in range(2)]
+        host_out = [torch.empty(n_out, dtype=torch.float32).pin_memory() for _ in range(4)]
         Te = min(T, 50)
         sync_value = None
         if world == 1:
@@ -603,7 +603,7 @@ def main():
                 # every timestep still moves its own inputs in and its own result out
                 for t in range(Te):
                     rc = lib.be_b200_projection_submit_host(proj, ctypes.c_void_p(host_spk[t % POOL].data_ptr()),
-                                                            ctypes.c_void_p(host_out[t & 1].data_ptr()))
+                                                            ctypes.c_void_p(host_out[t % 4].data_ptr()))
                     assert rc == 0
                 assert lib.be_b200_projection_wait(proj) == 0
 
@@ -642,7 +642,7 @@ def main():
                "note": f"per timestep: pinned host spikes (uint8[{n_in}]) -> device, hot path, fp32[{n_out}] result -> "
                        f"pinned host, stream sync; timed over {Ke}x{Te} timesteps with the host clock, bytes scaled to "
                        f"{T} timesteps/step; entry point: " +
-                       ("be_b200_projection_submit_host/_wait (C ABI, 2 calls in flight; `sync_value` is the "
+                       ("be_b200_projection_submit_host/_wait (C ABI, 4 calls in flight; `sync_value` is the "
                         "blocking be_b200_projection_apply_host)" if world == 1 else
                         "PostShardedProjection.step (per rank: its own spike block in, its own output block out)")}
         if sync_value is not None:

@@ -22,14 +22,17 @@ struct be_b200_projection {
     size_t ws_bytes;
     cudaStream_t stream;
     int borrowed;  // connectivity pointers belong to the caller
-    // pipelined submit/wait: two slots of device-side event/output buffers, copy streams either
-    // side of the compute stream so PCIe transfers of neighbouring calls overlap the kernels
-    uint8_t* d_ev2[2];
-    float* d_out2[2];
+    // pipelined submit/wait: kSlots sets of device-side event/output buffers, copy streams either
+    // side of the compute stream so PCIe transfers of neighbouring calls overlap the kernels.
+    // One slot's cycle is H2D + kernels + D2H; four slots keep the D2H engine (the bound for a
+    // 4-byte-per-post result) busy back to back.
+    uint8_t* d_ev2[4];
+    float* d_out2[4];
     cudaStream_t s_in, s_out;
-    cudaEvent_t ev_in[2], ev_done[2], ev_out[2];
-    int slot, inflight[2];
+    cudaEvent_t ev_in[4], ev_done[4], ev_out[4];
+    int slot, inflight[4];
 };
+constexpr int kSlots = 4;
 
 using namespace be;
 
@@ -45,7 +48,7 @@ static be_b200_projection* proj_new(int kind, int64_t n_pre, int64_t n_post) {
     ok = ok && cudaMalloc((void**)&p->d_out, (size_t)std::max<int64_t>(n_post, 4) * sizeof(float)) == cudaSuccess;
     ok = ok && cudaStreamCreateWithFlags(&p->s_in, cudaStreamNonBlocking) == cudaSuccess;
     ok = ok && cudaStreamCreateWithFlags(&p->s_out, cudaStreamNonBlocking) == cudaSuccess;
-    for (int i = 0; i < 2 && ok; ++i) {
+    for (int i = 0; i < kSlots && ok; ++i) {
         ok = ok && cudaMalloc((void**)&p->d_ev2[i], (size_t)std::max<int64_t>(n_pre, 16)) == cudaSuccess;
         ok = ok && cudaMalloc((void**)&p->d_out2[i], (size_t)std::max<int64_t>(n_post, 4) * sizeof(float)) == cudaSuccess;
         ok = ok && cudaEventCreateWithFlags(&p->ev_in[i], cudaEventDisableTiming) == cudaSuccess;
@@ -136,8 +139,8 @@ static int proj_compute(be_b200_projection* p, const uint8_t* d_events, float* d
 }
 
 // Asynchronous variant: returns once the call is enqueued.  Host buffers must be pinned and stay
-// untouched until be_b200_projection_wait() (or the second-next submit) returns; at most two
-// calls are in flight, the third submit first waits for the oldest one.
+// untouched until be_b200_projection_wait() (or the kSlots-th next submit) returns; at most
+// kSlots = 4 calls are in flight, the next submit first waits for the oldest one.
 extern "C" int be_b200_projection_submit_host(be_b200_projection* p, const uint8_t* events_host,
                                               float* out_host) {
     BE_REQUIRE(p && events_host && out_host, "projection_submit_host: NULL pointer");
@@ -153,14 +156,14 @@ extern "C" int be_b200_projection_submit_host(be_b200_projection* p, const uint8
     if (p->n_post > 0) BE_CUDA(cudaMemcpyAsync(out_host, p->d_out2[i], (size_t)p->n_post * sizeof(float), cudaMemcpyDeviceToHost, p->s_out));
     BE_CUDA(cudaEventRecord(p->ev_out[i], p->s_out));
     p->inflight[i] = 1;
-    p->slot ^= 1;
+    p->slot = (p->slot + 1) % kSlots;
     return BE_B200_OK;
 }
 
 // Blocks until every submitted call has delivered its result to host memory.
 extern "C" int be_b200_projection_wait(be_b200_projection* p) {
     BE_REQUIRE(p, "projection_wait: NULL pointer");
-    for (int i = 0; i < 2; ++i)
+    for (int i = 0; i < kSlots; ++i)
         if (p->inflight[i]) { BE_CUDA(cudaEventSynchronize(p->ev_out[i])); p->inflight[i] = 0; }
     return BE_B200_OK;
 }
@@ -182,7 +185,7 @@ extern "C" void be_b200_projection_destroy(be_b200_projection* p) {
     if (!p->borrowed) { cudaFree(p->d_weights); cudaFree(p->d_indices); cudaFree(p->d_indptr); }
     cudaFree(p->d_p);
     cudaFree(p->d_clen_seed); cudaFree(p->d_events); cudaFree(p->d_out); cudaFree(p->d_ws);
-    for (int i = 0; i < 2; ++i) {
+    for (int i = 0; i < kSlots; ++i) {
         cudaFree(p->d_ev2[i]); cudaFree(p->d_out2[i]);
         if (p->ev_in[i]) cudaEventDestroy(p->ev_in[i]);
         if (p->ev_done[i]) cudaEventDestroy(p->ev_done[i]);

@@ -328,8 +328,8 @@ be_b200_projection* be_b200_projection_create_jitc(int jit_kind, float p0, float
 int be_b200_projection_apply_host(be_b200_projection* p, const uint8_t* events_host,
                                   float* out_host);
 /* Pipelined form of apply_host: submit() enqueues copy-in, the hot path and copy-out on three
- * streams and returns; at most two calls are in flight (the third submit first waits for the
- * oldest).  Host buffers must be pinned and stay untouched until wait() (or the second-next
+ * streams and returns; at most four calls are in flight (the fifth submit first waits for the
+ * oldest).  Host buffers must be pinned and stay untouched until wait() (or the fourth-next
  * submit) returns.  PCIe transfers of neighbouring timesteps then overlap the kernels. */
 int be_b200_projection_submit_host(be_b200_projection* p, const uint8_t* events_host, float* out_host);
 int be_b200_projection_wait(be_b200_projection* p);
