@@ -2,6 +2,8 @@
 #include "common.cuh"
 #include "../../include/brainevent_b200_xla.h"
 
+#include <algorithm>
+#include <cmath>
 #include <cstring>
 #include <string>
 
@@ -50,6 +52,33 @@ struct Frame {
             }
         }
         return false;
+    }
+    bool attr_f64(const char* name, double* out) const {
+        for (int64_t i = 0; i < f->attrs.size; ++i) {
+            XLA_FFI_ByteSpan* n = f->attrs.names[i];
+            if (n->len == strlen(name) && memcmp(n->ptr, name, n->len) == 0 && f->attrs.types[i] == 3) {
+                XLA_FFI_Scalar* s = (XLA_FFI_Scalar*)f->attrs.attrs[i];
+                if (s->dtype == BE_XLA_F32) { *out = *(float*)s->value; return true; }
+                if (s->dtype == BE_XLA_F64) { *out = *(double*)s->value; return true; }
+                int64_t v;
+                if (attr_i64(name, &v)) { *out = (double)v; return true; }
+                return false;
+            }
+        }
+        return false;
+    }
+    XLA_FFI_Error* alloc_bytes(size_t bytes, void** out) {     // extra device scratch (freed by the caller)
+        XLA_FFI_DeviceMemory_Allocate_Args a;
+        a.struct_size = sizeof(a); a.extension_start = nullptr; a.ctx = f->ctx;
+        a.size = bytes; a.alignment = 256; a.data = nullptr;
+        XLA_FFI_Error* e = f->api->XLA_FFI_DeviceMemory_Allocate(&a);
+        *out = a.data;
+        return e;
+    }
+    void free_bytes(size_t bytes, void* p) {
+        XLA_FFI_DeviceMemory_Free_Args a;
+        a.struct_size = sizeof(a); a.extension_start = nullptr; a.ctx = f->ctx; a.size = bytes; a.data = p;
+        f->api->XLA_FFI_DeviceMemory_Free(&a);
     }
     XLA_FFI_Error* get_stream() {
         XLA_FFI_Stream_Get_Args a;
@@ -228,6 +257,72 @@ XLA_FFI_Error* dense_common(XLA_FFI_CallFrame* frame, bool matmat, const char* n
     return fr.finish(rc, name);
 }
 
+// ---- float (non-event) products: SURVEY 8(f)-1 -------------------------------------------------------
+XLA_FFI_Error* csr_val_common(XLA_FFI_CallFrame* frame, bool matmat, const char* name) {
+    BE_XLA_PROLOGUE(4, 1, "csr");
+    XLA_FFI_Buffer *w = fr.arg(0), *idx = fr.arg(1), *ptr = fr.arg(2), *x = fr.arg(3), *out = fr.ret(0);
+    int64_t transpose = 0;
+    fr.attr_i64("transpose", &transpose);
+    const int wt = wt_of(w->dtype);
+    if (wt < 0 || x->dtype != w->dtype) return fr.fail(BE_B200_EUNIMPL, std::string(name) + ": operand and weights must share a float dtype");
+    if (idx->dtype != BE_XLA_S32) return fr.fail(BE_B200_EINVAL, std::string(name) + ": indices must be int32");
+    const int64_t m = ptr->dims[0] - 1, nse = numel(idx);
+    const int64_t k = transpose ? out->dims[0] : x->dims[0];
+    int rc;
+    if (matmat)
+        rc = be_b200_csrmm(w->data, wt, numel(w) == 1, (const int32_t*)idx->data, ptr->data, ptr->dtype == BE_XLA_S64, x->data,
+                           m, k, nse, x->dims[1], (int)transpose, out->data, fr.stream);
+    else
+        rc = be_b200_csrmv(w->data, wt, numel(w) == 1, (const int32_t*)idx->data, ptr->data, ptr->dtype == BE_XLA_S64, x->data,
+                           m, k, nse, (int)transpose, out->data, fr.stream);
+    return fr.finish(rc, name);
+}
+
+XLA_FFI_Error* fcn_val_common(XLA_FFI_CallFrame* frame, bool matmat, const char* name) {
+    BE_XLA_PROLOGUE(3, 1, "fcn");
+    XLA_FFI_Buffer *w = fr.arg(0), *idx = fr.arg(1), *x = fr.arg(2), *out = fr.ret(0);
+    int64_t transpose = 0;
+    fr.attr_i64("transpose", &transpose);
+    const int wt = wt_of(w->dtype);
+    if (wt < 0 || x->dtype != w->dtype) return fr.fail(BE_B200_EUNIMPL, std::string(name) + ": operand and weights must share a float dtype");
+    if (idx->dtype != BE_XLA_S32 || idx->rank != 2) return fr.fail(BE_B200_EINVAL, std::string(name) + ": indices must be int32 [n_rows, n_conn]");
+    const int64_t n_rows = idx->dims[0], n_conn = idx->dims[1];
+    const int64_t n_other = transpose ? out->dims[0] : x->dims[0];
+    int rc;
+    if (matmat)
+        rc = be_b200_fcnmm(w->data, wt, numel(w) == 1, (const int32_t*)idx->data, n_rows, n_conn, x->data, n_other, x->dims[1],
+                           (int)transpose, out->data, fr.stream);
+    else
+        rc = be_b200_fcnmv(w->data, wt, numel(w) == 1, (const int32_t*)idx->data, n_rows, n_conn, x->data, n_other,
+                           (int)transpose, out->data, fr.stream);
+    return fr.finish(rc, name);
+}
+
+XLA_FFI_Error* jit_val_common(XLA_FFI_CallFrame* frame, bool matmat, const char* name) {
+    Frame fr(frame);
+    if (fr.metadata()) return nullptr;
+    if (frame->stage != 3) return nullptr;
+    int64_t kind = 0, corder = 1, chunk = 0;
+    fr.attr_i64("kind", &kind);
+    fr.attr_i64("corder", &corder);
+    if (!fr.attr_i64("chunk_size", &chunk)) return fr.fail(BE_B200_EINVAL, std::string(name) + ": attr chunk_size is required");
+    const int np = kind == BE_B200_JIT_SCALAR ? 1 : 2;
+    if (frame->args.size != np + 3 || frame->rets.size < 1) return fr.fail(BE_B200_EINVAL, std::string(name) + ": wrong number of buffers");
+    if (XLA_FFI_Error* e = fr.get_stream()) return e;
+    XLA_FFI_Buffer *p0 = fr.arg(0), *p1 = np == 2 ? fr.arg(1) : nullptr, *clen = fr.arg(np), *seed = fr.arg(np + 1),
+                   *x = fr.arg(np + 2), *out = fr.ret(0);
+    const int wt = wt_of(p0->dtype);
+    if (wt < 0 || x->dtype != p0->dtype) return fr.fail(BE_B200_EUNIMPL, std::string(name) + ": operand and weights must share a float dtype");
+    int rc;
+    if (matmat)
+        rc = be_b200_jitmm((int)kind, p0->data, p1 ? p1->data : nullptr, wt, (const int32_t*)clen->data, (const int32_t*)seed->data,
+                           x->data, x->dims[0], out->dims[0], x->dims[1], chunk, (int)corder, out->data, fr.stream);
+    else
+        rc = be_b200_jitmv((int)kind, p0->data, p1 ? p1->data : nullptr, wt, (const int32_t*)clen->data, (const int32_t*)seed->data,
+                           x->data, x->dims[0], out->dims[0], chunk, (int)corder, out->data, fr.stream);
+    return fr.finish(rc, name);
+}
+
 }  // namespace
 
 extern "C" {
@@ -282,6 +377,101 @@ XLA_FFI_Error* be_b200_xla_bitpack_1d(XLA_FFI_CallFrame* frame) {
     const int sk = spk_of(ev->dtype);
     if (sk < 0) return fr.fail(BE_B200_EUNIMPL, "bitpack_1d: unsupported spike dtype");
     return fr.finish(be_b200_bitpack_1d(ev->data, sk, ev->dims[0], 0, (uint32_t*)packed->data, fr.stream), "be_b200_xla_bitpack_1d");
+}
+
+// ---- SURVEY 8(f) rows -------------------------------------------------------------------------------
+XLA_FFI_Error* be_b200_xla_csrmv(XLA_FFI_CallFrame* frame) { return csr_val_common(frame, false, "be_b200_xla_csrmv"); }
+XLA_FFI_Error* be_b200_xla_csrmm(XLA_FFI_CallFrame* frame) { return csr_val_common(frame, true, "be_b200_xla_csrmm"); }
+XLA_FFI_Error* be_b200_xla_fcnmv(XLA_FFI_CallFrame* frame) { return fcn_val_common(frame, false, "be_b200_xla_fcnmv"); }
+XLA_FFI_Error* be_b200_xla_fcnmm(XLA_FFI_CallFrame* frame) { return fcn_val_common(frame, true, "be_b200_xla_fcnmm"); }
+XLA_FFI_Error* be_b200_xla_jitmv(XLA_FFI_CallFrame* frame) { return jit_val_common(frame, false, "be_b200_xla_jitmv"); }
+XLA_FFI_Error* be_b200_xla_jitmm(XLA_FFI_CallFrame* frame) { return jit_val_common(frame, true, "be_b200_xla_jitmm"); }
+
+// args: weights, indices, [indptr if has_indptr], [perm if has_perm], spikes, trace; ret: updated weights
+// (the reference aliases it onto arg 0, input_output_aliases={0: 0}; copied first when XLA did not).
+XLA_FFI_Error* be_b200_xla_plasticity_rows(XLA_FFI_CallFrame* frame) {
+    Frame fr(frame);
+    if (fr.metadata()) return nullptr;
+    if (frame->stage != 3) return nullptr;
+    int64_t has_indptr = 1, has_perm = 0;
+    fr.attr_i64("has_indptr", &has_indptr);
+    fr.attr_i64("has_perm", &has_perm);
+    double lo = -INFINITY, hi = INFINITY;
+    fr.attr_f64("w_min", &lo);
+    fr.attr_f64("w_max", &hi);
+    const int na = 4 + (has_indptr ? 1 : 0) + (has_perm ? 1 : 0);
+    if (frame->args.size != na || frame->rets.size < 1) return fr.fail(BE_B200_EINVAL, "plasticity_rows: wrong number of buffers");
+    if (XLA_FFI_Error* e = fr.get_stream()) return e;
+    int a = 0;
+    XLA_FFI_Buffer *w = fr.arg(a++), *idx = fr.arg(a++), *ptr = has_indptr ? fr.arg(a++) : nullptr,
+                   *perm = has_perm ? fr.arg(a++) : nullptr, *spk = fr.arg(a++), *trace = fr.arg(a++), *out = fr.ret(0);
+    const int wt = wt_of(w->dtype), sk = spk_of(spk->dtype);
+    if (wt < 0 || sk < 0 || trace->dtype != w->dtype) return fr.fail(BE_B200_EUNIMPL, "plasticity_rows: unsupported dtype");
+    if (idx->dtype != BE_XLA_S32) return fr.fail(BE_B200_EINVAL, "plasticity_rows: indices must be int32");
+    if (!has_indptr && idx->rank != 2) return fr.fail(BE_B200_EINVAL, "plasticity_rows: ELL indices must be [n_rows, n_conn]");
+    static const size_t kWt[4] = {4, 8, 2, 2};
+    if (out->data != w->data &&
+        cudaMemcpyAsync(out->data, w->data, (size_t)numel(w) * kWt[wt], cudaMemcpyDeviceToDevice, (cudaStream_t)fr.stream) != cudaSuccess)
+        return fr.fail(BE_B200_EINTERNAL, "plasticity_rows: weight copy failed");
+    const int64_t n_rows = has_indptr ? ptr->dims[0] - 1 : idx->dims[0];
+    const int64_t n_conn = has_indptr ? -1 : idx->dims[1];
+    if (XLA_FFI_Error* e = fr.get_scratch(n_rows, 1)) return e;
+    int rc = be_b200_plasticity_rows(out->data, wt, (const int32_t*)idx->data, ptr ? ptr->data : nullptr,
+                                     ptr && ptr->dtype == BE_XLA_S64, n_conn, perm ? perm->data : nullptr,
+                                     perm && perm->dtype == BE_XLA_S64, spk->data, nullptr, sk, trace->data, n_rows,
+                                     trace->dims[0], numel(idx), lo, hi, fr.scratch, fr.scratch_bytes, fr.stream);
+    if (rc == BE_B200_OK && (lo != -INFINITY || hi != INFINITY))
+        rc = be_b200_clip(out->data, wt, numel(w), lo, hi, fr.stream);     // the reference clips the whole array
+    return fr.finish(rc, "be_b200_xla_plasticity_rows");
+}
+
+// arg: spikes [n_src, n_batch]; rets per encoder as in brainevent_b200.h
+XLA_FFI_Error* be_b200_xla_binary_2d_csr_encode(XLA_FFI_CallFrame* frame) {
+    BE_XLA_PROLOGUE(1, 2, "csr_encode");
+    XLA_FFI_Buffer *ev = fr.arg(0), *indices = fr.ret(0), *indptr = fr.ret(1);
+    const int sk = spk_of(ev->dtype);
+    if (sk < 0 || sk == BE_B200_SPK_PACKED || ev->rank != 2) return fr.fail(BE_B200_EUNIMPL, "csr_encode: unsupported spike dtype/rank");
+    const int64_t n = ev->dims[0], b = ev->dims[1];
+    if (XLA_FFI_Error* e = fr.get_scratch(n * b, 1)) return e;
+    return fr.finish(be_b200_binary_2d_csr_encode(ev->data, sk, n, b, (int32_t*)indices->data, (int32_t*)indptr->data, fr.scratch,
+                                                  fr.scratch_bytes, fr.stream), "be_b200_xla_binary_2d_csr_encode");
+}
+
+XLA_FFI_Error* be_b200_xla_binary_2d_pair_stream_encode(XLA_FFI_CallFrame* frame) {
+    BE_XLA_PROLOGUE(1, 2, "pair_stream_encode");
+    XLA_FFI_Buffer *ev = fr.arg(0), *pairs = fr.ret(0), *np_ = fr.ret(1);
+    const int sk = spk_of(ev->dtype);
+    if (sk < 0 || sk == BE_B200_SPK_PACKED || ev->rank != 2) return fr.fail(BE_B200_EUNIMPL, "pair_stream_encode: unsupported spike dtype/rank");
+    const int64_t n = ev->dims[0], b = ev->dims[1];
+    if (XLA_FFI_Error* e = fr.get_scratch(n * b, 1)) return e;
+    return fr.finish(be_b200_binary_2d_pair_stream_encode(ev->data, sk, n, b, (int32_t*)pairs->data, (int32_t*)np_->data, fr.scratch,
+                                                          fr.scratch_bytes, fr.stream), "be_b200_xla_binary_2d_pair_stream_encode");
+}
+
+XLA_FFI_Error* be_b200_xla_binary_2d_csc_encode(XLA_FFI_CallFrame* frame) {
+    BE_XLA_PROLOGUE(1, 2, "csc_encode");
+    XLA_FFI_Buffer *ev = fr.arg(0), *indices = fr.ret(0), *indptr = fr.ret(1);
+    const int sk = spk_of(ev->dtype);
+    if (sk < 0 || sk == BE_B200_SPK_PACKED || ev->rank != 2) return fr.fail(BE_B200_EUNIMPL, "csc_encode: unsupported spike dtype/rank");
+    const int64_t n = ev->dims[0], b = ev->dims[1];
+    if (XLA_FFI_Error* e = fr.get_scratch(n * b, 1)) return e;
+    void* mask = nullptr;
+    const size_t mask_bytes = (size_t)std::max<int64_t>(n * b, 16);
+    if (XLA_FFI_Error* e = fr.alloc_bytes(mask_bytes, &mask)) { fr.release(); return e; }
+    const int rc = be_b200_binary_2d_csc_encode(ev->data, sk, n, b, (int32_t*)indices->data, (int32_t*)indptr->data, mask,
+                                                fr.scratch, fr.scratch_bytes, fr.stream);
+    fr.free_bytes(mask_bytes, mask);
+    return fr.finish(rc, "be_b200_xla_binary_2d_csc_encode");
+}
+
+// rets: spike_indices [n_src, row_size], max_row_nnz [1]
+XLA_FFI_Error* be_b200_xla_binary_2d_row_sparse_encode(XLA_FFI_CallFrame* frame) {
+    BE_XLA_PROLOGUE(1, 2, "row_sparse_encode");
+    XLA_FFI_Buffer *ev = fr.arg(0), *out = fr.ret(0), *mx = fr.ret(1);
+    const int sk = spk_of(ev->dtype);
+    if (sk < 0 || sk == BE_B200_SPK_PACKED || ev->rank != 2 || out->rank != 2) return fr.fail(BE_B200_EUNIMPL, "row_sparse_encode: unsupported spike dtype/rank");
+    return fr.finish(be_b200_binary_2d_row_sparse_encode(ev->data, sk, ev->dims[0], ev->dims[1], out->dims[1], (int32_t*)out->data,
+                                                         (int32_t*)mx->data, fr.stream), "be_b200_xla_binary_2d_row_sparse_encode");
 }
 
 }  // extern "C"

@@ -186,6 +186,29 @@ XLA_FFI_Error* be_b200_xla_compact_2d_only(XLA_FFI_CallFrame* frame);
 /* (spikes[n]) -> (packed u32[ceil(n/32)]); replaces jit_*.pack_bool (_jit_scalar/binary_jitsmv.cu:216-236) */
 XLA_FFI_Error* be_b200_xla_bitpack_1d(XLA_FFI_CallFrame* frame);
 
+/* ---- SURVEY 8(f) rows (same conventions; operands/weights share one float dtype) ---------------
+ * csrmv/csrmm: args (weights, indices, indptr, x) -> ret out {transpose}
+ * fcnmv/fcnmm: args (weights, indices [n_rows, n_conn], x) -> ret out {transpose}
+ * jitmv/jitmm: args (p0, [p1], clen, seed, x) -> ret out {kind, corder, chunk_size}
+ * plasticity_rows: args (weights, indices, [indptr], [perm], spikes, trace) -> ret updated weights
+ *   {has_indptr (default 1; 0 = ELL indices [n_rows, n_conn]), has_perm (default 0), w_min, w_max
+ *   (float scalars, optional)}; the ret buffer may alias arg 0 (input_output_aliases={0: 0})
+ * binary_2d_{csr,csc}_encode: arg spikes [n_src, n_batch] -> rets (indices [n_src*n_batch], indptr)
+ * binary_2d_pair_stream_encode: arg spikes -> rets (pair_stream [n_src*n_batch, 2], n_pairs [1])
+ * binary_2d_row_sparse_encode: arg spikes -> rets (spike_indices [n_src, row_size], max_row_nnz [1]) */
+XLA_FFI_Error* be_b200_xla_csrmv(XLA_FFI_CallFrame* frame);
+XLA_FFI_Error* be_b200_xla_csrmm(XLA_FFI_CallFrame* frame);
+XLA_FFI_Error* be_b200_xla_fcnmv(XLA_FFI_CallFrame* frame);
+XLA_FFI_Error* be_b200_xla_fcnmm(XLA_FFI_CallFrame* frame);
+XLA_FFI_Error* be_b200_xla_jitmv(XLA_FFI_CallFrame* frame);
+XLA_FFI_Error* be_b200_xla_jitmm(XLA_FFI_CallFrame* frame);
+XLA_FFI_Error* be_b200_xla_plasticity_rows(XLA_FFI_CallFrame* frame);
+XLA_FFI_Error* be_b200_xla_binary_2d_csr_encode(XLA_FFI_CallFrame* frame);
+XLA_FFI_Error* be_b200_xla_binary_2d_csc_encode(XLA_FFI_CallFrame* frame);
+XLA_FFI_Error* be_b200_xla_binary_2d_pair_stream_encode(XLA_FFI_CallFrame* frame);
+XLA_FFI_Error* be_b200_xla_binary_2d_row_sparse_encode(XLA_FFI_CallFrame* frame);
+
+
 #ifdef __cplusplus
 }
 #endif

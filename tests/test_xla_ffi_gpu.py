@@ -157,8 +157,12 @@ class FakeXla:
         aptr = (C.c_void_p * max(n, 1))()
         for i, k in enumerate(names):
             bs = ByteSpan(k.encode(), len(k))
-            val = C.c_int32(int(attrs[k]))
-            sc = Scalar(4, C.addressof(val))
+            if isinstance(attrs[k], float):
+                val = C.c_float(attrs[k])
+                sc = Scalar(11, C.addressof(val))       # F32 scalar attribute
+            else:
+                val = C.c_int32(int(attrs[k]))
+                sc = Scalar(4, C.addressof(val))
             self.keep += [bs, val, sc]
             nptr[i] = C.pointer(bs)
             aptr[i] = C.addressof(sc)
@@ -275,3 +279,70 @@ def test_errors_become_ffi_errors(lib):
     fr = fx.frame([torch.ones(3, device="cuda")], [out], {})
     assert call(lib, "be_b200_xla_binary_fcnmv", fx, fr) == 0xdead
     assert fx.errors and fx.errors[-1][0] == 3
+
+
+def test_next_row_frames(lib):
+    """float ops, plasticity and the 2-D encoders through hand-built call frames."""
+    fx = FakeXla()
+    rng = np.random.default_rng(20)
+    c = cases.csr_case(21, 1200, 900, 20, 0.1, ragged=True)
+    for tr in (0, 1):
+        x = rng.standard_normal(1200 if tr else 900).astype(np.float32)
+        out = torch.empty(900 if tr else 1200, device="cuda")
+        fr = fx.frame([t(c["data"]), t(c["indices"]), t(c["indptr"]), t(x)], [out], {"transpose": tr})
+        assert call(lib, "be_b200_xla_csrmv", fx, fr) is None, fx.errors
+        np.testing.assert_allclose(out.cpu().numpy(), O.csrmv(c["data"], c["indices"], c["indptr"], x, shape=(1200, 900), transpose=bool(tr)),
+                                   rtol=1e-4, atol=1e-4)
+    X = rng.standard_normal((900, 12)).astype(np.float32)
+    out = torch.empty((1200, 12), device="cuda")
+    assert call(lib, "be_b200_xla_csrmm", fx, fx.frame([t(c["data"]), t(c["indices"]), t(c["indptr"]), t(X)], [out], {"transpose": 0})) is None, fx.errors
+    np.testing.assert_allclose(out.cpu().numpy(), O.csrmm(c["data"], c["indices"], c["indptr"], X, shape=(1200, 900)), rtol=1e-4, atol=1e-4)
+    f = cases.fcn_case(22, 2000, 1500, 40)
+    x = rng.standard_normal(2000).astype(np.float32)
+    out = torch.empty(1500, device="cuda")
+    assert call(lib, "be_b200_xla_fcnmv", fx, fx.frame([t(f["weights"]), t(f["indices"]), t(x)], [out], {"transpose": 1})) is None, fx.errors
+    np.testing.assert_allclose(out.cpu().numpy(), O.fcnmv(f["weights"], f["indices"], x, shape=(2000, 1500), transpose=True), rtol=1e-4, atol=1e-4)
+    xv = rng.standard_normal(700).astype(np.float32)
+    out = torch.empty(900, device="cuda")
+    ins = [torch.tensor([1.0], device="cuda"), torch.tensor([0.1], device="cuda"),
+           torch.tensor([O.conn_length(0.02)], dtype=torch.int32, device="cuda"), torch.tensor([11], dtype=torch.int32, device="cuda"), t(xv)]
+    fr = fx.frame(ins, [out], {"kind": 1, "corder": 0, "chunk_size": O.normalize_chunk_size(900)})
+    assert call(lib, "be_b200_xla_jitmv", fx, fr) is None, fx.errors
+    np.testing.assert_allclose(out.cpu().numpy(), O.jitnmv(1.0, 0.1, 0.02, xv, 11, shape=(700, 900), transpose=True, corder=False), rtol=1e-4, atol=1e-4)
+    # plasticity: aliased (in place) and non-aliased output, bounds as float attributes
+    pre = cases.spikes(23, 1200, 0.2)
+    tr_post = rng.standard_normal(900).astype(np.float32)
+    want = O.update_csr_on_binary_pre(c["data"], c["indices"], c["indptr"], pre, tr_post, -0.5, 0.75, shape=(1200, 900))
+    w_in, w_out = t(c["data"]), torch.empty(c["data"].shape[0], device="cuda")
+    fr = fx.frame([w_in, t(c["indices"]), t(c["indptr"]), t(pre), t(tr_post)], [w_out], {"w_min": -0.5, "w_max": 0.75})
+    assert call(lib, "be_b200_xla_plasticity_rows", fx, fr) is None, fx.errors
+    np.testing.assert_array_equal(w_out.cpu().numpy(), want)
+    np.testing.assert_array_equal(w_in.cpu().numpy(), c["data"])
+    fr = fx.frame([w_in, t(c["indices"]), t(c["indptr"]), t(pre), t(tr_post)], [w_in], {"w_min": -0.5, "w_max": 0.75})
+    assert call(lib, "be_b200_xla_plasticity_rows", fx, fr) is None, fx.errors
+    np.testing.assert_array_equal(w_in.cpu().numpy(), want)
+    fw = t(f["weights"])
+    spk = cases.spikes(24, 2000, 0.1)
+    trf = rng.standard_normal(1500).astype(np.float32)
+    fr = fx.frame([fw, t(f["indices"]), t(spk), t(trf)], [fw], {"has_indptr": 0})
+    assert call(lib, "be_b200_xla_plasticity_rows", fx, fr) is None, fx.errors
+    np.testing.assert_array_equal(fw.cpu().numpy(), O.fcn_plasticity_row(f["weights"], f["indices"], spk, trf))
+    # encoders
+    S = cases.spikes(25, 300, 0.05, batch=70)
+    idx, ptr_ = torch.empty(300 * 70, dtype=torch.int32, device="cuda"), torch.empty(301, dtype=torch.int32, device="cuda")
+    assert call(lib, "be_b200_xla_binary_2d_csr_encode", fx, fx.frame([t(S)], [idx, ptr_], {})) is None, fx.errors
+    oi, op = O.binary_2d_csr_encode(S)
+    np.testing.assert_array_equal(idx.cpu().numpy(), oi); np.testing.assert_array_equal(ptr_.cpu().numpy(), op)
+    idx, ptr_ = torch.empty(300 * 70, dtype=torch.int32, device="cuda"), torch.empty(71, dtype=torch.int32, device="cuda")
+    assert call(lib, "be_b200_xla_binary_2d_csc_encode", fx, fx.frame([t(S)], [idx, ptr_], {})) is None, fx.errors
+    oi, op = O.binary_2d_csc_encode(S)
+    np.testing.assert_array_equal(idx.cpu().numpy(), oi); np.testing.assert_array_equal(ptr_.cpu().numpy(), op)
+    pairs, npairs = torch.empty((300 * 70, 2), dtype=torch.int32, device="cuda"), torch.empty(1, dtype=torch.int32, device="cuda")
+    assert call(lib, "be_b200_xla_binary_2d_pair_stream_encode", fx, fx.frame([t(S)], [pairs, npairs], {})) is None, fx.errors
+    op_, on = O.binary_2d_pair_stream_encode(S)
+    np.testing.assert_array_equal(pairs.cpu().numpy(), op_); assert int(npairs.item()) == int(on[0])
+    rs, mx = torch.empty((300, 40), dtype=torch.int32, device="cuda"), torch.empty(1, dtype=torch.int32, device="cuda")
+    assert call(lib, "be_b200_xla_binary_2d_row_sparse_encode", fx, fx.frame([t(S)], [rs, mx], {})) is None, fx.errors
+    np.testing.assert_array_equal(rs.cpu().numpy(), O.binary_2d_row_sparse_encode(S, 40))
+    assert int(mx.item()) == int((S != 0).sum(axis=1).max())
+    assert not fx.live
