@@ -1,14 +1,16 @@
 // exchange.cu -- fused bit-pack + all-gather of spike words over NVLink peer memory.
 //
 // Net-new relative to the reference (no distributed code there).  The compute
-// step "pack my block of spikes" and the collective "all-gather the packed words" are ONE kernel:
-// every rank packs its own block and stores each 32-bit word straight into every peer's gather
-// buffer (peer pointers from a symmetric-memory rendezvous; NVSwitch gives each pair full
-// bandwidth), then publishes a monotonically increasing step number into a flag slot on each
-// peer with release semantics at system scope.  A one-warp wait kernel on the consumer side
-// acquires the `world` flags before the propagation kernels read the gathered words.  The whole
-// exchange moves N/8 bytes and is latency-bound, so it replaces NCCL's all-gather launch +
-// protocol latency by a single store-and-flag round.
+// step "pack my block of spikes" and the collective "all-gather the packed words" share two
+// kernels: every rank packs its own block into its OWN symmetric buffer (local stores: the
+// system-scope fence that follows has no NVLink writes to wait for), then publishes a
+// monotonically increasing step number into a flag slot on every peer with relaxed stores behind
+// that one fence.  The consumer kernel acquires the `world` flags and PULLS each peer's words over
+// NVLink straight into the local gathered vector (peer pointers from a symmetric-memory
+// rendezvous; NVSwitch gives each pair full bandwidth).  The whole exchange moves N/8 bytes and is
+// latency-bound: one fence, one flag hop, one remote read.  (A first push-based version stored
+// every word into all peers and released each flag separately: 8.7 us of pack + remote-write
+// fences and 5.4 us of serial release stores at N=2, 32 us per exchange at N=8.)
 //
 // Buffers are double-buffered by the parity of the device-side step counter: a rank can run at
 // most one exchange ahead of a peer (its step t+1 needs every peer's step t+1 pack, which follows
@@ -24,6 +26,14 @@ namespace be {
 __device__ __forceinline__ void st_release_sys(uint32_t* p, uint32_t v) {
     asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
+__device__ __forceinline__ void st_relaxed_sys(uint32_t* p, uint32_t v) {
+    asm volatile("st.relaxed.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ uint32_t ld_relaxed_sys(const uint32_t* p) {
+    uint32_t v;
+    asm volatile("ld.relaxed.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
 __device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* p) {
     uint32_t v;
     asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
@@ -35,7 +45,16 @@ struct ExchangeCtl {      // local (non-symmetric) control block, zero-initialis
     uint32_t done;        // blocks of the pack kernel in flight that have finished their stores
     uint32_t timeout;     // set when a wait gave up (peer never published): surfaced by the host
     uint32_t pad;
+    // %globaltimer stamps of the last exchange (diagnostics, tools/mgpu_exchange_bench.py):
+    // [0] pack start, [1] last pack CTA after its fence, [2] flags published,
+    // [3] wait start, [4] all flags seen, [5] copy done
+    unsigned long long stamp[8];
 };
+__device__ __forceinline__ unsigned long long gtimer() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
 
 template <int KIND>
 __global__ void __launch_bounds__(256) pack_publish_kernel(const void* __restrict__ spikes, int64_t n_local,
@@ -44,6 +63,7 @@ __global__ void __launch_bounds__(256) pack_publish_kernel(const void* __restric
                                                            int rank, int64_t words_per_rank, ExchangeCtl* ctl) {
     const uint32_t t = ctl->step + 1;      // read by every block before the last one bumps it
     const int lane = threadIdx.x & 31;
+    if (blockIdx.x == 0 && threadIdx.x == 0) ctl->stamp[0] = gtimer();
     const int64_t slot0 = (int64_t)(t & 1u) * words_per_rank * world + (int64_t)rank * words_per_rank;
     for (int64_t h = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; (h - lane) < 2 * words_per_rank;
          h += (int64_t)gridDim.x * blockDim.x) {
@@ -69,43 +89,48 @@ __global__ void __launch_bounds__(256) pack_publish_kernel(const void* __restric
             }
         }
         const unsigned int hi = __shfl_down_sync(0xffffffffu, m, 1);
-        if ((h & 1) == 0 && (h >> 1) < words_per_rank) {
-            const uint32_t word = m | (hi << 16);
-            for (int p = 0; p < world; ++p) peer_bufs[p][slot0 + (h >> 1)] = word;   // NVLink peer stores
-        }
+        if ((h & 1) == 0 && (h >> 1) < words_per_rank)
+            peer_bufs[rank][slot0 + (h >> 1)] = m | (hi << 16);      // my own symmetric buffer
     }
     __syncthreads();                       // this CTA's peer stores are ordered before thread 0's fence
     if (threadIdx.x == 0) {
         __threadfence_system();            // cumulative: publishes the whole CTA's stores at system scope
         const uint32_t prev = atomicAdd(&ctl->done, 1u);
         if (prev == gridDim.x - 1) {
-            __threadfence_system();
-            for (int p = 0; p < world; ++p) st_release_sys(peer_flags[p] + rank, t);
+            ctl->stamp[1] = gtimer();
+            __threadfence_system();          // cumulative over every CTA's words (observed through `done`)
+            for (int p = 0; p < world; ++p) st_relaxed_sys(peer_flags[p] + rank, t);
+            ctl->stamp[2] = gtimer();
             ctl->done = 0u;
             ctl->step = t;
         }
     }
 }
 
-// every block waits until all peers have published this rank's current step, then copies its
-// share of the gathered words (current parity half) into the fixed local buffer
+// every block waits until all peers have published this rank's current step, then pulls its share
+// of every peer's words (current parity half of the peer's own buffer) into the local vector
 __global__ void __launch_bounds__(256) wait_copy_kernel(const uint32_t* __restrict__ my_flags,
-                                                        const uint32_t* __restrict__ my_buf, int world,
+                                                        uint32_t* const* __restrict__ peer_bufs, int world,
                                                         int64_t words_per_rank, uint32_t* __restrict__ dst,
                                                         ExchangeCtl* ctl) {
     const uint32_t t = ctl->step;
+    if (blockIdx.x == 0 && threadIdx.x == 0) ctl->stamp[3] = gtimer();
     if ((int)threadIdx.x < world) {
         unsigned long long spins = 0;
         while ((int32_t)(ld_acquire_sys(my_flags + threadIdx.x) - t) < 0) {
             if (++spins > (1ull << 26)) { ctl->timeout = 1u; break; }   // bounded: never hang the GPU
-            __nanosleep(32);
+            __nanosleep(20);
         }
     }
     __syncthreads();
+    if (blockIdx.x == 0 && threadIdx.x == 0) ctl->stamp[4] = gtimer();
     const int64_t n = words_per_rank * world;
-    const uint32_t* src = my_buf + (int64_t)(t & 1u) * n;
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
-        dst[i] = __ldcv(src + i);     // peers wrote these words: bypass any stale cached copy
+    const int64_t half = (int64_t)(t & 1u) * n;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const int p = (int)(i / words_per_rank);
+        dst[i] = ld_relaxed_sys(peer_bufs[p] + half + i);     // remote (NVLink) read; ordered after the flag acquire
+    }
+    if (blockIdx.x == gridDim.x - 1 && threadIdx.x == 0) ctl->stamp[5] = gtimer();
 }
 
 }  // namespace be
@@ -135,11 +160,11 @@ extern "C" int be_b200_pack_publish(const void* spikes_local, int spk_kind, int6
     return BE_B200_OK;
 }
 
-extern "C" int be_b200_wait_exchange(const void* my_flags, const void* my_buf, int world,
+extern "C" int be_b200_wait_exchange(const void* my_flags, void* const* peer_bufs, int world,
                                      int64_t words_per_rank, uint32_t* gathered_out, void* ctl, void* stream) {
-    BE_REQUIRE(my_flags && my_buf && gathered_out && ctl && world >= 1 && world <= 32, "wait_exchange: bad arguments");
+    BE_REQUIRE(my_flags && peer_bufs && gathered_out && ctl && world >= 1 && world <= 32, "wait_exchange: bad arguments");
     const int blocks = (int)std::max<int64_t>(1, std::min<int64_t>(ceil_div(words_per_rank * world, 1024), kNumSM));
-    wait_copy_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>((const uint32_t*)my_flags, (const uint32_t*)my_buf, world,
+    wait_copy_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>((const uint32_t*)my_flags, (uint32_t* const*)peer_bufs, world,
                                                               words_per_rank, gathered_out, (ExchangeCtl*)ctl);
     BE_LAUNCH_CHECK("wait_copy_kernel");
     return BE_B200_OK;

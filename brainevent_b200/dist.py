@@ -85,9 +85,9 @@ class SpikeExchange:
 
 
 class P2PSpikeExchange(SpikeExchange):
-    """Fused bit-pack + all-gather over NVLink peer memory (csrc/exchange.cu): every rank stores
-    its packed words directly into all peers' gather buffers and flags completion; no NCCL call
-    on the per-timestep path.  Peer pointers come from a torch symmetric-memory rendezvous
+    """Fused bit-pack + all-gather over NVLink peer memory (csrc/exchange.cu): every rank packs
+    into its own symmetric buffer, flags completion on every peer, and pulls the peers' words
+    over NVLink; no NCCL call on the per-timestep path.  Peer pointers come from a torch symmetric-memory rendezvous
     (torch is used for the memory mapping only; the kernels are ours)."""
 
     def __init__(self, n_neurons: int, group=None, device="cuda"):
@@ -126,7 +126,7 @@ class P2PSpikeExchange(SpikeExchange):
         _lib.check(L.be_b200_pack_publish(ptr(s), kind, s.numel(), ptr(self.peer_bufs), ptr(self.peer_flags), self.world,
                                           self.rank, self.words_per_rank, ptr(self.ctl), stream_ptr(dev)), "pack_publish")
         import ctypes
-        _lib.check(L.be_b200_wait_exchange(ctypes.c_void_p(me.data_ptr() + 4 * self.n_buf), ptr(me), self.world,
+        _lib.check(L.be_b200_wait_exchange(ctypes.c_void_p(me.data_ptr() + 4 * self.n_buf), ptr(self.peer_bufs), self.world,
                                            self.words_per_rank, ptr(self.gathered), ptr(self.ctl), stream_ptr(dev)),
                    "wait_exchange")
         return self.gathered[: self.n_words]

@@ -287,11 +287,10 @@ int be_b200_csr_to_csc(const void* indptr, int is64, const int32_t* indices, int
                        void* perm, void* workspace, size_t workspace_bytes, void* stream);
 
 /* ---- multi-GPU spike exchange over NVLink peer memory (net-new: the reference is single-device) --
- * Fused "bit-pack my block + all-gather the words": each rank stores its packed words directly
- * into every peer's gather buffer and publishes a step number in a flag slot on each peer;
- * be_b200_wait_exchange then holds the stream (acquire loads, bounded spin) until all `world`
- * peers have published and copies the gathered words uint32[world * words_per_rank] into
- * `gathered_out`.  peer_bufs[p] / peer_flags[p] are DEVICE arrays of peer-mapped pointers (e.g.
+ * Fused "bit-pack my block + all-gather the words": each rank packs into its OWN symmetric
+ * buffer and publishes a step number in a flag slot on each peer; be_b200_wait_exchange then
+ * holds the stream (acquire loads, bounded spin) until all `world` peers have published and
+ * pulls every peer's words over NVLink into `gathered_out` = uint32[world * words_per_rank].  peer_bufs[p] / peer_flags[p] are DEVICE arrays of peer-mapped pointers (e.g.
  * from a torch symmetric-memory rendezvous): buffer = uint32[2 * world * words_per_rank]
  * (double-buffered by the parity of the device-side step counter), flags = uint32[world], both
  * zero before first use.  `ctl` is a local zero-initialised control block of
@@ -300,7 +299,7 @@ size_t be_b200_exchange_ctl_bytes(void);
 int be_b200_pack_publish(const void* spikes_local, int spk_kind, int64_t n_local,
                          void* const* peer_bufs, void* const* peer_flags, int world, int rank,
                          int64_t words_per_rank, void* ctl, void* stream);
-int be_b200_wait_exchange(const void* my_flags, const void* my_buf, int world, int64_t words_per_rank,
+int be_b200_wait_exchange(const void* my_flags, void* const* peer_bufs, int world, int64_t words_per_rank,
                           uint32_t* gathered_out, void* ctl, void* stream);
 
 /* ---- host-buffer session (end-to-end entry: host spikes in, host result out) -----------------

@@ -52,6 +52,9 @@ if os.environ.get("NO_P2P") != "1":
     xp = bd.P2PSpikeExchange(N, device=dev)
     t_p2p = time_graph(lambda s: xp.exchange_spikes(s))
     msg += f", fused pack+P2P exchange {t_p2p:.1f} us (timed_out={xp.timed_out()})"
+    st = xp.ctl.view(torch.int64)[2:8].tolist()     # %globaltimer stamps of the last exchange (ns)
+    print(f"[{tag}] rank {rank} last exchange: pack {st[1]-st[0]} ns, fence+flags {st[2]-st[1]} ns, "
+          f"gap to wait kernel {st[3]-st[2]} ns, poll {st[4]-st[3]} ns, copy {st[5]-st[4]} ns", flush=True)
 if rank == 0:
     print(msg, flush=True)
 dist.barrier()
