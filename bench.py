@@ -615,14 +615,15 @@ def main():
                 e2e_step_sync()
             sync_value = wl.total_events_per_timestep() * Te * 3 / (time.perf_counter() - t0)
         else:
-            d_spk = torch.empty(n_in, dtype=torch.uint8, device=device)
+            from brainevent_b200 import dist as bd
+            pipe = bd.HostStepPipeline(wl.proj, n_in, slots=4)
 
             def e2e_step():
+                # pipelined like the single-GPU C-ABI entry: four timesteps in flight per rank, each moving
+                # its own spike block in and its own output block out
                 for t in range(Te):
-                    d_spk.copy_(host_spk[t % POOL], non_blocking=True)
-                    out = wl.proj.step(d_spk)
-                    host_out[0].copy_(out, non_blocking=True)
-                    torch.cuda.current_stream().synchronize()
+                    pipe.submit(host_spk[t % POOL], host_out[t % 4])
+                pipe.wait()
         for _ in range(2):
             e2e_step()
         if world > 1:
@@ -644,11 +645,15 @@ def main():
                        f"{T} timesteps/step; entry point: " +
                        ("be_b200_projection_submit_host/_wait (C ABI, 4 calls in flight; `sync_value` is the "
                         "blocking be_b200_projection_apply_host)" if world == 1 else
-                        "PostShardedProjection.step (per rank: its own spike block in, its own output block out)")}
+                        "HostStepPipeline.submit/wait over PostShardedProjection.step (per rank: its own spike block in, its "
+                        "own output block out, 4 timesteps in flight)")}
         if sync_value is not None:
             e2e["sync_value"] = sync_value
         if world == 1:
             L.lib().be_b200_projection_destroy(proj)
+        else:
+            pipe.close()        # graphs that captured NCCL collectives must go before the group is destroyed
+            del pipe, e2e_step
 
     if rank != 0:
         if world > 1:

@@ -181,3 +181,75 @@ class PostShardedProjection:
         if hasattr(self.x, "exchange_spikes"):           # fused pack + peer-memory all-gather
             return self.propagate(self.x.exchange_spikes(local_spikes))
         return self.propagate(self.x.exchange(self.pack_local(local_spikes)))
+
+
+class HostStepPipeline:
+    """Host-buffer entry of the post-sharded step: per timestep this rank's spike block comes from
+    pinned host memory and its output block goes back to pinned host memory (the multi-GPU twin of
+    be_b200_projection_submit_host / _wait).  `slots` timesteps are in flight: copy-in, the device
+    step (bit-pack, all-gather, compaction, scatter -- one CUDA graph per slot, so the host issues
+    three calls per timestep) and copy-out run on three streams and overlap across neighbouring
+    timesteps.  Every rank must call submit() the same number of times (the step has a collective).
+    """
+
+    def __init__(self, proj: "PostShardedProjection", n_in: int, slots: int = 4, use_graph: bool = True):
+        self.proj, self.slots = proj, slots
+        dev = proj.x.gathered.device
+        self.dev = dev
+        self.s_in, self.s_out = torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)
+        self.main = torch.cuda.Stream(device=dev)
+        self.d_in = [torch.zeros(n_in, dtype=torch.uint8, device=dev) for _ in range(slots)]
+        mk = lambda: [torch.cuda.Event() for _ in range(slots)]
+        self.ev_in, self.ev_done, self.ev_out = mk(), mk(), mk()
+        self.inflight = [False] * slots
+        self.i = 0
+        self.graphs, self.d_out = [None] * slots, [None] * slots
+        with torch.cuda.stream(self.main):
+            for k in range(slots):                       # warm-up: allocations, workspaces, NCCL channels
+                self.d_out[k] = proj.step(self.d_in[k])
+        self.main.synchronize()
+        if use_graph:
+            for k in range(slots):
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g, stream=self.main):
+                    self.d_out[k] = proj.step(self.d_in[k])
+                self.graphs[k] = g
+        self.main.synchronize()
+
+    def submit(self, spikes_host: torch.Tensor, out_host: torch.Tensor) -> None:
+        """spikes_host: pinned uint8/bool [n_in]; out_host: pinned [n_out] in the weight dtype.  Both must
+        stay untouched until wait() (or the `slots`-th next submit) returns."""
+        i = self.i
+        if self.inflight[i]:
+            self.ev_out[i].synchronize()
+        with torch.cuda.stream(self.s_in):
+            self.d_in[i].copy_(spikes_host.view(torch.uint8), non_blocking=True)
+            self.ev_in[i].record(self.s_in)
+        self.main.wait_event(self.ev_in[i])
+        with torch.cuda.stream(self.main):
+            if self.graphs[i] is not None:
+                self.graphs[i].replay()
+            else:
+                self.d_out[i] = self.proj.step(self.d_in[i])
+            self.ev_done[i].record(self.main)
+        self.s_out.wait_event(self.ev_done[i])
+        with torch.cuda.stream(self.s_out):
+            out_host.copy_(self.d_out[i], non_blocking=True)
+            self.ev_out[i].record(self.s_out)
+        self.inflight[i] = True
+        self.i = (i + 1) % self.slots
+
+    def wait(self) -> None:
+        for k in range(self.slots):
+            if self.inflight[k]:
+                self.ev_out[k].synchronize()
+                self.inflight[k] = False
+
+    def close(self) -> None:
+        """Drain and drop the captured graphs.  Call before dist.destroy_process_group(): tearing the
+        NCCL communicator down while graphs that captured its collectives are alive can block."""
+        self.wait()
+        self.main.synchronize()
+        self.graphs = [None] * self.slots
+        self.d_out = [None] * self.slots
+        torch.cuda.synchronize(self.dev)

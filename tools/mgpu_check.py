@@ -39,6 +39,22 @@ for step in range(7):          # odd count on purpose: parity lives on the devic
     ref = O.binary_fcnmv(w, idx, spikes, shape=(N, N), transpose=True)[lo:hi]
     np.testing.assert_allclose(out, ref, rtol=1e-5, atol=2e-5)
 assert not xp.timed_out()
+# host-buffer pipeline (4 timesteps in flight, one CUDA graph per slot) == the plain step
+pipe = bd.HostStepPipeline(proj_n, hi - lo, slots=4)
+h_in = [torch.empty(hi - lo, dtype=torch.uint8).pin_memory() for _ in range(9)]
+h_out = [torch.empty(hi - lo, dtype=torch.float32).pin_memory() for _ in range(9)]
+refs = []
+for q in range(9):
+    sp = np.random.default_rng(300 + q).random(N) < 0.04
+    h_in[q].copy_(torch.from_numpy(sp[lo:hi].astype(np.uint8)))
+    refs.append(O.binary_fcnmv(w, idx, sp, shape=(N, N), transpose=True)[lo:hi])
+for q in range(9):
+    pipe.submit(h_in[q], h_out[q])
+pipe.wait()
+for q in range(9):
+    np.testing.assert_allclose(h_out[q].numpy(), refs[q], rtol=1e-5, atol=2e-5)
+pipe.close()
+del pipe
 # JITC post-sharding (column window for scatter, row window for gather) against the oracle
 for corder in (False, True):
     pj = bd.PostShardedProjection("jitc", N, N, xp, family="normal", params=(1.0, 0.1), prob=0.01, seed=5, corder=corder)
