@@ -534,3 +534,26 @@ def test_other_weight_dtypes(G, dt):
         close(be.binary_densemv(Wd, T(s), transpose=tr), O.binary_densemv(Wd64, s, transpose=tr))
         B = cases.spikes(68, 300 if tr else 260, 0.1, batch=70)
         close(be.binary_densemm(Wd, T(B), transpose=tr), O.binary_densemm(Wd64, B, transpose=tr))
+
+
+def test_host_step_pipeline_single_rank(G):
+    """HostStepPipeline (pinned host spikes in, pinned host block out, 4 timesteps in flight, one CUDA
+    graph per slot) over a world-size-1 PostShardedProjection == the oracle's product."""
+    from brainevent_b200 import dist as bd
+    n, conn = 20_000 + 64, 24
+    f = cases.fcn_case(70, n, n, conn)
+    x = bd.SpikeExchange(n, device="cuda")
+    proj = bd.PostShardedProjection("fcn", n, n, x, weights=torch.as_tensor(f["weights"], device="cuda"),
+                                    indices=torch.as_tensor(f["indices"], device="cuda"))
+    for use_graph in (True, False):
+        pipe = bd.HostStepPipeline(proj, n, slots=4, use_graph=use_graph)
+        spikes = [cases.spikes(71 + q, n, 0.03) for q in range(7)]
+        h_in = [torch.from_numpy(s.astype(np.uint8)).pin_memory() for s in spikes]
+        h_out = [torch.empty(n, dtype=torch.float32).pin_memory() for _ in spikes]
+        for a, b in zip(h_in, h_out):
+            pipe.submit(a, b)
+        pipe.wait()
+        for s, o in zip(spikes, h_out):
+            np.testing.assert_allclose(o.numpy(), O.binary_fcnmv(f["weights"], f["indices"], s, shape=(n, n), transpose=True),
+                                       rtol=RTOL, atol=2e-5)
+        pipe.close()
