@@ -549,6 +549,12 @@ def main():
     import brainevent_b200 as be
     from brainevent_b200 import _lib as L
     L.check(L.lib().be_b200_check_device(), "check_device")
+    if os.environ.get("BE_B200_NUMA_BIND", "1") != "0":
+        # pinned host buffers of the e2e leg and the copy-issuing thread go to the GPU's NUMA node
+        from brainevent_b200.dist import bind_to_gpu_numa
+        numa_bound = bind_to_gpu_numa(local_rank)
+    else:
+        numa_bound = False
     peak, peak_src = peaks()
     K, W, T = args.steps, args.warmup, args.timesteps
 
@@ -640,6 +646,7 @@ def main():
         e2e_events = wl.total_events_per_timestep() * Te * Ke
         e2e = {"value": e2e_events / float(dt.item()), "unit": "events/s",
                "h2d_bytes_per_step": int(n_in * T), "d2h_bytes_per_step": int(4 * n_out * T),
+               "numa_bound": bool(numa_bound),
                "note": f"per timestep: pinned host spikes (uint8[{n_in}]) -> device, hot path, fp32[{n_out}] result -> "
                        f"pinned host, stream sync; timed over {Ke}x{Te} timesteps with the host clock, bytes scaled to "
                        f"{T} timesteps/step; entry point: " +

@@ -8,6 +8,7 @@ of uint32 words delivers the global spike vector (N/32 words in total); propagat
 the packed words directly (event kind PACKED of the C ABI).  Block sizes are multiples of 32 so
 the concatenation of per-rank words IS the packing of the concatenated spike vector.
 """
+import os
 from typing import List, Optional, Tuple
 
 import numpy as np
@@ -59,6 +60,27 @@ def partition_fcn_by_post(indices, weights, n_post: int, world: int):
     w = np.asarray(weights)
     return partition_csr_by_post(indptr if indptr[-1] >= 2**31 else indptr.astype(np.int32),
                                  indices.reshape(-1), w if w.size == 1 else w.reshape(-1), n_post, world)
+
+
+def bind_to_gpu_numa(device_index: int) -> bool:
+    """Pin the calling process to the CPUs NVML reports as local to the GPU, so that pinned host
+    buffers allocated afterwards (first touch) and the copy-issuing thread sit on the GPU's NUMA
+    node.  With 8 ranks streaming host<->device every timestep this keeps the traffic off the
+    inter-socket link.  Returns False (and changes nothing) when NVML is unavailable."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(device_index)
+        n_words = (os.cpu_count() + 63) // 64
+        mask = pynvml.nvmlDeviceGetCpuAffinity(h, n_words)
+        cpus = {64 * w + b for w, word in enumerate(mask) for b in range(64) if (word >> b) & 1}
+        cpus &= os.sched_getaffinity(0)
+        if not cpus:
+            return False
+        os.sched_setaffinity(0, cpus)
+        return True
+    except Exception:
+        return False
 
 
 class SpikeExchange:

@@ -79,3 +79,24 @@ def test_shape_assertions_match_reference_behaviour():
     with pytest.raises((AssertionError, be.KernelExecutionError)):
         be.binary_csrmv(w, idx, ptr, torch.tensor([True, False]), shape=(2, 3))
     assert _csr._prep_structure  # host logic is importable without CUDA
+
+
+def test_reference_cuda_shim_exports():
+    """oracle/_ref/libref_*.so (the reference's own kernels behind a plain C ABI, built in the
+    container that has /root/reference) load and export the entry points oracle/ref_cuda.py binds."""
+    import ctypes
+    from oracle import ref_cuda as R
+    want = {"fcnmv": ["binary_fcnmv_scatter_homo_bool_f32", "binary_fcnmv_scatter_hetero_bool_f32"],
+            "csrmv": ["binary_csrmv_nt_auto_homo_f32_bool", "binary_csrmv_nt_auto_hetero_f32_bool"],
+            "csrmv_hybrid": ["binary_csrmv_wat_hybrid_homo_f32_bool", "binary_csrmv_wat_hybrid_hetero_f32_bool"],
+            "csrmm_hybrid": ["binary_csrmm_sraw_hybrid_homo_f32_bool", "binary_csrmm_sraw_hybrid_hetero_f32_bool"],
+            "jitsmv": ["pack_bool", "notrans_f32", "trans_f32"], "jitnmv": ["pack_bool", "notrans_f32", "trans_f32"],
+            "jitumv": ["pack_bool", "notrans_f32", "trans_f32"], "densemm": ["binary_densemm_transpose_f32_bool"],
+            "compact": ["compact_1d_bool"]}
+    built = [n for n in want if R.available(n)]
+    if not built:
+        pytest.skip("oracle/_ref not built (needs /root/reference at build time)")
+    for name in built:
+        lib = ctypes.CDLL(os.path.join(os.path.dirname(R.__file__), "_ref", f"libref_{name}.so"))
+        for fn in want[name]:
+            assert hasattr(lib, "ref_" + fn), (name, fn)
