@@ -108,7 +108,15 @@ struct Events {
     // product (decided on the device, no host sync): with sel_thr >= 0 a scatter kernel runs only
     // when n_active <= sel_thr and a gather kernel only when n_active > sel_thr.
     int sel_thr = -1;
+    // small bool vectors consumed by the shared-memory gather: the caller sets defer_pack_ok, and
+    // prepare_events_1d then skips the pack kernel and hands the raw bytes over (raw_bool); the
+    // gather CTAs pack them straight into shared memory (one launch instead of two).  A consumer
+    // that cannot use raw_bool calls pack_deferred() first.
+    bool defer_pack_ok = false;
+    const uint8_t* raw_bool = nullptr;
+    int64_t raw_n = 0;
 };
+constexpr int64_t kDeferPackMax = 32768;    // sources
 
 // ------------------------------------------------------------------------------------------
 // device helpers
@@ -230,5 +238,7 @@ int prepare_events_1d(const void* spikes, const void* aux, int spk_kind, int64_t
 int prepare_events_2d(const void* spikes, const void* aux, int spk_kind, int64_t n, int64_t batch,
                       bool need_ids, void* workspace, size_t workspace_bytes, cudaStream_t stream,
                       Events* ev);
+// runs the pack kernel that prepare_events_1d deferred (ev->raw_bool set) and clears the deferral
+int pack_deferred(Events* ev, cudaStream_t stream);
 
 }  // namespace be

@@ -300,6 +300,7 @@ static int run_conn(const Rows& rows, const RowsDesc& rd, const ConnArgs& c, con
     int rc;
     const bool mm = n_batch > 0;
     const int64_t out_elems = n_out * (mm ? n_batch : 1);
+    ev.defer_pack_ok = !mm && !scatter;     // the matvec gather can pack small bool vectors itself
     if (mm) rc = prepare_events_2d(spikes, aux, spk_kind, n_src, n_batch, scatter, workspace, workspace_bytes, s, &ev);
     else rc = prepare_events_1d(spikes, aux, spk_kind, n_src, scatter, !scatter, workspace, workspace_bytes, s, &ev,
                                 scatter ? (void*)out : nullptr, scatter ? (size_t)out_elems * sizeof(T) : 0,

@@ -26,11 +26,43 @@ __global__ void __launch_bounds__(SMEM ? 1024 : 256) gather_mv_kernel(Rows rows,
                                                                       const uint32_t* __restrict__ packed,
                                                                       int64_t n_words, int64_t n_rows,
                                                                       T* __restrict__ out,
-                                                                      const int* __restrict__ sel_n_active, int sel_thr) {
+                                                                      const int* __restrict__ sel_n_active, int sel_thr,
+                                                                      const uint8_t* __restrict__ raw_bool, int64_t raw_n) {
     using A = typename Acc<T>::type;
     if (sel_thr >= 0 && *sel_n_active <= sel_thr) return;   // the scatter variant owns this call
     extern __shared__ __align__(16) uint32_t s_bits[];
-    if (SMEM) {
+    // the first row's extent (and the homogeneous weight) are requested before the spike vector is
+    // staged, so their latency overlaps the staging instead of following it
+    const A w0 = HOMO ? to_acc<T>(__ldg(weights)) : A(0);
+    const int GROUPS = blockDim.x / LPR;
+    const int g = threadIdx.x / LPR, gl = threadIdx.x % LPR;
+    const int64_t row_stride = (int64_t)gridDim.x * GROUPS;
+    const int64_t row_iters = ceil_div(n_rows, row_stride);
+    int64_t r = (int64_t)blockIdx.x * GROUPS + g;
+    int64_t s_n = 0, e_n = 0;
+    if (r < n_rows) rows.get(r, s_n, e_n);
+    if (SMEM && raw_bool != nullptr) {
+        // small bool vector: every CTA packs the raw bytes itself (no separate pack kernel)
+        for (int64_t w = threadIdx.x; w < n_words; w += blockDim.x) {
+            const int64_t base = w * 32;
+            uint32_t bits = 0;
+            if ((((uintptr_t)raw_bool) & 15u) == 0 && base + 32 <= raw_n) {
+                const int4 v0 = __ldg((const int4*)(raw_bool + base)), v1 = __ldg((const int4*)(raw_bool + base) + 1);
+                const uint32_t q[8] = {(uint32_t)v0.x, (uint32_t)v0.y, (uint32_t)v0.z, (uint32_t)v0.w,
+                                       (uint32_t)v1.x, (uint32_t)v1.y, (uint32_t)v1.z, (uint32_t)v1.w};
+#pragma unroll
+                for (int i = 0; i < 8; ++i)
+#pragma unroll
+                    for (int b = 0; b < 4; ++b)
+                        if ((q[i] >> (8 * b)) & 0xffu) bits |= 1u << (i * 4 + b);
+            } else {
+                for (int b = 0; b < 32 && base + b < raw_n; ++b)
+                    if (__ldg(raw_bool + base + b)) bits |= 1u << b;
+            }
+            s_bits[w] = bits;
+        }
+        __syncthreads();
+    } else if (SMEM) {
         // TMA bulk copy (cp.async.bulk, SASS UBLKCP) of the packed spike vector into shared memory:
         // one thread issues <= 32 KB chunks against an mbarrier, everybody waits on its phase
         __shared__ uint64_t s_bar;
@@ -69,14 +101,6 @@ __global__ void __launch_bounds__(SMEM ? 1024 : 256) gather_mv_kernel(Rows rows,
         const uint32_t w = SMEM ? s_bits[idx >> 5] : __ldg(packed + (idx >> 5));
         return (w >> (idx & 31)) & 1u;
     };
-    const A w0 = HOMO ? to_acc<T>(__ldg(weights)) : A(0);
-    const int GROUPS = blockDim.x / LPR;
-    const int g = threadIdx.x / LPR, gl = threadIdx.x % LPR;
-    const int64_t row_stride = (int64_t)gridDim.x * GROUPS;
-    const int64_t row_iters = ceil_div(n_rows, row_stride);
-    int64_t r = (int64_t)blockIdx.x * GROUPS + g;
-    int64_t s_n = 0, e_n = 0;
-    if (r < n_rows) rows.get(r, s_n, e_n);
     for (int64_t it = 0; it < row_iters; ++it, r += row_stride) {
         A acc = A(0);
         int cnt = 0;
@@ -217,15 +241,21 @@ static int launch_gather_mv(const Rows& rows, const ConnArgs& c, const Events& e
     bool use_smem = vec && al16(ev.packed) && smem <= kGatherSmemMax &&
                     (double)n_rows * c.avg_row >= 4.0 * (double)n_words * kNumSM;
     if (const char* e = getenv("BE_B200_GATHER_SMEM")) use_smem = use_smem && e[0] != '0';   // A/B switch
+    Events evl = ev;
+    if (evl.raw_bool != nullptr && !use_smem) {       // only the shared-memory variant packs in-kernel
+        const int rc = pack_deferred(&evl, s);
+        if (rc) return rc;
+    }
     ProfileScope prof(s);
     if (use_smem) {
-        const int blocks = kNumSM;
+        const int blocks = (int)std::min<int64_t>(kNumSM, ceil_div(n_rows, 1024 / lpr));
 #define BE_GAS(LPR)                                                                                           \
         do {                                                                                                  \
             BE_CUDA(cudaFuncSetAttribute(gather_mv_kernel<T, HOMO, PERM, true, LPR, true, Rows>,              \
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kGatherSmemMax));  \
             gather_mv_kernel<T, HOMO, PERM, true, LPR, true, Rows><<<blocks, 1024, smem, s>>>(                \
-                rows, c.indices, (const T*)c.weights, c.perm, ev.packed, n_words, n_rows, out, ev.n_active, ev.sel_thr); \
+                rows, c.indices, (const T*)c.weights, c.perm, evl.packed, n_words, n_rows, out, evl.n_active, evl.sel_thr, \
+                evl.raw_bool, evl.raw_n);                                                                     \
         } while (0)
         switch (lpr) { case 4: BE_GAS(4); break; case 8: BE_GAS(8); break; case 16: BE_GAS(16); break; default: BE_GAS(32); }
 #undef BE_GAS
@@ -233,7 +263,8 @@ static int launch_gather_mv(const Rows& rows, const ConnArgs& c, const Events& e
         int blocks = (int)std::min<int64_t>(ceil_div(n_rows, 256 / lpr), (int64_t)kNumSM * 16);
 #define BE_GA(VEC, LPR)                                                                      \
         gather_mv_kernel<T, HOMO, PERM, VEC, LPR, false, Rows><<<blocks, 256, 0, s>>>(       \
-            rows, c.indices, (const T*)c.weights, c.perm, ev.packed, n_words, n_rows, out, ev.n_active, ev.sel_thr)
+            rows, c.indices, (const T*)c.weights, c.perm, evl.packed, n_words, n_rows, out, evl.n_active, evl.sel_thr, \
+            nullptr, 0)
 #define BE_GA2(VEC) switch (lpr) { case 4: BE_GA(VEC, 4); break; case 8: BE_GA(VEC, 8); break; \
                                    case 16: BE_GA(VEC, 16); break; default: BE_GA(VEC, 32); }
         if (vec) { BE_GA2(true) } else { BE_GA2(false) }

@@ -15,7 +15,10 @@
 //     shared-memory layout; the spike bits of the same 64 sources are expanded to bf16 0/1;
 //   * one elected thread issues tcgen05.mma.kind::f16 (M=128, N=64, K=16) with the accumulator
 //     in TMEM; tcgen05.commit on an mbarrier hands the shared-memory stage back (2 stages);
-//   * k-blocks whose 64 sources are all silent are skipped before W is even read (event-driven);
+//   * event-driven at ROW granularity: the CTA compacts the sources of its K range that fired in at
+//     least one batch column of its tile into a shared-memory list (ascending) and builds its
+//     k-blocks from 32 consecutive LIST entries, so a silent source row of W is never read (the
+//     CUDA cores place the operands in the UMMA layout themselves, so gathering rows is free);
 //   * epilogue: tcgen05.ld (32 lanes x 32 columns per warp) -> registers -> out (plain stores, or
 //     RED when the K range is split across CTAs).
 #include "common.cuh"
@@ -27,10 +30,18 @@ namespace be {
 
 constexpr int TC_BM = 128, TC_BK = 32, TC_THREADS = 256, TC_STAGES = 2;   // BN (batch tile) is a template parameter: 64 / 128 / 256
 constexpr int TC_A_PLANE = TC_BM * TC_BK * 2;            // 8 KB: one bf16 plane of the A tile
-constexpr int TC_MAX_KB = 2048;                            // k-blocks per CTA (live map in shared memory)
+constexpr int TC_CHUNK = 3072;                             // source rows compacted per pass (u16 list in shared memory; with
+                                                           // 4096 the static arrays push 3 CTAs/SM past the 196 KB carve-out and
+                                                           // leave only 28 KB of L1 for the W loads in flight)
+constexpr int TC_CHUNK_PASSES = TC_CHUNK / TC_THREADS;    // rows per thread per pass
+static_assert((TC_CHUNK_PASSES * (TC_THREADS / 32)) % 32 == 0, "the ballot words are scanned by one warp, an equal share per lane");
 constexpr int TC_ITEMS = (TC_BK / 8) * 8 / 8;            // [8 k x 16 m] load items per warp per k-block
 __host__ __device__ constexpr int tc_stage_bytes(int bn) { return 3 * TC_A_PLANE + bn * TC_BK * 2; }
 __host__ __device__ constexpr int tc_smem_bytes(int bn) { return TC_STAGES * tc_stage_bytes(bn) + 1024; }
+// three CTAs per SM (batch tile 64) must fit the 196 KB shared-memory carve-out, which leaves 60 KB of
+// L1 for the ~48 KB of W loads in flight per SM; one step up (228 KB, 28 KB of L1) measured 7 % slower
+static_assert(3 * (tc_smem_bytes(64) + (TC_CHUNK + TC_BK) * 2 + TC_CHUNK_PASSES * 8 * 6 + 64 + 1024) <= 196 * 1024,
+              "static + dynamic shared memory of dense_mm_t_tc_kernel<64> exceeds the 196 KB carve-out at 3 CTAs/SM");
 
 // canonical MN-major, no swizzle: core matrix = 8 (K) rows x 16 B (8 bf16 along MN), 128 B each.
 // A: core (mi, kk) at (kk * 16 + mi) * 128  -> SBO (MN step) = 128 B, LBO (K step) = 2048 B
@@ -132,52 +143,29 @@ dense_mm_t_tc_kernel(const float* __restrict__ W, int64_t k, int64_t m, const ui
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem_d = tmem_base_s;
 
-    // ---- live-block map (event-driven skip): one pass over this CTA's share of the packed spikes,
-    // all threads in parallel, result in shared memory; a silent k-block is then dropped before its
-    // weights are read, without any global-memory latency inside the main loop
-    __shared__ uint8_t s_live[TC_MAX_KB];
-    const int n_kb = kb_end - kb_begin;
-    for (int i = tid; i < n_kb; i += TC_THREADS) s_live[i] = 0;
-    __syncthreads();
-    for (int item = tid; item < n_kb * TC_BK; item += TC_THREADS) {
-        const int64_t kr = (int64_t)kb_begin * TC_BK + item;
-        if (kr >= k) continue;
-        uint32_t any = 0;
-#pragma unroll
-        for (int w = 0; w < WPT; ++w) {
-            const int wi = (int)(n0 >> 5) + w;
-            if (wi >= wpr) break;
-            uint32_t word = __ldg(packed + kr * wpr + wi);
-            const int64_t cbase = (int64_t)wi * 32;
-            if (cbase + 32 > n) word &= (n > cbase) ? ((1u << (n - cbase)) - 1u) : 0u;
-            any |= word;
-        }
-        if (any) s_live[item / TC_BK] = 1;
-    }
-    __syncthreads();
-    auto find_next = [&](int kb) {
-        while (kb < kb_end && !s_live[kb - kb_begin]) ++kb;
-        return kb;
-    };
+    // ---- loop-invariant per-thread coordinates ---------------------------------------------------
     // each warp streams TC_ITEMS [8 k x 16 m] patches of the tile: lane = (k8 = lane/4, quad = lane%4);
     // the spike words this thread will expand into the B tile are fetched with the same batch of loads.
-    // Per-thread offsets are loop-invariant; interior tiles (the common case) take a path without
-    // any bounds checks.
+    __shared__ uint16_t s_rows[TC_CHUNK + TC_BK];                   // active rows of the chunk (chunk-relative), 0xffff padded
+    __shared__ uint32_t s_ballot[TC_CHUNK_PASSES * (TC_THREADS / 32)];
+    __shared__ uint16_t s_off[TC_CHUNK_PASSES * (TC_THREADS / 32)];
+    __shared__ int s_total;
     constexpr int B_CELLS = TC_BK * (TC_BN / 8) / TC_THREADS;      // (k, n-octet) cells per thread
-    const int k8_l = lane_map ? (lane & 7) : (lane >> 2);
-    const int quad_l = lane_map ? (lane >> 3) : (lane & 3);
-    int64_t a_goff[TC_ITEMS];     // element offset of my float4 inside a k-block of W
+    const int k8_l = (lane_map & 1) ? (lane & 7) : (lane >> 2);
+    const int quad_l = (lane_map & 1) ? (lane >> 3) : (lane & 3);
+    // with TC_ITEMS == 4 the four patches of a warp share their source slot (kk = warp / 2) and sit
+    // 16 columns apart, so one list lookup and one 64-bit multiply address all four 128-bit loads
+    static_assert(TC_ITEMS == 4 && TC_BK == 32 && TC_THREADS == 256, "patch mapping below assumes 4 items per warp");
+    const int a_k = (warp >> 1) * 8 + k8_l;                        // my source slot inside a k-block
+    const int64_t a_col0 = m0 + (warp & 1) * 64 + quad_l * 4;     // my first output column (item i: + 16 i)
     uint32_t a_soff[TC_ITEMS];    // byte offset of my 4 elements inside an A plane
 #pragma unroll
     for (int i = 0; i < TC_ITEMS; ++i) {
-        const int item = warp * TC_ITEMS + i;              // (kk, mq) = (item / 8, item % 8)
-        const int kk = item >> 3, mq = item & 7;
-        const int m_local = mq * 16 + quad_l * 4;
-        a_goff[i] = (int64_t)(kk * 8 + k8_l) * m + m0 + m_local;
-        a_soff[i] = (uint32_t)((kk * 16 + (m_local >> 3)) * 128 + k8_l * 16 + (m_local & 7) * 2);
+        const int m_local = ((warp & 1) * 4 + i) * 16 + quad_l * 4;
+        a_soff[i] = (uint32_t)(((warp >> 1) * 16 + (m_local >> 3)) * 128 + k8_l * 16 + (m_local & 7) * 2);
     }
-    int b_k[B_CELLS], b_sh[B_CELLS];
-    int64_t b_goff[B_CELLS];
+    int b_k[B_CELLS], b_sh[B_CELLS], b_w[B_CELLS];
+    int64_t b_c0[B_CELLS];
     uint32_t b_soff[B_CELLS];
 #pragma unroll
     for (int i = 0; i < B_CELLS; ++i) {
@@ -185,105 +173,169 @@ dense_mm_t_tc_kernel(const float* __restrict__ W, int64_t k, int64_t m, const ui
         const int k_local = (cell / (8 * (TC_BN / 8))) * 8 + (cell & 7), ni = (cell >> 3) % (TC_BN / 8);
         const int64_t c0 = n0 + ni * 8;
         b_k[i] = k_local;
+        b_c0[i] = c0;
         b_sh[i] = (int)(c0 & 31);
-        b_goff[i] = (int64_t)k_local * wpr + (c0 >> 5);
+        b_w[i] = (int)(c0 >> 5);
         b_soff[i] = (uint32_t)(((k_local >> 3) * (TC_BN / 8) + ni) * 128 + (k_local & 7) * 16);
     }
-    const bool m_interior = (m0 + TC_BM <= m);
-    const bool n_interior = (n0 + TC_BN <= n);
-    auto load_tile = [&](int kb, float4 (&wv)[TC_ITEMS], uint32_t (&bw)[B_CELLS]) {
-        const int64_t k0 = (int64_t)kb * TC_BK;
-        const float* wbase = W + k0 * m;
-        const uint32_t* pbase = packed + k0 * wpr;
-        if (m_interior && n_interior && k0 + TC_BK <= k) {
-#pragma unroll
-            for (int i = 0; i < TC_ITEMS; ++i) wv[i] = __ldg(reinterpret_cast<const float4*>(wbase + a_goff[i]));
-#pragma unroll
-            for (int i = 0; i < B_CELLS; ++i) bw[i] = (__ldg(pbase + b_goff[i]) >> b_sh[i]) & 0xffu;
-            return;
-        }
-#pragma unroll
-        for (int i = 0; i < TC_ITEMS; ++i) {
-            const int item = warp * TC_ITEMS + i;
-            const int64_t kr = k0 + (item >> 3) * 8 + k8_l;
-            const int64_t mc = m0 + (item & 7) * 16 + quad_l * 4;
-            float t[4];
-#pragma unroll
-            for (int q = 0; q < 4; ++q) t[q] = (kr < k && mc + q < m) ? __ldg(W + kr * m + mc + q) : 0.0f;
-            wv[i] = make_float4(t[0], t[1], t[2], t[3]);
-        }
-#pragma unroll
-        for (int i = 0; i < B_CELLS; ++i) {
-            const int64_t kr = k0 + b_k[i];
-            const int64_t c0 = n0 + (int64_t)(((tid + i * TC_THREADS) >> 3) % (TC_BN / 8)) * 8;
-            uint32_t bits = 0;
-            if (kr < k && c0 < n) {
-                bits = (__ldg(pbase + b_goff[i]) >> b_sh[i]) & 0xffu;
-                if (c0 + 8 > n) bits &= (1u << (n - c0)) - 1u;
-            }
-            bw[i] = bits;
-        }
-    };
+    const bool mn_interior = (m0 + TC_BM <= m) && (n0 + TC_BN <= n);
+    const int64_t row_begin = (int64_t)kb_begin * TC_BK;
+    const int64_t row_end = min(k, (int64_t)kb_end * TC_BK);
 
     int n_issued = 0;      // k-blocks that actually reached the tensor core (uniform across the CTA)
-    float4 cur[TC_ITEMS], nxt[TC_ITEMS];
-    uint32_t cur_b[B_CELLS], nxt_b[B_CELLS];
-    int kb = find_next(kb_begin);
-    if (kb < kb_end) load_tile(kb, cur, cur_b);
-    while (kb < kb_end) {
-        // software pipeline: the next live block's weights are in flight while this one is
-        // converted, staged and multiplied
-        const int kb_next = find_next(kb + 1);
-        if (kb_next < kb_end) load_tile(kb_next, nxt, nxt_b);
-
-        const int stage = n_issued % TC_STAGES;
-        uint8_t* sA = smem + stage * TC_STAGE_BYTES;
-        uint8_t* sB = sA + 3 * TC_A_PLANE;
-        if (n_issued >= TC_STAGES) mbar_wait(&empty_bar[stage], ((n_issued / TC_STAGES) - 1) & 1);
-        // ---- A: split into bf16 hi/mid/lo planes, MN-major core matrices ------------------------
+    for (int64_t c_begin = row_begin; c_begin < row_end; c_begin += TC_CHUNK) {
+        const int c_rows = (int)min((int64_t)TC_CHUNK, row_end - c_begin);
+        const float* Wc = W + c_begin * m;
+        const uint32_t* pc = packed + c_begin * wpr;
+        // ---- ordered compaction of the chunk's active rows (active = fired in a column of this tile);
+        // all spike words are requested before the first ballot so the passes share one round trip
+        uint32_t anyv[TC_CHUNK_PASSES];
 #pragma unroll
-        for (int i = 0; i < TC_ITEMS; ++i) {
-            // error-free 3-way split, two elements per cvt.rn.bf16x2.f32
-            uint32_t hi[2], mid[2], lo[2];
-            split3(cur[i].x, cur[i].y, hi[0], mid[0], lo[0]);
-            split3(cur[i].z, cur[i].w, hi[1], mid[1], lo[1]);
-            *reinterpret_cast<uint2*>(sA + a_soff[i]) = make_uint2(hi[0], hi[1]);
-            *reinterpret_cast<uint2*>(sA + TC_A_PLANE + a_soff[i]) = make_uint2(mid[0], mid[1]);
-            *reinterpret_cast<uint2*>(sA + 2 * TC_A_PLANE + a_soff[i]) = make_uint2(lo[0], lo[1]);
-        }
-        // ---- B: 0/1 bf16 from the prefetched spike bits ---------------------------------------------
+        for (int j = 0; j < TC_CHUNK_PASSES; ++j) {
+            const int r = j * TC_THREADS + tid;
+            uint32_t any = 0;
+            if (r < c_rows) {
 #pragma unroll
-        for (int i = 0; i < B_CELLS; ++i) {
-            const uint32_t bits = cur_b[i];
-            uint32_t v[4];
-#pragma unroll
-            for (int q = 0; q < 4; ++q)
-                v[q] = ((bits >> (2 * q)) & 1u ? 0x3f80u : 0u) | ((bits >> (2 * q + 1)) & 1u ? 0x3f800000u : 0u);
-            *reinterpret_cast<uint4*>(sB + b_soff[i]) = make_uint4(v[0], v[1], v[2], v[3]);
-        }
-        // generic-proxy writes -> visible to the tensor core (async proxy)
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-        __syncthreads();
-        if (tid == 0) {
-            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            const uint32_t a0 = smem_u32(sA), b0 = smem_u32(sB);
-#pragma unroll
-            for (int ks = 0; ks < TC_BK / 16; ++ks) {
-                const uint64_t bd = umma_desc(b0 + ks * 2 * TC_B_LBO, TC_B_LBO, TC_B_SBO);
-#pragma unroll
-                for (int p = 0; p < 3; ++p) {
-                    const uint64_t ad = umma_desc(a0 + p * TC_A_PLANE + ks * 2 * TC_A_LBO, TC_A_LBO, TC_A_SBO);
-                    umma_bf16(tmem_d, ad, bd, tc_idesc(TC_BN), (n_issued > 0 || ks > 0 || p > 0) ? 1u : 0u);
+                for (int w = 0; w < WPT; ++w) {
+                    const int wi = (int)(n0 >> 5) + w;
+                    if (wi < wpr) {
+                        uint32_t word = __ldg(pc + (int64_t)r * wpr + wi);
+                        const int64_t cbase = (int64_t)wi * 32;
+                        if (cbase + 32 > n) word &= (n > cbase) ? ((1u << (n - cbase)) - 1u) : 0u;
+                        any |= word;
+                    }
                 }
             }
-            umma_commit(&empty_bar[stage]);     // arrives when these MMAs have finished reading smem
+            anyv[j] = any;
         }
-        ++n_issued;
-        kb = kb_next;
 #pragma unroll
-        for (int i = 0; i < TC_ITEMS; ++i) cur[i] = nxt[i];
+        for (int j = 0; j < TC_CHUNK_PASSES; ++j) {
+            const uint32_t bal = __ballot_sync(0xffffffffu, anyv[j] != 0);
+            if (lane == 0) s_ballot[j * (TC_THREADS / 32) + warp] = bal;
+        }
+        __syncthreads();
+        if (warp == 0) {
+            constexpr int PER = TC_CHUNK_PASSES * (TC_THREADS / 32) / 32;     // ballot words per lane
+            int c[PER], sum = 0;
 #pragma unroll
-        for (int i = 0; i < B_CELLS; ++i) cur_b[i] = nxt_b[i];
+            for (int q = 0; q < PER; ++q) { c[q] = __popc(s_ballot[lane * PER + q]); sum += c[q]; }
+            int incl = sum;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const int t = __shfl_up_sync(0xffffffffu, incl, d);
+                if (lane >= d) incl += t;
+            }
+            int run = incl - sum;
+#pragma unroll
+            for (int q = 0; q < PER; ++q) { s_off[lane * PER + q] = (uint16_t)run; run += c[q]; }
+            if (lane == 31) s_total = incl;
+        }
+        __syncthreads();
+        const int total = s_total;
+#pragma unroll
+        for (int j = 0; j < TC_CHUNK_PASSES; ++j) {
+            const uint32_t bal = s_ballot[j * (TC_THREADS / 32) + warp];
+            if ((bal >> lane) & 1u)
+                s_rows[s_off[j * (TC_THREADS / 32) + warp] + __popc(bal & ((1u << lane) - 1u))] = (uint16_t)(j * TC_THREADS + tid);
+        }
+        if (tid < TC_BK) s_rows[total + tid] = 0xffffu;
+        __syncthreads();
+        const int n_vkb = (total + TC_BK - 1) / TC_BK;
+
+        auto load_tile = [&](int vkb, float4 (&wv)[TC_ITEMS], uint32_t (&bw)[B_CELLS]) {
+            const uint16_t* rows = s_rows + vkb * TC_BK;
+            if (mn_interior && (vkb + 1) * TC_BK <= total) {
+                const float4* wrow = reinterpret_cast<const float4*>(Wc + (int64_t)rows[a_k] * m + a_col0);
+                // plain __ldg: ld.global.nc.L1::no_allocate measured 4 % slower here
+#pragma unroll
+                for (int i = 0; i < TC_ITEMS; ++i) wv[i] = __ldg(wrow + i * 4);
+#pragma unroll
+                for (int i = 0; i < B_CELLS; ++i)
+                    bw[i] = (__ldg(pc + (int64_t)rows[b_k[i]] * wpr + b_w[i]) >> b_sh[i]) & 0xffu;
+                return;
+            }
+            const uint32_t rid_a = rows[a_k];
+#pragma unroll
+            for (int i = 0; i < TC_ITEMS; ++i) {
+                const int64_t col = a_col0 + i * 16;
+                float t[4];
+#pragma unroll
+                for (int q = 0; q < 4; ++q)
+                    t[q] = (rid_a != 0xffffu && col + q < m) ? __ldg(Wc + (int64_t)rid_a * m + col + q) : 0.0f;
+                wv[i] = make_float4(t[0], t[1], t[2], t[3]);
+            }
+#pragma unroll
+            for (int i = 0; i < B_CELLS; ++i) {
+                const uint32_t rid = rows[b_k[i]];
+                uint32_t bits = 0;
+                if (rid != 0xffffu && b_c0[i] < n) {
+                    bits = (__ldg(pc + (int64_t)rid * wpr + b_w[i]) >> b_sh[i]) & 0xffu;
+                    if (b_c0[i] + 8 > n) bits &= (1u << (n - b_c0[i])) - 1u;
+                }
+                bw[i] = bits;
+            }
+        };
+
+        // one k-block: request block vkb + 1 into (nxt, nxt_b), then convert / stage / multiply block
+        // vkb from (cur, cur_b).  The caller alternates two explicit register sets, so the loads of
+        // the next block are always issued BEFORE the wait on the current one (two blocks in flight)
+        auto step = [&](int vkb, float4 (&cur)[TC_ITEMS], uint32_t (&cur_b)[B_CELLS], float4 (&nxt)[TC_ITEMS],
+                        uint32_t (&nxt_b)[B_CELLS]) {
+            if (vkb + 1 < n_vkb) load_tile(vkb + 1, nxt, nxt_b);
+
+            const int stage = n_issued % TC_STAGES;
+            uint8_t* sA = smem + stage * TC_STAGE_BYTES;
+            uint8_t* sB = sA + 3 * TC_A_PLANE;
+            if (n_issued >= TC_STAGES) mbar_wait(&empty_bar[stage], ((n_issued / TC_STAGES) - 1) & 1);
+            // ---- A: split into bf16 hi/mid/lo planes, MN-major core matrices --------------------
+#pragma unroll
+            for (int i = 0; i < TC_ITEMS; ++i) {
+                // error-free 3-way split, two elements per cvt.rn.bf16x2.f32
+                uint32_t hi[2], mid[2], lo[2];
+                split3(cur[i].x, cur[i].y, hi[0], mid[0], lo[0]);
+                split3(cur[i].z, cur[i].w, hi[1], mid[1], lo[1]);
+                *reinterpret_cast<uint2*>(sA + a_soff[i]) = make_uint2(hi[0], hi[1]);
+                *reinterpret_cast<uint2*>(sA + TC_A_PLANE + a_soff[i]) = make_uint2(mid[0], mid[1]);
+                *reinterpret_cast<uint2*>(sA + 2 * TC_A_PLANE + a_soff[i]) = make_uint2(lo[0], lo[1]);
+            }
+            // ---- B: 0/1 bf16 from the prefetched spike bits -----------------------------------------
+#pragma unroll
+            for (int i = 0; i < B_CELLS; ++i) {
+                const uint32_t bits = cur_b[i];
+                uint32_t v[4];
+#pragma unroll
+                for (int q = 0; q < 4; ++q)
+                    v[q] = ((bits >> (2 * q)) & 1u ? 0x3f80u : 0u) | ((bits >> (2 * q + 1)) & 1u ? 0x3f800000u : 0u);
+                *reinterpret_cast<uint4*>(sB + b_soff[i]) = make_uint4(v[0], v[1], v[2], v[3]);
+            }
+            // generic-proxy writes -> visible to the tensor core (async proxy)
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            __syncthreads();
+            if (tid == 0) {
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                const uint32_t a0 = smem_u32(sA), b0 = smem_u32(sB);
+#pragma unroll
+                for (int ks = 0; ks < TC_BK / 16; ++ks) {
+                    const uint64_t bd = umma_desc(b0 + ks * 2 * TC_B_LBO, TC_B_LBO, TC_B_SBO);
+#pragma unroll
+                    for (int p = 0; p < 3; ++p) {
+                        const uint64_t ad = umma_desc(a0 + p * TC_A_PLANE + ks * 2 * TC_A_LBO, TC_A_LBO, TC_A_SBO);
+                        umma_bf16(tmem_d, ad, bd, tc_idesc(TC_BN), (n_issued > 0 || ks > 0 || p > 0) ? 1u : 0u);
+                    }
+                }
+                umma_commit(&empty_bar[stage]);     // arrives when these MMAs have finished reading smem
+            }
+            ++n_issued;
+        };
+        float4 ra[TC_ITEMS], rb[TC_ITEMS];
+        uint32_t ra_b[B_CELLS], rb_b[B_CELLS];
+        if (n_vkb > 0) load_tile(0, ra, ra_b);
+        for (int vkb = 0; vkb < n_vkb; vkb += 2) {
+            step(vkb, ra, ra_b, rb, rb_b);
+            if (vkb + 1 < n_vkb) step(vkb + 1, rb, rb_b, ra, ra_b);
+        }
+        // every thread is past the last block's __syncthreads, i.e. done reading s_rows: the next
+        // chunk may overwrite the lists
     }
 
     // ---- drain + epilogue ---------------------------------------------------------------------
@@ -344,7 +396,6 @@ int launch_dense_mm_t_tc(const float* W, int64_t k, int64_t m, const uint32_t* p
     const int total_kb = (int)ceil_div(k, TC_BK);
     const int64_t tiles = ceil_div(m, TC_BM) * ceil_div(n, bn);
     int split_k = (int)std::max<int64_t>(1, std::min<int64_t>({(int64_t)total_kb, (6 * kNumSM) / std::max<int64_t>(tiles, 1), (int64_t)32}));
-    split_k = std::max(split_k, (int)ceil_div(std::max(total_kb, 1), TC_MAX_KB));
     const int kb_per_split = (int)ceil_div(std::max(total_kb, 1), split_k);
     split_k = (int)ceil_div(std::max(total_kb, 1), kb_per_split);
     if (split_k > 1) BE_CUDA(cudaMemsetAsync(out, 0, (size_t)(m * n) * sizeof(float), s));

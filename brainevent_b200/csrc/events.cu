@@ -478,12 +478,24 @@ int prepare_events_1d(const void* spikes, const void* aux, int spk_kind, int64_t
         return compact_1d_any(spikes, spk_kind, n, nonzero, ws, ws.active_ids, nullptr,
                               need_packed ? ws.packed : nullptr, s, zero_ptr, zero_bytes, ordered_ids);
     if (need_packed && n > 0) {
+        if (spk_kind == BE_B200_SPK_BOOL && ev->defer_pack_ok && n <= kDeferPackMax) {
+            ev->raw_bool = (const uint8_t*)spikes;      // nonzero byte == active either way for bool
+            ev->raw_n = n;
+            return BE_B200_OK;
+        }
         if (spk_kind == BE_B200_SPK_BOOL) return launch_bitpack<BE_B200_SPK_BOOL>(spikes, n, nonzero, ws.packed, s);
         if (spk_kind == BE_B200_SPK_F32) return launch_bitpack<BE_B200_SPK_F32>(spikes, n, nonzero, ws.packed, s);
         set_error("unsupported event kind %d", spk_kind);
         return BE_B200_EINVAL;
     }
     return BE_B200_OK;
+}
+
+int pack_deferred(Events* ev, cudaStream_t s) {
+    if (ev->raw_bool == nullptr) return BE_B200_OK;
+    const void* raw = ev->raw_bool;
+    ev->raw_bool = nullptr;
+    return launch_bitpack<BE_B200_SPK_BOOL>(raw, ev->raw_n, false, const_cast<uint32_t*>(ev->packed), s);
 }
 
 int prepare_events_2d(const void* spikes, const void* aux, int spk_kind, int64_t n, int64_t batch,

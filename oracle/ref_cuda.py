@@ -3,7 +3,7 @@
 
 Nothing under `brainevent_b200/` imports this module.  It exists so that (1) the GPU parity tests
 have a second oracle that is the reference itself (modulo atomic ordering), and (2)
-`tools/bench_vs_reference_cuda.py` can time "the reference's kernels recompiled for sm_100a" beside
+`tests/bench_vs_reference_cuda.py` can time "the reference's kernels recompiled for sm_100a" beside
 the new ones on the same B200, same inputs.  Each function mirrors the Python side of the
 reference's kernel generator for that op (cited per function): same operands, same attributes.
 """

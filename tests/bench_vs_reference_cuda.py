@@ -4,7 +4,7 @@ buffers, same spike vectors, both replayed from a CUDA graph of POOL calls so ho
 is out of the picture.  Prints one JSON line per case: per-call time of each side, the ratio, and the
 largest output difference (a GPU-side parity check against the reference itself).
 
-    python tools/bench_vs_reference_cuda.py [case ...]     cases: fcn csr spmm jits jitn jitu dense compact
+    python tests/bench_vs_reference_cuda.py [case ...]     cases: fcn csr spmm jits jitn jitu dense compact
 """
 import json
 import os
