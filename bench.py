@@ -31,6 +31,7 @@ FCN_NEURONS_PER_GPU = 1_250_016   # multiple of 32 (packed all-gather slots), ~1
 FCN_CONN = 1000
 RATE = 0.01
 POOL = 16                          # distinct spike vectors cycled through the timesteps
+DEFAULT_EXCHANGE = "p2p"           # spike exchange at N > 1: "nccl" (all_gather_into_tensor) or "p2p" (csrc/exchange.cu); env BE_B200_EXCHANGE overrides
 
 
 def peaks():
@@ -120,7 +121,7 @@ class FcnWeak(Workload):
     dominant_kernel = "scatter_mv_kernel"
 
     def __init__(self, torch, be, rank, world, device, neurons_per_gpu=FCN_NEURONS_PER_GPU, n_conn=FCN_CONN, rate=RATE,
-                 emulate_world=0):
+                 emulate_world=0, exchange=None):
         from brainevent_b200 import dist as bd
         self.torch, self.be, self.world, self.rank = torch, be, world, rank
         self.emulate = emulate_world      # profile one rank's shard of an `emulate_world`-GPU run on a single GPU
@@ -137,10 +138,11 @@ class FcnWeak(Workload):
         self.pool = spike_pool(torch, self.n_local, rate, 99 + rank, device)     # spikes of the neurons I own
         self.exchange_kind = "nccl all_gather"
         self.x = None
-        if world > 1 and os.environ.get("BE_B200_EXCHANGE", "nccl") == "p2p":
+        exchange = exchange or os.environ.get("BE_B200_EXCHANGE", DEFAULT_EXCHANGE)
+        if world > 1 and exchange == "p2p":
             try:
                 self.x = bd.P2PSpikeExchange(self.n_total, device=device)
-                self.exchange_kind = "fused pack + NVLink peer-store all-gather (exchange.cu)"
+                self.exchange_kind = "fused bit-pack + NVLink peer-memory all-gather (csrc/exchange.cu: pack into the own symmetric buffer, flag the peers, pull their words)"
             except Exception as e:  # pragma: no cover - symmetric memory unavailable: NCCL path
                 sys.stderr.write(f"[bench] P2P exchange unavailable ({type(e).__name__}: {e}); using NCCL\n")
         if self.x is None:
@@ -579,6 +581,18 @@ def main():
 
     sampler = ClockSampler(local_rank) if rank == 0 else None
     res = measure_workload(torch, dist, L, wl, K, W, T, world, peak, peak_src, sampler, not args.no_graph)
+    if world > 1 and hasattr(getattr(wl, "x", None), "timed_out"):
+        # the peer-memory exchange bounds its flag waits; a wait that gave up means a peer never
+        # published (results would be stale): fall back to NCCL on every rank and measure again
+        bad = torch.tensor([int(wl.x.timed_out())], device=device)
+        dist.all_reduce(bad, op=dist.ReduceOp.MAX)
+        if int(bad.item()):
+            sys.stderr.write("[bench] peer-memory exchange timed out; re-measuring with the NCCL all-gather\n")
+            del wl
+            torch.cuda.empty_cache()
+            wl = FcnWeak(torch, be, rank, world, device, emulate_world=args.emulate_world, exchange="nccl")
+            sampler = ClockSampler(local_rank) if rank == 0 else None
+            res = measure_workload(torch, dist, L, wl, K, W, T, world, peak, peak_src, sampler, not args.no_graph)
 
     # ---- e2e: host buffers in, host buffers out, every timestep -------------------------------
     e2e = None

@@ -94,7 +94,10 @@ __global__ void __launch_bounds__(256) pack_publish_kernel(const void* __restric
     }
     __syncthreads();                       // this CTA's peer stores are ordered before thread 0's fence
     if (threadIdx.x == 0) {
-        __threadfence_system();            // cumulative: publishes the whole CTA's stores at system scope
+        // gpu-scope fence only: the words live in THIS GPU's memory, the `done` counter orders every
+        // CTA's words before the last CTA's single system-scope fence below (release cumulativity),
+        // and peers read them through this GPU's L2.  A system fence per CTA cost ~5 us of the pack.
+        __threadfence();
         const uint32_t prev = atomicAdd(&ctl->done, 1u);
         if (prev == gridDim.x - 1) {
             ctl->stamp[1] = gtimer();
@@ -126,9 +129,23 @@ __global__ void __launch_bounds__(256) wait_copy_kernel(const uint32_t* __restri
     if (blockIdx.x == 0 && threadIdx.x == 0) ctl->stamp[4] = gtimer();
     const int64_t n = words_per_rank * world;
     const int64_t half = (int64_t)(t & 1u) * n;
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
-        const int p = (int)(i / words_per_rank);
-        dst[i] = ld_relaxed_sys(peer_bufs[p] + half + i);     // remote (NVLink) read; ordered after the flag acquire
+    // remote (NVLink) reads, ordered after the flag acquire.  A remote load is a ~2 us round trip, so
+    // all of a thread's words are requested before the first one is stored (with one load per loop
+    // trip the copy of 10 M bits took 14.5 us = 8 serial round trips; stamps [4] -> [5])
+    constexpr int U = 8;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i0 < n; i0 += stride * U) {
+        uint32_t v[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int64_t i = i0 + u * stride;
+            if (i < n) v[u] = ld_relaxed_sys(peer_bufs[(int)(i / words_per_rank)] + half + i);
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int64_t i = i0 + u * stride;
+            if (i < n) dst[i] = v[u];
+        }
     }
     if (blockIdx.x == gridDim.x - 1 && threadIdx.x == 0) ctl->stamp[5] = gtimer();
 }
