@@ -248,12 +248,15 @@ static int launch_gather_mv(const Rows& rows, const ConnArgs& c, const Events& e
     }
     ProfileScope prof(s);
     if (use_smem) {
-        const int blocks = (int)std::min<int64_t>(kNumSM, ceil_div(n_rows, 1024 / lpr));
+        // small problems (a few thousand rows): 256-thread CTAs spread over more SMs instead of a
+        // handful of 1024-thread ones -- the call is launch/latency-bound there
+        const int threads = (n_rows * lpr <= (int64_t)kNumSM * 256) ? 256 : 1024;
+        const int blocks = (int)std::min<int64_t>(kNumSM, ceil_div(n_rows, threads / lpr));
 #define BE_GAS(LPR)                                                                                           \
         do {                                                                                                  \
             BE_CUDA(cudaFuncSetAttribute(gather_mv_kernel<T, HOMO, PERM, true, LPR, true, Rows>,              \
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kGatherSmemMax));  \
-            gather_mv_kernel<T, HOMO, PERM, true, LPR, true, Rows><<<blocks, 1024, smem, s>>>(                \
+            gather_mv_kernel<T, HOMO, PERM, true, LPR, true, Rows><<<blocks, threads, smem, s>>>(                \
                 rows, c.indices, (const T*)c.weights, c.perm, evl.packed, n_words, n_rows, out, evl.n_active, evl.sel_thr, \
                 evl.raw_bool, evl.raw_n);                                                                     \
         } while (0)
