@@ -71,6 +71,14 @@ __global__ void __launch_bounds__(256) jit_mv_gather_kernel(JitParams jp, const 
 // mv scatter (corder=False): for every active row, out[j] += w(row,j) for j in C(row)
 // one warp per (active row, chunk) task.  [col_begin, col_end) is the owned output window.
 // ------------------------------------------------------------------------------------------
+// Normal weights: the central branch of the inverse CDF is evaluated inline; a draw that falls in a
+// tail (4.85 %) is parked as (row, column) in a per-warp shared-memory queue and evaluated later by
+// converged lanes.  Evaluating it in place made the warp run the tail path (logf, sqrt, two Horner
+// chains, a division) in ~2 of 3 walk iterations for the sake of one lane.  Scatter order is free
+// (reductions), so the result is the same sum.
+constexpr int kTailCap = 128;       // entries per warp
+constexpr int kTailFlush = 48;      // flush at a task boundary once this many are waiting
+
 template <typename T, int KIND>
 __global__ void __launch_bounds__(256) jit_mv_scatter_kernel(JitParams jp, const int32_t* __restrict__ ids,
                                                              const int* __restrict__ n_active_ptr,
@@ -79,12 +87,32 @@ __global__ void __launch_bounds__(256) jit_mv_scatter_kernel(JitParams jp, const
                                                              int64_t col_begin, int64_t col_end,
                                                              T* __restrict__ out) {
     using A = typename Acc<T>::type;
+    constexpr bool DEFER = (KIND == BE_B200_JIT_NORMAL);
     A p0, p1; uint32_t cl, seed;
     load_params<T, KIND>(jp, p0, p1, cl, seed);
     const uint32_t lane = threadIdx.x & 31;
+    const int wib = threadIdx.x >> 5;
+    __shared__ uint2 s_tail[DEFER ? 8 : 1][DEFER ? kTailCap : 1];
+    __shared__ int s_ntail[8];
+    if (DEFER) {
+        if (lane == 0) s_ntail[wib] = 0;
+        __syncwarp();
+    }
+    auto flush_tails = [&]() {       // converged: every lane of the warp calls it
+        __syncwarp();
+        const int n = min(s_ntail[wib], kTailCap);
+        for (int i = lane; i < n; i += 32) {
+            const uint2 e = s_tail[DEFER ? wib : 0][DEFER ? i : 0];
+            const float u = normal01_clamp_u(hash_uniform01(seed, e.x, e.y));
+            red_add(out + ((int64_t)e.y - col_begin), p0 + (A)normal01_tail(u) * p1);
+        }
+        __syncwarp();
+        if (lane == 0) s_ntail[wib] = 0;
+        __syncwarp();
+    };
     const int n_chunks = (int)ceil_div(out_len, chunk_size);
     const int64_t n_tasks = (int64_t)(*n_active_ptr) * n_chunks;
-    for (int64_t t = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5); t < n_tasks; t += (int64_t)gridDim.x * 8) {
+    for (int64_t t = (int64_t)blockIdx.x * 8 + wib; t < n_tasks; t += (int64_t)gridDim.x * 8) {
         const int64_t a = t / n_chunks;
         const int c = (int)(t - a * n_chunks);
         const int64_t r = __ldg(ids + a);
@@ -100,11 +128,29 @@ __global__ void __launch_bounds__(256) jit_mv_scatter_kernel(JitParams jp, const
         const int64_t b0 = cs + lane;
         while (q < qmax) {
             const int64_t j = b0 + 32 * (int64_t)q;
-            if (j >= col_begin) red_add(out + (j - col_begin), jit_weight<KIND, A>(p0, p1, seed, row, (uint32_t)j));
+            if (j >= col_begin) {
+                if (DEFER) {
+                    const float u = normal01_clamp_u(hash_uniform01(seed, row, (uint32_t)j));
+                    if (!normal01_is_tail(u)) {
+                        red_add(out + (j - col_begin), p0 + (A)normal01_central(u) * p1);
+                    } else {
+                        const int slot = atomicAdd(&s_ntail[wib], 1);
+                        if (slot < kTailCap) s_tail[DEFER ? wib : 0][DEFER ? slot : 0] = make_uint2(row, (uint32_t)j);
+                        else red_add(out + (j - col_begin), p0 + (A)normal01_tail(u) * p1);   // queue full: in place
+                    }
+                } else {
+                    red_add(out + (j - col_begin), jit_weight<KIND, A>(p0, p1, seed, row, (uint32_t)j));
+                }
+            }
             s = rng_next(s);
             q += 1U + __umulhi(s, cl - 1U);
         }
+        if (DEFER) {
+            __syncwarp();
+            if (s_ntail[wib] >= kTailFlush) flush_tails();
+        }
     }
+    if (DEFER) flush_tails();
 }
 
 // ------------------------------------------------------------------------------------------
@@ -273,12 +319,32 @@ __global__ void __launch_bounds__(256) jit_mv_val_scatter_kernel(JitParams jp, c
                                                                  int64_t vec_len, int64_t out_len,
                                                                  int64_t chunk_size, T* __restrict__ out) {
     using A = typename Acc<T>::type;
+    constexpr bool DEFER = (KIND == BE_B200_JIT_NORMAL);     // tails of the inverse CDF: see jit_mv_scatter_kernel
     A p0, p1; uint32_t cl, seed;
     load_params<T, KIND>(jp, p0, p1, cl, seed);
     const uint32_t lane = threadIdx.x & 31;
+    const int wib = threadIdx.x >> 5;
+    __shared__ uint2 s_tail[DEFER ? 8 : 1][DEFER ? kTailCap : 1];
+    __shared__ int s_ntail[8];
+    if (DEFER) {
+        if (lane == 0) s_ntail[wib] = 0;
+        __syncwarp();
+    }
+    auto flush_tails = [&]() {       // converged: every lane of the warp calls it
+        __syncwarp();
+        const int n = min(s_ntail[wib], kTailCap);
+        for (int i = lane; i < n; i += 32) {
+            const uint2 e = s_tail[DEFER ? wib : 0][DEFER ? i : 0];
+            const float u = normal01_clamp_u(hash_uniform01(seed, e.x, e.y));
+            red_add(out + e.y, (p0 + (A)normal01_tail(u) * p1) * to_acc<T>(__ldg(x + e.x)));
+        }
+        __syncwarp();
+        if (lane == 0) s_ntail[wib] = 0;
+        __syncwarp();
+    };
     const int n_chunks = (int)ceil_div(out_len, chunk_size);
     const int64_t n_tasks = vec_len * n_chunks;
-    for (int64_t t = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5); t < n_tasks; t += (int64_t)gridDim.x * 8) {
+    for (int64_t t = (int64_t)blockIdx.x * 8 + wib; t < n_tasks; t += (int64_t)gridDim.x * 8) {
         const int64_t r = t / n_chunks;
         const int c = (int)(t - r * n_chunks);
         const A xv = to_acc<T>(__ldg(x + r));
@@ -292,11 +358,27 @@ __global__ void __launch_bounds__(256) jit_mv_val_scatter_kernel(JitParams jp, c
         const int64_t b0 = cs + lane;
         while (q < qmax) {
             const int64_t j = b0 + 32 * (int64_t)q;
-            red_add(out + j, jit_weight<KIND, A>(p0, p1, seed, row, (uint32_t)j) * xv);
+            if (DEFER) {
+                const float u = normal01_clamp_u(hash_uniform01(seed, row, (uint32_t)j));
+                if (!normal01_is_tail(u)) {
+                    red_add(out + j, (p0 + (A)normal01_central(u) * p1) * xv);
+                } else {
+                    const int slot = atomicAdd(&s_ntail[wib], 1);
+                    if (slot < kTailCap) s_tail[DEFER ? wib : 0][DEFER ? slot : 0] = make_uint2(row, (uint32_t)j);
+                    else red_add(out + j, (p0 + (A)normal01_tail(u) * p1) * xv);   // queue full: in place
+                }
+            } else {
+                red_add(out + j, jit_weight<KIND, A>(p0, p1, seed, row, (uint32_t)j) * xv);
+            }
             s = rng_next(s);
             q += 1U + __umulhi(s, cl - 1U);
         }
+        if (DEFER) {
+            __syncwarp();
+            if (s_ntail[wib] >= kTailFlush) flush_tails();
+        }
     }
+    if (DEFER) flush_tails();
 }
 
 // mm: lanes 0..3 walk the four residue streams of one (row, chunk), every connection is broadcast

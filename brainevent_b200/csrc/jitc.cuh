@@ -40,30 +40,37 @@ __device__ __forceinline__ float hash_uniform01(uint32_t seed, uint32_t row, uin
 }
 // Horner steps with explicit rounding (no FMA contraction): bit-identical to strict IEEE f32.
 __device__ __forceinline__ float hs(float acc, float x, float c) { return __fadd_rn(__fmul_rn(acc, x), c); }
-__device__ __forceinline__ float hash_normal01(uint32_t seed, uint32_t row, uint32_t col) {
-    float u = hash_uniform01(seed, row, col);
-    u = fmaxf(fminf(u, 1.0f - 1e-10f), 1e-10f);
+// Acklam's inverse normal CDF in three pieces so that callers can evaluate the common central branch
+// inline and hand the rare tails (4.85 % of the draws; logf + sqrt + two more Horner chains) to
+// converged lanes.  hash_normal01 composes them exactly as before: same operations, same roundings.
+__device__ __forceinline__ float normal01_clamp_u(float u) { return fmaxf(fminf(u, 1.0f - 1e-10f), 1e-10f); }
+__device__ __forceinline__ bool normal01_is_tail(float u) { return u < 0.02425f || u > 0.97575f; }
+__device__ __forceinline__ float normal01_tail(float u) {
+    const float c1 = -0.007784894f, c2 = -0.32239646f, c3 = -2.4007583f, c4 = -2.5497325f,
+                c5 = 4.3746641f, c6 = 2.9381640f;
+    const float d1 = 0.007784696f, d2 = 0.32246713f, d3 = 2.4451342f, d4 = 3.7544087f;
+    const bool lower = u < 0.02425f;
+    const float t = lower ? u : __fsub_rn(1.0f, u);
+    const float v = __fsqrt_rn(__fmul_rn(-2.0f, logf(t)));
+    const float num = hs(hs(hs(hs(hs(c1, v, c2), v, c3), v, c4), v, c5), v, c6);
+    const float den = hs(hs(hs(hs(d1, v, d2), v, d3), v, d4), v, 1.0f);
+    const float z = __fdiv_rn(num, den);
+    return lower ? -z : z;
+}
+__device__ __forceinline__ float normal01_central(float u) {
     const float a1 = -39.696830f, a2 = 220.94609f, a3 = -275.92851f, a4 = 138.35775f,
                 a5 = -30.664799f, a6 = 2.5066283f;
     const float b1 = -54.476099f, b2 = 161.58584f, b3 = -155.69898f, b4 = 66.801312f,
                 b5 = -13.280681f;
-    const float c1 = -0.007784894f, c2 = -0.32239646f, c3 = -2.4007583f, c4 = -2.5497325f,
-                c5 = 4.3746641f, c6 = 2.9381640f;
-    const float d1 = 0.007784696f, d2 = 0.32246713f, d3 = 2.4451342f, d4 = 3.7544087f;
-    if (u < 0.02425f || u > 0.97575f) {
-        const bool lower = u < 0.02425f;
-        const float t = lower ? u : __fsub_rn(1.0f, u);
-        const float v = __fsqrt_rn(__fmul_rn(-2.0f, logf(t)));
-        const float num = hs(hs(hs(hs(hs(c1, v, c2), v, c3), v, c4), v, c5), v, c6);
-        const float den = hs(hs(hs(hs(d1, v, d2), v, d3), v, d4), v, 1.0f);
-        const float z = __fdiv_rn(num, den);
-        return lower ? -z : z;
-    }
     const float v = __fsub_rn(u, 0.5f);
     const float r = __fmul_rn(v, v);
     const float num = __fmul_rn(hs(hs(hs(hs(hs(a1, r, a2), r, a3), r, a4), r, a5), r, a6), v);
     const float den = hs(hs(hs(hs(hs(b1, r, b2), r, b3), r, b4), r, b5), r, 1.0f);
     return __fdiv_rn(num, den);
+}
+__device__ __forceinline__ float hash_normal01(uint32_t seed, uint32_t row, uint32_t col) {
+    const float u = normal01_clamp_u(hash_uniform01(seed, row, col));
+    return normal01_is_tail(u) ? normal01_tail(u) : normal01_central(u);
 }
 
 template <int KIND, typename A>
