@@ -14,6 +14,7 @@ CSRC = os.path.join(_HERE, "csrc")
 # dtype / event-kind codes (include/brainevent_b200.h)
 F32, F64, F16, BF16 = 0, 1, 2, 3
 SPK_BOOL, SPK_F32, SPK_PACKED, SPK_COMPACT = 0, 1, 2, 3
+SPK_COMPACT_CLEARED = 4      # COMPACT whose producer already cleared the consumer's output (dist.P2PSpikeExchange)
 JIT_SCALAR, JIT_NORMAL, JIT_UNIFORM = 0, 1, 2
 
 _lib = None
@@ -83,6 +84,8 @@ _SIGNATURES = {
     "be_b200_exchange_ctl_bytes": (_Z, []),
     "be_b200_pack_publish": (_I, [_P, _I, _L, _P, _P, _I, _I, _L, _P, _P]),
     "be_b200_wait_exchange": (_I, [_P, _P, _I, _L, _P, _P, _P]),
+    "be_b200_pack_publish_reset": (_I, [_P, _I, _L, _P, _P, _I, _I, _L, _P, _P, _P]),
+    "be_b200_wait_exchange_compact": (_I, [_P, _P, _I, _L, _L, _P, _P, _P, _Z, _P, _P]),
     "be_b200_projection_create_csr": (_P, [_P, _I, _P, _P, _L, _L]),
     "be_b200_projection_create_fcn": (_P, [_P, _I, _P, _L, _L, _L]),
     "be_b200_projection_adopt_fcn": (_P, [_P, _I, _P, _L, _L, _L]),

@@ -455,9 +455,11 @@ int prepare_events_1d(const void* spikes, const void* aux, int spk_kind, int64_t
     if (rc) return rc;
     Workspace ws = ws_carve(workspace, n, 1);
     ev->words_per_row = 1;
-    const bool compacts = need_ids && spk_kind != BE_B200_SPK_COMPACT;
-    if (!compacts && zero_ptr != nullptr && zero_bytes > 0) BE_CUDA(cudaMemsetAsync(zero_ptr, 0, zero_bytes, s));
-    if (spk_kind == BE_B200_SPK_COMPACT) {
+    const bool is_compact = spk_kind == BE_B200_SPK_COMPACT || spk_kind == BE_B200_SPK_COMPACT_CLEARED;
+    const bool compacts = need_ids && !is_compact;
+    if (!compacts && zero_ptr != nullptr && zero_bytes > 0 && spk_kind != BE_B200_SPK_COMPACT_CLEARED)
+        BE_CUDA(cudaMemsetAsync(zero_ptr, 0, zero_bytes, s));
+    if (is_compact) {
         BE_REQUIRE(aux != nullptr, "COMPACT events need aux = active_ids[n] ++ n_active");
         BE_REQUIRE(!need_packed || spikes != nullptr, "COMPACT events: packed words required here");
         ev->packed = (const uint32_t*)spikes;

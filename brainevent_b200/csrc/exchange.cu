@@ -60,10 +60,16 @@ template <int KIND>
 __global__ void __launch_bounds__(256) pack_publish_kernel(const void* __restrict__ spikes, int64_t n_local,
                                                            uint32_t* const* __restrict__ peer_bufs,
                                                            uint32_t* const* __restrict__ peer_flags, int world,
-                                                           int rank, int64_t words_per_rank, ExchangeCtl* ctl) {
+                                                           int rank, int64_t words_per_rank, ExchangeCtl* ctl,
+                                                           int32_t* __restrict__ reset_counter) {
     const uint32_t t = ctl->step + 1;      // read by every block before the last one bumps it
     const int lane = threadIdx.x & 31;
-    if (blockIdx.x == 0 && threadIdx.x == 0) ctl->stamp[0] = gtimer();
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        ctl->stamp[0] = gtimer();
+        // n_active of the fused wait + compaction below: the previous step's consumer is behind us in
+        // stream order, this step's wait kernel ahead of us
+        if (reset_counter != nullptr) *reset_counter = 0;
+    }
     const int64_t slot0 = (int64_t)(t & 1u) * words_per_rank * world + (int64_t)rank * words_per_rank;
     for (int64_t h = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; (h - lane) < 2 * words_per_rank;
          h += (int64_t)gridDim.x * blockDim.x) {
@@ -150,15 +156,112 @@ __global__ void __launch_bounds__(256) wait_copy_kernel(const uint32_t* __restri
     if (blockIdx.x == gridDim.x - 1 && threadIdx.x == 0) ctl->stamp[5] = gtimer();
 }
 
+
+// wait + pull + COMPACTION + output clear in one kernel, for scatter consumers at N > 1.  While the
+// peers are still publishing, every block clears its slice of the consumer's output vector; after the
+// flags it pulls the words exactly like wait_copy_kernel and, with the words still in registers,
+// turns them into the active-id list (block scan of the popcounts, one atomic per block and trip on
+// the global cursor; the order of the list is irrelevant to a scatter).  This removes the separate
+// compaction kernel (5-11 us on 10 M bits, mostly launch + tail latency) from the per-timestep chain.
+__global__ void __launch_bounds__(256) wait_copy_compact_kernel(const uint32_t* __restrict__ my_flags,
+                                                                uint32_t* const* __restrict__ peer_bufs, int world,
+                                                                int64_t words_per_rank, int64_t n_bits,
+                                                                uint32_t* __restrict__ dst, int32_t* __restrict__ ids,
+                                                                int32_t* __restrict__ n_active,
+                                                                int4* __restrict__ zero_ptr, size_t zero_vec16,
+                                                                ExchangeCtl* ctl) {
+    const uint32_t t = ctl->step;
+    if (blockIdx.x == 0 && threadIdx.x == 0) ctl->stamp[3] = gtimer();
+    if (zero_ptr != nullptr) {
+        const size_t per = (zero_vec16 + gridDim.x - 1) / gridDim.x;
+        const size_t z0 = (size_t)blockIdx.x * per, z1 = min(z0 + per, zero_vec16);
+        for (size_t z = z0 + threadIdx.x; z < z1; z += blockDim.x) zero_ptr[z] = make_int4(0, 0, 0, 0);
+    }
+    if ((int)threadIdx.x < world) {
+        unsigned long long spins = 0;
+        while ((int32_t)(ld_acquire_sys(my_flags + threadIdx.x) - t) < 0) {
+            if (++spins > (1ull << 26)) { ctl->timeout = 1u; break; }   // bounded: never hang the GPU
+            __nanosleep(20);
+        }
+    }
+    __syncthreads();
+    if (blockIdx.x == 0 && threadIdx.x == 0) ctl->stamp[4] = gtimer();
+    const int64_t n = words_per_rank * world;
+    const int64_t half = (int64_t)(t & 1u) * n;
+    constexpr int U = 8;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    __shared__ int s_warp[8];
+    __shared__ int s_base;
+    for (int64_t b0 = (int64_t)blockIdx.x * blockDim.x; b0 < n; b0 += stride * U) {     // block-uniform trip count
+        const int64_t i0 = b0 + threadIdx.x;
+        uint32_t v[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int64_t i = i0 + u * stride;
+            v[u] = (i < n) ? ld_relaxed_sys(peer_bufs[(int)(i / words_per_rank)] + half + i) : 0u;
+        }
+        int cnt = 0;
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int64_t i = i0 + u * stride;
+            if (i < n) dst[i] = v[u];
+            cnt += __popc(v[u]);
+        }
+        int incl = cnt;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const int o = __shfl_up_sync(0xffffffffu, incl, d);
+            if (lane >= d) incl += o;
+        }
+        if (lane == 31) s_warp[warp] = incl;
+        __syncthreads();
+        int woff = 0, total = 0;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) {
+            const int c = s_warp[w];
+            if (w < warp) woff += c;
+            total += c;
+        }
+        if (threadIdx.x == 0) s_base = total ? atomicAdd(n_active, total) : 0;
+        __syncthreads();
+        int pos = s_base + woff + incl - cnt;
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            uint32_t w = v[u];
+            const int64_t bit0 = (i0 + u * stride) * 32;
+            while (w) {
+                const int b = __ffs(w) - 1;
+                w &= w - 1;
+                if (bit0 + b < n_bits) ids[pos] = (int32_t)(bit0 + b);
+                ++pos;
+            }
+        }
+        __syncthreads();      // s_warp / s_base are reused by the next trip
+    }
+    if (blockIdx.x == gridDim.x - 1 && threadIdx.x == 0) ctl->stamp[5] = gtimer();
+}
+
 }  // namespace be
 
 using namespace be;
 
 extern "C" size_t be_b200_exchange_ctl_bytes(void) { return sizeof(ExchangeCtl); }
 
+extern "C" int be_b200_pack_publish_reset(const void* spikes_local, int spk_kind, int64_t n_local,
+                                          void* const* peer_bufs, void* const* peer_flags, int world, int rank,
+                                          int64_t words_per_rank, void* ctl, int32_t* reset_counter, void* stream);
+
 extern "C" int be_b200_pack_publish(const void* spikes_local, int spk_kind, int64_t n_local,
                                     void* const* peer_bufs, void* const* peer_flags, int world, int rank,
                                     int64_t words_per_rank, void* ctl, void* stream) {
+    return be_b200_pack_publish_reset(spikes_local, spk_kind, n_local, peer_bufs, peer_flags, world, rank,
+                                      words_per_rank, ctl, nullptr, stream);
+}
+
+extern "C" int be_b200_pack_publish_reset(const void* spikes_local, int spk_kind, int64_t n_local,
+                                          void* const* peer_bufs, void* const* peer_flags, int world, int rank,
+                                          int64_t words_per_rank, void* ctl, int32_t* reset_counter, void* stream) {
     cudaStream_t s = (cudaStream_t)stream;
     BE_REQUIRE(spikes_local && peer_bufs && peer_flags && ctl, "pack_publish: NULL pointer");
     BE_REQUIRE(world >= 1 && world <= 32 && rank >= 0 && rank < world, "pack_publish: bad rank/world");
@@ -167,11 +270,11 @@ extern "C" int be_b200_pack_publish(const void* spikes_local, int spk_kind, int6
     if (spk_kind == BE_B200_SPK_BOOL)
         pack_publish_kernel<BE_B200_SPK_BOOL><<<blocks, 256, 0, s>>>(spikes_local, n_local, (uint32_t* const*)peer_bufs,
                                                                       (uint32_t* const*)peer_flags, world, rank,
-                                                                      words_per_rank, (ExchangeCtl*)ctl);
+                                                                      words_per_rank, (ExchangeCtl*)ctl, reset_counter);
     else if (spk_kind == BE_B200_SPK_F32)
         pack_publish_kernel<BE_B200_SPK_F32><<<blocks, 256, 0, s>>>(spikes_local, n_local, (uint32_t* const*)peer_bufs,
                                                                      (uint32_t* const*)peer_flags, world, rank,
-                                                                     words_per_rank, (ExchangeCtl*)ctl);
+                                                                     words_per_rank, (ExchangeCtl*)ctl, reset_counter);
     else { set_error("pack_publish: unsupported event kind %d", spk_kind); return BE_B200_EINVAL; }
     BE_LAUNCH_CHECK("pack_publish_kernel");
     return BE_B200_OK;
@@ -184,5 +287,28 @@ extern "C" int be_b200_wait_exchange(const void* my_flags, void* const* peer_buf
     wait_copy_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>((const uint32_t*)my_flags, (uint32_t* const*)peer_bufs, world,
                                                               words_per_rank, gathered_out, (ExchangeCtl*)ctl);
     BE_LAUNCH_CHECK("wait_copy_kernel");
+    return BE_B200_OK;
+}
+
+extern "C" int be_b200_wait_exchange_compact(const void* my_flags, void* const* peer_bufs, int world,
+                                             int64_t words_per_rank, int64_t n_bits, uint32_t* gathered_out,
+                                             int32_t* ids_and_count, void* clear_ptr, size_t clear_bytes,
+                                             void* ctl, void* stream) {
+    BE_REQUIRE(my_flags && peer_bufs && gathered_out && ids_and_count && ctl && world >= 1 && world <= 32,
+               "wait_exchange_compact: bad arguments");
+    BE_REQUIRE(n_bits >= 0 && n_bits <= words_per_rank * world * 32 && n_bits < ((int64_t)1 << 31),
+               "wait_exchange_compact: n_bits outside the gathered vector");
+    cudaStream_t s = (cudaStream_t)stream;
+    int4* zp = nullptr;
+    size_t zv = 0;
+    if (clear_ptr != nullptr && clear_bytes > 0) {
+        if ((((uintptr_t)clear_ptr) & 15u) == 0 && clear_bytes % 16 == 0) { zp = (int4*)clear_ptr; zv = clear_bytes / 16; }
+        else BE_CUDA(cudaMemsetAsync(clear_ptr, 0, clear_bytes, s));
+    }
+    const int blocks = (int)std::max<int64_t>(1, std::min<int64_t>(ceil_div(words_per_rank * world, 1024), kNumSM));
+    wait_copy_compact_kernel<<<blocks, 256, 0, s>>>((const uint32_t*)my_flags, (uint32_t* const*)peer_bufs, world,
+                                                    words_per_rank, n_bits, gathered_out, ids_and_count,
+                                                    ids_and_count + n_bits, zp, zv, (ExchangeCtl*)ctl);
+    BE_LAUNCH_CHECK("wait_copy_compact_kernel");
     return BE_B200_OK;
 }

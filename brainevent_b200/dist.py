@@ -153,6 +153,38 @@ class P2PSpikeExchange(SpikeExchange):
                    "wait_exchange")
         return self.gathered[: self.n_words]
 
+    def exchange_compact(self, local_spikes: torch.Tensor, out: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
+        """Exchange for a SCATTER consumer: like exchange_spikes, but the wait kernel also turns the
+        gathered words into the active-id list and clears `out` (the consumer's output vector) while it
+        waits for the peers, so no separate compaction kernel or memset runs on the per-timestep chain.
+        Returns (words int32[ceil(N/32)], ids_and_count int32[N + 1]); consume with event kind
+        SPK_COMPACT_CLEARED (spikes = words, aux = ids_and_count)."""
+        import ctypes
+        from . import _lib
+        from ._runtime import ptr, stream_ptr
+        s = local_spikes
+        if s.dtype in (torch.bool, torch.uint8, torch.int8):
+            kind = _lib.SPK_BOOL
+        elif s.dtype == torch.float32:
+            kind = _lib.SPK_F32
+        else:
+            s, kind = (s > 0), _lib.SPK_BOOL
+        s = s.contiguous()
+        if getattr(self, "ids", None) is None:
+            self.ids = torch.zeros(self.n_neurons + 1, dtype=torch.int32, device=s.device)
+        L = _lib.lib()
+        dev = s.device
+        counter = ctypes.c_void_p(self.ids.data_ptr() + 4 * self.n_neurons)
+        _lib.check(L.be_b200_pack_publish_reset(ptr(s), kind, s.numel(), ptr(self.peer_bufs), ptr(self.peer_flags),
+                                                self.world, self.rank, self.words_per_rank, ptr(self.ctl), counter,
+                                                stream_ptr(dev)), "pack_publish_reset")
+        _lib.check(L.be_b200_wait_exchange_compact(ctypes.c_void_p(self.symm.data_ptr() + 4 * self.n_buf),
+                                                   ptr(self.peer_bufs), self.world, self.words_per_rank, self.n_neurons,
+                                                   ptr(self.gathered), ptr(self.ids), ptr(out),
+                                                   out.numel() * out.element_size(), ptr(self.ctl), stream_ptr(dev)),
+                   "wait_exchange_compact")
+        return self.gathered[: self.n_words], self.ids
+
     def timed_out(self) -> bool:
         return bool(self.ctl[2].item())
 
@@ -199,7 +231,26 @@ class PostShardedProjection:
                       corder=corder, **extra)
         raise ValueError(self.kind)
 
+    def _step_fcn_fused(self, local_spikes: torch.Tensor) -> torch.Tensor:
+        """FixedNumPerPre scatter behind the fused exchange: three kernels per timestep (pack + publish,
+        wait + pull + compaction + output clear, scatter) instead of five launches."""
+        from . import _lib
+        from ._runtime import ptr, stream_ptr, workspace, wt_code
+        w, idx = self.conn["weights"], self.conn["indices"]
+        n_loc = self.hi - self.lo
+        out = torch.empty(n_loc, dtype=w.dtype, device=w.device)
+        words, ids = self.x.exchange_compact(local_spikes, out)
+        ws = workspace(w.device, self.n_pre, 1)
+        rc = _lib.lib().be_b200_binary_fcnmv(ptr(w), wt_code(w.dtype), int(w.numel() == 1), ptr(idx), idx.shape[0],
+                                            idx.shape[1], ptr(words), ptr(ids), _lib.SPK_COMPACT_CLEARED, self.n_pre,
+                                            n_loc, 1, ptr(out), ptr(ws), ws.numel(), stream_ptr(w.device))
+        _lib.check(rc, "binary_fcnmv")
+        return out
+
     def step(self, local_spikes: torch.Tensor) -> torch.Tensor:
+        if (self.kind == "fcn" and hasattr(self.x, "exchange_compact")
+                and os.environ.get("BE_B200_FUSED_COMPACT", "1") != "0"):
+            return self._step_fcn_fused(local_spikes)
         if hasattr(self.x, "exchange_spikes"):           # fused pack + peer-memory all-gather
             return self.propagate(self.x.exchange_spikes(local_spikes))
         return self.propagate(self.x.exchange(self.pack_local(local_spikes)))

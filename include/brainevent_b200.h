@@ -49,6 +49,9 @@ extern "C" {
 #define BE_B200_SPK_F32 1
 #define BE_B200_SPK_PACKED 2
 #define BE_B200_SPK_COMPACT 3
+/* COMPACT whose producer has already cleared the consumer's output vector (the fused
+ * exchange + compaction of be_b200_wait_exchange_compact): 1-D scatter consumers skip their own clear */
+#define BE_B200_SPK_COMPACT_CLEARED 4
 
 /* ---- JITC weight families (ref: _jit_scalar/, _jit_normal/, _jit_uniform/) ------------------ */
 #define BE_B200_JIT_SCALAR 0   /* w = p0 */
@@ -301,6 +304,18 @@ int be_b200_pack_publish(const void* spikes_local, int spk_kind, int64_t n_local
                          int64_t words_per_rank, void* ctl, void* stream);
 int be_b200_wait_exchange(const void* my_flags, void* const* peer_bufs, int world, int64_t words_per_rank,
                           uint32_t* gathered_out, void* ctl, void* stream);
+/* Scatter consumers: the wait kernel also compacts the gathered words into ids_and_count =
+ * int32[n_bits + 1] (active ids in any order, count at [n_bits]) and clears clear_ptr[0..clear_bytes)
+ * (the consumer's output) while it waits; consume with spk_kind BE_B200_SPK_COMPACT_CLEARED,
+ * spikes = gathered_out, aux = ids_and_count.  The pack of the same step must be issued through
+ * be_b200_pack_publish_reset with reset_counter = ids_and_count + n_bits. */
+int be_b200_pack_publish_reset(const void* spikes_local, int spk_kind, int64_t n_local,
+                               void* const* peer_bufs, void* const* peer_flags, int world, int rank,
+                               int64_t words_per_rank, void* ctl, int32_t* reset_counter, void* stream);
+int be_b200_wait_exchange_compact(const void* my_flags, void* const* peer_bufs, int world,
+                                  int64_t words_per_rank, int64_t n_bits, uint32_t* gathered_out,
+                                  int32_t* ids_and_count, void* clear_ptr, size_t clear_bytes,
+                                  void* ctl, void* stream);
 
 /* ---- host-buffer session (end-to-end entry: host spikes in, host result out) -----------------
  * A projection keeps its connectivity resident in HBM (uploaded once at creation, like the

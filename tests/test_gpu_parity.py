@@ -250,7 +250,11 @@ def test_dense_vs_oracle(G, rows, cols, transpose):
 
 
 @pytest.mark.parametrize("k,m,batch,rate", [(64, 128, 64, 0.3), (4097, 300, 64, 0.05), (1000, 2048, 100, 0.01),
-                                             (3000, 1028, 256, 0.2), (513, 132, 70, 0.5), (8192, 4096, 64, 0.02)])
+                                             (3000, 1028, 256, 0.2), (513, 132, 70, 0.5), (8192, 4096, 64, 0.02),
+                                             # row lists: several 3072-row chunks per CTA (k > 32 x 3072), sparse and
+                                             # dense lists, padded last block, nothing active at all, batch tile 128
+                                             (200000, 128, 64, 0.002), (200000, 128, 64, 0.3), (120000, 256, 128, 0.0005),
+                                             (5000, 256, 64, 0.0)])
 def test_dense_tensor_core_path(G, k, m, batch, rate):
     """binary_densemm(transpose=True) at batch >= 64 runs on tcgen05 with a 3 x bf16 split of the
     fp32 weights: must still meet the fp32 tolerance (exact products, fp32 accumulation)."""

@@ -39,6 +39,38 @@ for step in range(7):          # odd count on purpose: parity lives on the devic
     ref = O.binary_fcnmv(w, idx, spikes, shape=(N, N), transpose=True)[lo:hi]
     np.testing.assert_allclose(out, ref, rtol=1e-5, atol=2e-5)
 assert not xp.timed_out()
+# FixedNumPerPre shard behind the FUSED exchange (wait + pull + compaction + output clear in one kernel,
+# consumed as SPK_COMPACT_CLEARED): every pre neuron has c_loc targets inside this rank's block
+n_loc, c_loc = hi - lo, 6
+rl = np.random.default_rng(50 + rank)
+idx_f = rl.integers(0, n_loc, (N, c_loc)).astype(np.int32)
+w_f = rl.standard_normal((N, c_loc)).astype(np.float32)
+proj_f = bd.PostShardedProjection("fcn", N, N, xp, weights=t(w_f), indices=t(idx_f))
+for step, rate in enumerate([0.03, 0.0, 0.5, 0.01, 0.2]):
+    spikes = np.random.default_rng(200 + step).random(N) < rate
+    out = proj_f.step(t(spikes[lo:hi]))
+    ids = xp.ids.cpu().numpy()
+    assert ids[N] == spikes.sum(), f"rank {rank} step {step}: n_active {ids[N]} != {spikes.sum()}"
+    np.testing.assert_array_equal(np.sort(ids[: ids[N]]), np.nonzero(spikes)[0])
+    ref = O.binary_fcnmv(w_f, idx_f, spikes, shape=(N, n_loc), transpose=True)
+    np.testing.assert_allclose(out.cpu().numpy(), ref, rtol=1e-5, atol=2e-5)
+assert not xp.timed_out()
+pipe_f = bd.HostStepPipeline(proj_f, n_loc, slots=4)            # the fused step inside one CUDA graph per slot
+hf_in = [torch.empty(n_loc, dtype=torch.uint8).pin_memory() for _ in range(7)]
+hf_out = [torch.empty(n_loc, dtype=torch.float32).pin_memory() for _ in range(7)]
+refs_f = []
+for q in range(7):
+    sp = np.random.default_rng(400 + q).random(N) < 0.05
+    hf_in[q].copy_(torch.from_numpy(sp[lo:hi].astype(np.uint8)))
+    refs_f.append(O.binary_fcnmv(w_f, idx_f, sp, shape=(N, n_loc), transpose=True))
+for q in range(7):
+    pipe_f.submit(hf_in[q], hf_out[q])
+pipe_f.wait()
+for q in range(7):
+    np.testing.assert_allclose(hf_out[q].numpy(), refs_f[q], rtol=1e-5, atol=2e-5)
+pipe_f.close()
+del pipe_f
+assert not xp.timed_out()
 # host-buffer pipeline (4 timesteps in flight, one CUDA graph per slot) == the plain step
 pipe = bd.HostStepPipeline(proj_n, hi - lo, slots=4)
 h_in = [torch.empty(hi - lo, dtype=torch.uint8).pin_memory() for _ in range(9)]
