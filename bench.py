@@ -318,7 +318,9 @@ class DenseMm(Workload):
         self.pool = torch.rand((4, k, batch), device=device, generator=g) < rate
         self.events_per_timestep = float(self.pool.sum((1, 2)).double().mean().item()) * m
         self.bytes_per_event = 0.0
-        self.extra_bytes_per_timestep = 4.0 * k * m + 4.0 * m * batch      # W streamed once + output
+        # 4 B x m x (rows that fired in at least one batch column) + output; silent rows of W are never read
+        live_rows = float(self.pool.any(2).sum(1).double().mean().item())
+        self.extra_bytes_per_timestep = 4.0 * live_rows * m + 4.0 * m * batch
         self.config = {"workload": f"BinaryArray[{batch},{k}] @ dense W[{k},{m}] fp32, {rate:.0%} spikes "
                                    "(binary_densemm transpose=True on tcgen05; events = active (source, column) pairs x m)"}
 
