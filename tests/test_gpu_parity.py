@@ -266,7 +266,11 @@ def test_dense_tensor_core_path(G, k, m, batch, rate):
     scale = (np.abs(W).astype(np.float64).T @ B.astype(np.float64))          # sum |w| of each output
     err = np.abs(got - ref)
     assert np.all(err <= 1e-5 * np.abs(ref) + 2e-6 * scale + 1e-6), float((err / (scale + 1e-6)).max())
-    np.testing.assert_allclose(got, O.binary_densemm(W, B, transpose=True), rtol=1e-4, atol=1e-3)
+    if k <= 10000:
+        # the oracle accumulates sequentially in fp32 like the reference's numba loop; over 6e4 terms of
+        # magnitude 30 its OWN rounding error (~0.1) exceeds this tolerance, so the large cases rest on
+        # the float64 bound above, which is the stricter check
+        np.testing.assert_allclose(got, O.binary_densemm(W, B, transpose=True), rtol=1e-4, atol=1e-3)
 
 
 def test_event_containers_and_classes(G):
