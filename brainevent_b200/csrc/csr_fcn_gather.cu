@@ -124,6 +124,34 @@ __global__ void __launch_bounds__(SMEM ? 1024 : 256) gather_mv_kernel(Rows rows,
                         const int64_t j = j0 + (int64_t)u * LPR * 4;
                         ix[u] = (j < aend) ? ldg_stream((const int4*)(indices + j)) : make_int4(-1, -1, -1, -1);
                     }
+                    if (!HOMO && PERM == 0 && std::is_same<T, float>::value) {
+                        // fp32 weights: first all lookups (4-bit hit mask per quad), then ALL the weight quads
+                        // that were hit are requested with predicated 128-bit loads before the first one is
+                        // used -- one exposed latency per trip instead of one per hit quad, and no divergence
+                        uint32_t hm = 0;
+#pragma unroll
+                        for (int u = 0; u < U; ++u) {
+                            if (ix[u].x < 0) continue;
+                            hm |= ((uint32_t)bit(ix[u].x) | ((uint32_t)bit(ix[u].y) << 1) | ((uint32_t)bit(ix[u].z) << 2) |
+                                   ((uint32_t)bit(ix[u].w) << 3)) << (4 * u);
+                        }
+                        if (hm) {
+                            int4 wq[U];
+#pragma unroll
+                            for (int u = 0; u < U; ++u) {
+                                wq[u] = make_int4(0, 0, 0, 0);
+                                if ((hm >> (4 * u)) & 15u)
+                                    wq[u] = ldg_stream((const int4*)((const float*)weights + j0 + (int64_t)u * LPR * 4));
+                            }
+#pragma unroll
+                            for (int u = 0; u < U; ++u) {
+                                const uint32_t q = (hm >> (4 * u)) & 15u;
+                                acc += (A)((q & 1u ? __int_as_float(wq[u].x) : 0.0f) + (q & 2u ? __int_as_float(wq[u].y) : 0.0f) +
+                                           (q & 4u ? __int_as_float(wq[u].z) : 0.0f) + (q & 8u ? __int_as_float(wq[u].w) : 0.0f));
+                            }
+                        }
+                        continue;
+                    }
 #pragma unroll
                     for (int u = 0; u < U; ++u) {
                         if (ix[u].x < 0) continue;
