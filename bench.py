@@ -348,6 +348,51 @@ class Jitc1M(Workload):
         return self.be.BinaryArray(self.pool[t % POOL]) @ self.m
 
 
+class Jitc1MSharded(Workload):
+    """BASELINE configs[3]: spk @ JITCNormalR 1 M x 1 M, prob 1e-3, post-sharded over the ranks with the
+    spike exchange (STRONG scaling: the network is fixed, each rank regenerates only its post block --
+    a column window of the scatter order or a row window of the gather order, the GLOBAL shape keys the
+    RNG so the union of the shards is index-for-index the single-GPU matrix)."""
+    name = "jitc_normal_1m_sharded"
+    bytes_per_event = 8.0
+    scaling = "strong"
+
+    def __init__(self, torch, be, rank, world, device, gather=False, rate=0.01):
+        from brainevent_b200 import dist as bd
+        self.world, n = world, 1_000_000
+        self.dominant_kernel = "jit_mv_gather_kernel" if gather else "jit_mv_scatter_kernel"
+        bounds = bd.post_block_bounds(n, world)
+        lo, hi = bounds[rank]
+        self.n_local = hi - lo
+        self.pool = spike_pool(torch, self.n_local, rate, 5 + rank, device)       # spikes of the neurons I own
+        self.x = None
+        if world > 1 and os.environ.get("BE_B200_EXCHANGE", DEFAULT_EXCHANGE) == "p2p":
+            try:
+                self.x = bd.P2PSpikeExchange(n, device=device)
+            except Exception as e:  # pragma: no cover
+                sys.stderr.write(f"[bench] P2P exchange unavailable ({type(e).__name__}: {e}); using NCCL\n")
+        if self.x is None:
+            self.x = bd.SpikeExchange(n, device=device)
+        # operator corder: True = gather order (rows = post), False = scatter order (cols = post)
+        self.proj = bd.PostShardedProjection("jitc", n, n, self.x, family="normal", params=(1.0, 0.1), prob=1e-3,
+                                             seed=123, corder=gather)
+        act = sum(float(spike_pool(torch, b[1] - b[0], rate, 5 + r, device).sum(1).double().mean().item())
+                  for r, b in enumerate(bounds))
+        self.events_per_timestep = act * self.n_local * 1e-3                       # this rank's share
+        self._total = act * n * 1e-3
+        self.extra_bytes_per_timestep = 0.0
+        self.launches_per_timestep = 3 if world > 1 else 2
+        self.config = {"workload": f"spk @ JITCNormalR 1M x 1M, prob 1e-3, {'gather' if gather else 'scatter'} order, "
+                                   f"{rate:.0%} spikes, post-sharded over {world} GPU(s) with the spike exchange "
+                                   "(BASELINE configs[3]; strong scaling)"}
+
+    def timestep(self, t):
+        return self.proj.step(self.pool[t % POOL])
+
+    def total_events_per_timestep(self):
+        return self._total
+
+
 # ------------------------------------------------------------------------------------------------
 # timing helpers
 # ------------------------------------------------------------------------------------------------
@@ -528,7 +573,8 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default="fcn", choices=["fcn", "coba", "cuba_jitc", "csr_spmm", "jitc_1m", "csr_gather", "csr_scatter", "dense_mm", "jitc_1m_gather"])
+    ap.add_argument("--workload", default="fcn", choices=["fcn", "coba", "cuba_jitc", "csr_spmm", "jitc_1m", "csr_gather", "csr_scatter", "dense_mm", "jitc_1m_gather",
+                                                           "jitc_1m_sharded", "jitc_1m_sharded_gather"])
     ap.add_argument("--timesteps", type=int, default=100, help="simulated timesteps per step")
     ap.add_argument("--no-extra", action="store_true", help="skip the other BASELINE configs at N=1")
     ap.add_argument("--no-graph", action="store_true")
@@ -578,6 +624,8 @@ def main():
         wl = DenseMm(torch, be, device)
     elif args.workload == "jitc_1m_gather":
         wl = Jitc1M(torch, be, device, corder=False)
+    elif args.workload in ("jitc_1m_sharded", "jitc_1m_sharded_gather"):
+        wl = Jitc1MSharded(torch, be, rank, world, device, gather=args.workload.endswith("gather"))
     else:
         wl = Jitc1M(torch, be, device, corder=True)
 
@@ -588,6 +636,8 @@ def main():
         # published (results would be stale): fall back to NCCL on every rank and measure again
         bad = torch.tensor([int(wl.x.timed_out())], device=device)
         dist.all_reduce(bad, op=dist.ReduceOp.MAX)
+        if int(bad.item()) and args.workload != "fcn":
+            raise RuntimeError("peer-memory spike exchange timed out (a peer never published); rerun with BE_B200_EXCHANGE=nccl")
         if int(bad.item()):
             sys.stderr.write("[bench] peer-memory exchange timed out; re-measuring with the NCCL all-gather\n")
             del wl
@@ -722,8 +772,8 @@ def main():
                              "working set of one cycle (~1.6 GB of a 10 GB matrix) exceeds the 126 MB L2",
                 "parallelism": f"post-sharded x{world}" if world > 1 else "single GPU"})
     line = {"metric": "synaptic events/sec", "value": res["value"], "unit": "events/s", "n_gpus": world,
-            "steps": K, "warmup": W, "ms_per_step": res["ms_per_step"], "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": cfg,
+            "steps": K, "warmup": W, "ms_per_step": res["ms_per_step"], "higher_is_better": True,
+            "scaling": getattr(wl, "scaling", "weak"), "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": cfg,
             "roofline": res["roofline"], "cpu_baseline": cpu, "e2e": e2e,
             "gpu_launches": int(wl.launches_per_timestep * T * K), "clocks": res["clocks"],
             "events_per_step": res["events_per_step"]}

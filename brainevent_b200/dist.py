@@ -224,11 +224,19 @@ class PostShardedProjection:
         if self.kind == "csr":
             return binary_csrmv(c["data"], c["indices"], c["indptr"], ev, shape=(self.n_pre, n_loc), transpose=True)
         if self.kind == "jitc":
-            op = {"scalar": _jitc.binary_jitsmv, "normal": _jitc.binary_jitnmv, "uniform": _jitc.binary_jitumv}[c["family"]]
+            prim = {"scalar": _jitc.binary_jitsmv_p, "normal": _jitc.binary_jitnmv_p,
+                    "uniform": _jitc.binary_jitumv_p}[c["family"]]
             corder = c["corder"]  # passed corder: True = gather (rows = post), False = scatter (cols = post)
             extra = dict(row_window=(self.lo, n_loc)) if corder else dict(col_window=(self.lo, self.hi))
-            return op(*c["params"], c["prob"], ev, c["seed"], shape=(self.n_pre, self.n_post), transpose=True,
-                      corder=corder, **extra)
+            if getattr(self, "_jit_dev", None) is None:
+                # parameters, clen and seed live on the device once: per-step calls then issue no host
+                # copy and the whole step can be captured in a CUDA graph
+                dev = packed_all.device
+                self._jit_dev = ([torch.as_tensor([float(p)], dtype=torch.float32, device=dev) for p in c["params"]],
+                                 _jitc._initialize_conn_length(c["prob"], dev), _jitc._initialize_seed(c["seed"], dev))
+            params, clen, seed = self._jit_dev
+            return _jitc._jit_p_call(prim, params, clen, ev, seed, (self.n_pre, self.n_post), True, corder, None, False,
+                                     **extra)[0]
         raise ValueError(self.kind)
 
     def _step_fcn_fused(self, local_spikes: torch.Tensor) -> torch.Tensor:
