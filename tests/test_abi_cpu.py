@@ -100,3 +100,24 @@ def test_reference_cuda_shim_exports():
         lib = ctypes.CDLL(os.path.join(os.path.dirname(R.__file__), "_ref", f"libref_{name}.so"))
         for fn in want[name]:
             assert hasattr(lib, "ref_" + fn), (name, fn)
+
+
+def test_exchange_entry_points_validate_before_launching():
+    """The peer-memory exchange entries reject bad arguments with BE_B200_EINVAL and a message before
+    they touch the device (safe to call without a GPU), and the ctypes table matches the header."""
+    from brainevent_b200 import _lib
+    L = _lib.lib()
+    assert L.be_b200_exchange_ctl_bytes() >= 16
+    null = ctypes.c_void_p(0)
+    one = ctypes.c_void_p(16)            # never dereferenced: validation fails first
+    rc = L.be_b200_wait_exchange_compact(null, null, 2, 4, 128, null, null, null, 0, null, null)
+    assert rc != 0 and b"wait_exchange_compact" in L.be_b200_last_error()
+    rc = L.be_b200_wait_exchange_compact(one, one, 2, 4, 4 * 2 * 32 + 1, one, one, null, 0, one, null)
+    assert rc != 0 and b"n_bits" in L.be_b200_last_error()            # ids would overrun the gathered vector
+    rc = L.be_b200_pack_publish_reset(one, _lib.SPK_BOOL, 129, one, one, 2, 0, 4, one, null, null)
+    assert rc != 0 and b"n_local" in L.be_b200_last_error()           # 129 spikes do not fit 4 words
+    rc = L.be_b200_pack_publish_reset(one, _lib.SPK_BOOL, 64, one, one, 2, 5, 4, one, null, null)
+    assert rc != 0 and b"rank" in L.be_b200_last_error()
+    assert _lib.SPK_COMPACT_CLEARED == 4
+    hdr = open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "include", "brainevent_b200.h")).read()
+    assert "#define BE_B200_SPK_COMPACT_CLEARED 4" in hdr
