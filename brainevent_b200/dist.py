@@ -281,7 +281,11 @@ class HostStepPipeline:
         self.main = torch.cuda.Stream(device=dev)
         self.d_in = [torch.zeros(n_in, dtype=torch.uint8, device=dev) for _ in range(slots)]
         mk = lambda: [torch.cuda.Event() for _ in range(slots)]
-        self.ev_in, self.ev_done, self.ev_out = mk(), mk(), mk()
+        self.ev_in, self.ev_done = mk(), mk()
+        # the host waits on ev_out when it reuses a slot: a blocking event lets that thread sleep instead
+        # of spinning on a core, which matters when 8 ranks (plus their driver threads) share the host
+        blocking = os.environ.get("BE_B200_BLOCKING_EVENTS", "0") != "0"
+        self.ev_out = [torch.cuda.Event(blocking=blocking) for _ in range(slots)]
         self.inflight = [False] * slots
         self.i = 0
         self.graphs, self.d_out = [None] * slots, [None] * slots
