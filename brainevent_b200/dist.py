@@ -307,20 +307,26 @@ class HostStepPipeline:
         i = self.i
         if self.inflight[i]:
             self.ev_out[i].synchronize()
-        with torch.cuda.stream(self.s_in):
+        # plain set_stream calls instead of three `with torch.cuda.stream(...)` blocks: the host side of a
+        # timestep is ~70 us of Python (tools/e2e_pipeline_probe.py), close to what the PCIe copies take
+        prev = torch.cuda.current_stream(self.dev)
+        try:
+            torch.cuda.set_stream(self.s_in)
             self.d_in[i].copy_(spikes_host.view(torch.uint8), non_blocking=True)
             self.ev_in[i].record(self.s_in)
-        self.main.wait_event(self.ev_in[i])
-        with torch.cuda.stream(self.main):
+            self.main.wait_event(self.ev_in[i])
+            torch.cuda.set_stream(self.main)
             if self.graphs[i] is not None:
                 self.graphs[i].replay()
             else:
                 self.d_out[i] = self.proj.step(self.d_in[i])
             self.ev_done[i].record(self.main)
-        self.s_out.wait_event(self.ev_done[i])
-        with torch.cuda.stream(self.s_out):
+            self.s_out.wait_event(self.ev_done[i])
+            torch.cuda.set_stream(self.s_out)
             out_host.copy_(self.d_out[i], non_blocking=True)
             self.ev_out[i].record(self.s_out)
+        finally:
+            torch.cuda.set_stream(prev)
         self.inflight[i] = True
         self.i = (i + 1) % self.slots
 
