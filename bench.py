@@ -4,12 +4,22 @@
 Contract (see the task statement): `python bench.py --gpus N --steps K --warmup W` prints ONE JSON
 line on rank 0.  A *step* is one block of T simulated timesteps (default 100) of ONE projection:
 every timestep takes a fresh synthetic spike vector through the hot path
-(bit-pack + ordered compaction -> [all-gather of packed words when N > 1] -> active-row scatter).
+(N = 1: bit-pack + compaction -> active-row scatter; N > 1: bit-pack + publish -> spike exchange
+over NVLink peer memory fused into the active-row scatter).
 
 Default workload `fcn` (BASELINE.json configs[4], weak scaling): FixedNumPerPre, 1.25 M neurons per
-GPU x 1000 synapses per neuron, fp32 heterogeneous weights, 1 % spikes per timestep, post-sharded:
-at N = 8 this is the named 10 M-neuron x 1000 network.  Other configs: --workload
-{coba, cuba_jitc, csr_spmm, jitc_1m}; at N = 1 their short results ride along under "other_workloads".
+GPU x 1000 synapses per neuron, fp32 heterogeneous weights, 1 % spikes per timestep.  The matrix is
+the SURVEY 8(d) generator: every pre neuron draws its 1000 targets uniformly over ALL post neurons;
+it is generated shard-wise with counter-based seeds (every rank draws the same chunk stream and keeps
+the synapses ending in its post block), so a rank's shard is a RAGGED CSR (binomial ~1000/N per
+row) and the union of the shards is the single-GPU matrix.  At N = 8 this is the named
+10 M-neuron x 1000 network.  The line also carries
+  * `parity` (N > 1): every rank's output block checked before timing against an independent path
+    (NCCL all-gather + the plain operator) and an oracle slice; the run fails if it differs;
+  * `strong_scaling`: the FULL 10 000 128 x 1000 network on these N GPUs (80 GB on one GPU at N = 1);
+  * `other_workloads`: N = 1: the other BASELINE configs with `reference_cuda_us` = the reference's own
+    CUDA kernel (oracle/_ref, recompiled for sm_100a) timed on the same buffers; N > 1: configs[3]
+    (JITCNormalR 1 M, post-sharded, both orders).
 
 `--impl reference` times the CPU arm: the C restatement of the reference's numba kernels
 (oracle/, kind "port") on the host cores, on a bounded sample of the same workload.
@@ -108,76 +118,228 @@ def spike_pool(torch, n, rate, seed, device):
     return torch.rand((POOL, n), device=device, generator=g) < rate
 
 
+C5_NEURONS = 8 * FCN_NEURONS_PER_GPU   # 10 000 128: the named 10 M network
+C5_SEED = 1234
+C5_CHUNK_ROWS = 65_536
+
+
+P2P_TEXT = ("NVLink peer-memory exchange fused into the scatter (csrc/sharded.cu: pack + publish, then one kernel pulls each "
+            "peer's words as its flag arrives and scatters them; own rows first)")
+
+
 def fcn_workload_text(n_total, n_conn, rate, shards):
     return (f"FixedNumPerPre {n_total} neurons x {n_conn} synapses/neuron, fp32 hetero weights, "
             f"{rate:.0%} spikes/timestep, post-sharded over {shards} GPU(s) "
-            f"({n_total // shards} post neurons and {n_conn // shards} synapses/pre-neuron per GPU, "
-            "targets stratified evenly over post blocks), BASELINE configs[4] at 8 GPUs")
+            f"({n_total // shards} post neurons per GPU; every pre neuron draws {n_conn} targets uniformly over ALL "
+            f"{n_total} posts, so a GPU holds a ragged CSR of ~{n_conn // shards} synapses/pre-neuron), "
+            "BASELINE configs[4] at 8 GPUs")
 
 
-class FcnWeak(Workload):
-    """FixedNumPerPre, post-sharded, weak scaling (configs[4] at N = 8)."""
+def fcn_config(n_total, n_conn, rate, world, T):
+    """The `config` object of the line: identical for the B200 arm and the CPU (reference) arm."""
+    return {"workload": fcn_workload_text(n_total, n_conn, rate, world),
+            "neurons": n_total, "synapses_per_neuron": n_conn, "spike_rate": rate,
+            "generator": f"SURVEY 8(d): targets = randint(0, {n_total}) per (pre, slot), weights U(0,1), chunks of "
+                         f"{C5_CHUNK_ROWS} pre rows seeded {C5_SEED} * 1000003 + chunk on every rank",
+            "spike_exchange": P2P_TEXT if world > 1 else "none (single GPU)",
+            "timesteps_per_step": T,
+            "l2_policy": f"inputs larger than L2: {POOL} distinct spike vectors cycle, so the active-row working set "
+                         "of one cycle exceeds the 126 MB L2",
+            "parallelism": f"post-sharded x{world}" if world > 1 else "single GPU"}
+
+
+def c5_chunks(torch, device, n_total, n_conn, seed, with_weights=True, out_idx=None, out_w=None):
+    """Yields (row0, targets int32[rows, n_conn], weights f32[rows, n_conn] | None) of the SURVEY 8(d) network.
+    Chunk c is drawn from its own generator seeded from (seed, c): every rank, and the single-GPU build,
+    produce the identical matrix without anybody materialising more than one chunk."""
+    for c, r0 in enumerate(range(0, n_total, C5_CHUNK_ROWS)):
+        rows = min(C5_CHUNK_ROWS, n_total - r0)
+        g = torch.Generator(device=device).manual_seed(seed * 1_000_003 + c)
+        # in-place draws (what torch.randint / torch.rand do internally): identical streams whether the chunk is a
+        # fresh tensor or a row slice of the preallocated single-GPU matrix
+        tgt = out_idx[r0:r0 + rows] if out_idx is not None else torch.empty((rows, n_conn), device=device, dtype=torch.int32)
+        tgt.random_(0, n_total, generator=g)
+        wv = None
+        if with_weights:
+            wv = out_w[r0:r0 + rows] if out_w is not None else torch.empty((rows, n_conn), device=device, dtype=torch.float32)
+            wv.uniform_(0.0, 1.0, generator=g)
+        yield r0, tgt, wv
+
+
+def build_c5_ell(torch, device, n_total, n_conn, seed=C5_SEED):
+    """The whole network on one GPU: indices int32 [n_total, n_conn], weights f32 [n_total, n_conn] (FixedNumPerPre)."""
+    idx = torch.empty((n_total, n_conn), device=device, dtype=torch.int32)
+    w = torch.empty((n_total, n_conn), device=device, dtype=torch.float32)
+    for _ in c5_chunks(torch, device, n_total, n_conn, seed, out_idx=idx, out_w=w):
+        pass
+    return idx, w
+
+
+def build_c5_shard(torch, device, n_total, n_conn, lo, hi, seed=C5_SEED):
+    """One rank's share: the synapses ending in post block [lo, hi) as a ragged CSR over all n_total pre rows with
+    LOCAL post ids (two passes over the chunk stream: count, then fill exact-size arrays)."""
+    counts = torch.empty(n_total, device=device, dtype=torch.int64)
+    for r0, tgt, _ in c5_chunks(torch, device, n_total, n_conn, seed, with_weights=False):
+        counts[r0:r0 + tgt.shape[0]] = ((tgt >= lo) & (tgt < hi)).sum(1)
+    indptr = torch.zeros(n_total + 1, device=device, dtype=torch.int64)
+    torch.cumsum(counts, 0, out=indptr[1:])
+    nse = int(indptr[-1].item())
+    indices = torch.empty(nse, device=device, dtype=torch.int32)
+    weights = torch.empty(nse, device=device, dtype=torch.float32)
+    for r0, tgt, wv in c5_chunks(torch, device, n_total, n_conn, seed):
+        m = (tgt >= lo) & (tgt < hi)
+        p0, p1 = int(indptr[r0].item()), int(indptr[r0 + tgt.shape[0]].item())
+        indices[p0:p1] = tgt[m] - lo
+        weights[p0:p1] = wv[m]
+    if nse < 2**31:
+        indptr = indptr.to(torch.int32)
+    return indptr, indices, weights, counts
+
+
+class FcnSharded(Workload):
+    """FixedNumPerPre network of n_total neurons x n_conn synapses, post-sharded over the ranks.
+    world == 1: the FixedNumPerPre operator on the ELL matrix; world > 1: ragged CSR shards behind the
+    peer-memory spike exchange fused into the scatter (csrc/sharded.cu), or NCCL all-gather + operator."""
     name = "fcn_perpre_postsharded"
     dominant_kernel = "scatter_mv_kernel"
 
-    def __init__(self, torch, be, rank, world, device, neurons_per_gpu=FCN_NEURONS_PER_GPU, n_conn=FCN_CONN, rate=RATE,
-                 emulate_world=0, exchange=None):
+    def __init__(self, torch, be, rank, world, device, n_total, n_conn=FCN_CONN, rate=RATE, exchange=None, T=100,
+                 scaling="weak", emulate_world=0):
         from brainevent_b200 import dist as bd
-        self.torch, self.be, self.world, self.rank = torch, be, world, rank
-        self.emulate = emulate_world      # profile one rank's shard of an `emulate_world`-GPU run on a single GPU
-        shards = emulate_world if emulate_world else world
-        self.n_local = neurons_per_gpu
-        self.n_total = neurons_per_gpu * shards
-        self.conn_local = n_conn // shards          # targets stratified evenly over the post blocks
-        g = torch.Generator(device=device).manual_seed(1234 + rank)
-        # this rank's incoming synapses: for every pre neuron of the whole network, conn_local
-        # targets inside the local post block (local ids) with U(0,1) fp32 weights
-        self.indices = torch.randint(0, self.n_local, (self.n_total, self.conn_local), device=device,
-                                     dtype=torch.int32, generator=g)
-        self.weights = torch.rand((self.n_total, self.conn_local), device=device, generator=g)
-        self.pool = spike_pool(torch, self.n_local, rate, 99 + rank, device)     # spikes of the neurons I own
-        self.exchange_kind = "nccl all_gather"
-        self.x = None
-        exchange = exchange or os.environ.get("BE_B200_EXCHANGE", DEFAULT_EXCHANGE)
-        if world > 1 and exchange == "p2p":
-            try:
-                self.x = bd.P2PSpikeExchange(self.n_total, device=device)
-                self.exchange_kind = "fused bit-pack + NVLink peer-memory all-gather (csrc/exchange.cu: pack into the own symmetric buffer, flag the peers, pull their words)"
-            except Exception as e:  # pragma: no cover - symmetric memory unavailable: NCCL path
-                sys.stderr.write(f"[bench] P2P exchange unavailable ({type(e).__name__}: {e}); using NCCL\n")
-        if self.x is None:
-            self.x = bd.SpikeExchange(self.n_total, device=device)
-        self.proj = bd.PostShardedProjection("fcn", self.n_total, self.n_total, self.x,
-                                             weights=self.weights, indices=self.indices)
-        self.launches_per_timestep = 2 if world == 1 else 3
-        # events: every rank sees ALL spikes; count from the global pool (same seeds on every rank)
+        self.emulate = emulate_world      # (profiling) rank 0's shard of an `emulate_world`-GPU run on ONE GPU
         if emulate_world:
-            # no exchange: the global packed spike vector of every timestep is precomputed
-            gpool = torch.cat([spike_pool(torch, self.n_local, rate, 99 + r, device) for r in range(shards)], 1)
-            self.packed_pool = [be.BitPackedBinary(gpool[i]) for i in range(POOL)]
-            per_t = gpool.sum(1).double()
-        elif world == 1:
-            per_t = self.pool.sum(1).double()
+            world, rank = emulate_world, 0
+        self.torch, self.be, self.world, self.rank, self.device = torch, be, world, rank, device
+        self.n_total, self.n_conn, self.rate, self.scaling = n_total, n_conn, rate, scaling
+        self.bounds = bd.post_block_bounds(n_total, world)
+        self.lo, self.hi = self.bounds[rank]
+        self.n_local = self.hi - self.lo
+        # spikes of the neurons I own (every rank can regenerate every rank's pool: seeds 99 + r)
+        self.pool = spike_pool(torch, self.n_local, rate, 99 + rank, device)
+        gpool = (self.pool if world == 1 else
+                 torch.cat([spike_pool(torch, b[1] - b[0], rate, 99 + r, device) for r, b in enumerate(self.bounds)], 1))
+        self.active_per_timestep = float(gpool.sum(1).double().mean().item())
+        self.exchange_kind = "none (single GPU)"
+        self.x = self.proj = None
+        if world == 1:
+            self.indices, self.weights = build_c5_ell(torch, device, n_total, n_conn)
+            self.events_per_timestep = self.active_per_timestep * n_conn
+            self.launches_per_timestep = 2
+            indptr_bytes = 0.0
         else:
-            per_t = sum(spike_pool(torch, self.n_local, rate, 99 + r, device).sum(1).double() for r in range(world))
-        self.active_per_timestep = float(per_t.mean().item())
-        self.events_per_timestep = self.active_per_timestep * self.conn_local          # per rank
-        self.extra_bytes_per_timestep = 4.0 * self.active_per_timestep
-        self.config = {"workload": fcn_workload_text(self.n_total, n_conn, rate, shards),
-                       "neurons": self.n_total, "synapses_per_neuron": n_conn, "spike_rate": rate,
-                       "spike_exchange": self.exchange_kind if world > 1 else "none (single GPU)"}
+            self.indptr, self.indices, self.weights, counts = build_c5_shard(torch, device, n_total, n_conn, self.lo, self.hi)
+            self.events_per_timestep = float((gpool.double() @ counts.double()).mean().item())     # this rank's share
+            del counts
+            exchange = exchange or os.environ.get("BE_B200_EXCHANGE", DEFAULT_EXCHANGE)
+            if emulate_world:
+                # all ranks' exchange buffers on this GPU: per timestep every emulated peer publishes its block,
+                # then rank 0's fused kernel runs exactly as on the 8-GPU box (peer reads become local reads)
+                self.peers = bd.P2PSpikeExchange.emulate(n_total, world, device)
+                self.x = self.peers[0]
+                self.peer_pools = [spike_pool(torch, b[1] - b[0], rate, 99 + r, device) for r, b in enumerate(self.bounds)]
+                self.exchange_kind = f"emulated: {world} ranks' buffers on one GPU (profiling)"
+                self.dominant_kernel = "exchange_scatter_kernel"
+                self.launches_per_timestep = 1 + world
+            elif exchange == "p2p":
+                try:
+                    self.x = bd.P2PSpikeExchange(n_total, device=device)
+                    self.exchange_kind = P2P_TEXT
+                    self.dominant_kernel = "exchange_scatter_kernel"
+                    self.launches_per_timestep = 2
+                except Exception as e:  # pragma: no cover - symmetric memory unavailable: NCCL path
+                    sys.stderr.write(f"[bench] P2P exchange unavailable ({type(e).__name__}: {e}); using NCCL\n")
+            if self.x is None:
+                self.x = bd.SpikeExchange(n_total, device=device)
+                self.exchange_kind = "bit-pack + NCCL all_gather_into_tensor + operator"
+                self.launches_per_timestep = 4
+            self.proj = bd.PostShardedProjection("csr", n_total, n_total, self.x, data=self.weights, indices=self.indices,
+                                                 indptr=self.indptr)
+            indptr_bytes = 8.0 * self.active_per_timestep
+        del gpool
+        # SURVEY 8(d): 8 B/event + packed spikes + indptr pair per active row (CSR) + the output vector
+        self.extra_bytes_per_timestep = n_total / 8.0 + indptr_bytes + 4.0 * self.n_local
+        self.config = fcn_config(n_total, n_conn, rate, world, T)
+        if world > 1 and self.exchange_kind != P2P_TEXT:
+            self.config["spike_exchange"] = self.exchange_kind
 
     def timestep(self, t):
-        if self.emulate:
-            return self.be.binary_fcnmv(self.weights, self.indices, self.packed_pool[t % POOL],
-                                        shape=(self.n_total, self.n_local), transpose=True)
         if self.world == 1:
             return self.be.binary_fcnmv(self.weights, self.indices, self.pool[t % POOL],
                                         shape=(self.n_total, self.n_local), transpose=True)
+        if self.emulate:
+            for r in range(1, self.world):
+                self.peers[r].publish_only(self.peer_pools[r][t % POOL])
         return self.proj.step(self.pool[t % POOL])
 
+    def reference_cuda_timestep(self, R, t):
+        if self.world != 1:
+            return None
+        if getattr(self, "_ref_out", None) is None:
+            self._ref_out = self.torch.empty(self.n_local, device=self.device)
+        return R.binary_fcnmv_scatter(self.weights, self.indices, self.pool[t % POOL], self.n_local, self._ref_out)
+
     def total_events_per_timestep(self):
-        return self.events_per_timestep * self.world
+        return self.active_per_timestep * self.n_conn          # every synapse lands on exactly one rank
+
+    def release(self):
+        self.proj = self.x = None
+        for a in ("indptr", "indices", "weights"):
+            if hasattr(self, a):
+                delattr(self, a)
+        self.torch.cuda.empty_cache()
+
+
+def parity_block(torch, dist, be, wl):
+    """N > 1, before any timing: every rank checks its output block against an independent result and rank 0 gets
+    the verdict for the JSON line.  (1) three timesteps of the measured step vs NCCL all-gather of the bit-packed
+    spikes + the plain single-GPU operator (its own compaction + scatter kernels); (2) the gathered words of a second
+    peer-memory exchange vs NCCL's, bit for bit; (3) a timestep whose only active pre rows are a 2000-row slice owned by
+    rank 1, against the CPU oracle on this rank's shard of those rows.  Raises if anything differs."""
+    import oracle as O
+    from brainevent_b200 import dist as bd
+    dev, n, n_loc = wl.device, wl.n_total, wl.n_local
+    xn = bd.SpikeExchange(n, device=dev)
+    pack = bd.PostShardedProjection("csr", n, n, xn, data=wl.weights, indices=wl.indices, indptr=wl.indptr)
+    xp2 = bd.P2PSpikeExchange(n, device=dev) if isinstance(wl.x, bd.P2PSpikeExchange) else None
+    max_err, max_ref, ids_equal = 0.0, 0.0, True
+    for t in range(3):
+        mine = wl.pool[t]
+        out = wl.proj.step(mine).clone()
+        words = xn.exchange(pack.pack_local(mine)).clone()
+        ref = be.binary_csrmv(wl.weights, wl.indices, wl.indptr, be.BitPackedBinary(packed=words, shape=(n,)),
+                              shape=(n, n_loc), transpose=True)
+        max_err = max(max_err, float((out - ref).abs().max().item()))
+        max_ref = max(max_ref, float(ref.abs().max().item()))
+        if xp2 is not None:
+            ids_equal = ids_equal and bool(torch.equal(xp2.exchange_spikes(mine), words))
+    # oracle slice: rows [r0, r0 + 2000) of the GLOBAL vector, owned by rank 1, every third one active
+    r0 = wl.bounds[1][0] + 4096
+    rows = np.arange(r0, r0 + 2000)
+    active = rows[(rows - r0) % 3 == 0]
+    mine = torch.zeros(n_loc, dtype=torch.bool, device=dev)
+    if wl.rank == 1:
+        mine[torch.as_tensor(active - wl.lo, device=dev)] = True
+    out = wl.proj.step(mine).cpu().numpy()
+    ip = wl.indptr[r0:r0 + 2001].cpu().numpy().astype(np.int64)
+    sub_ip = (ip - ip[0]).astype(np.int32)
+    sub_ix = wl.indices[int(ip[0]):int(ip[-1])].cpu().numpy()
+    sub_w = wl.weights[int(ip[0]):int(ip[-1])].cpu().numpy()
+    sl = np.zeros(2000, bool)
+    sl[active - r0] = True
+    ref = O.binary_csrmv(sub_w, sub_ix, sub_ip, sl, shape=(2000, n_loc), transpose=True)
+    oracle_err = float(np.abs(out - ref).max())
+    timed_out = bool(wl.x.timed_out()) if hasattr(wl.x, "timed_out") else False
+    ok = (max_err <= 1e-5 * max(max_ref, 1.0) + 1e-5) and oracle_err <= 2e-5 and ids_equal and not timed_out
+    v = torch.tensor([max_err, oracle_err, 0.0 if ok else 1.0, 0.0 if ids_equal else 1.0], device=dev, dtype=torch.float64)
+    dist.all_reduce(v, op=dist.ReduceOp.MAX)
+    res = {"checked": True, "ok": bool(v[2].item() == 0.0), "timesteps": 3, "max_abs_err": float(v[0].item()),
+           "against": "NCCL all_gather of bit-packed spikes + binary_csrmv (separate compaction + scatter kernels) on the same shard",
+           "ids_equal_nccl": bool(v[3].item() == 0.0) if xp2 is not None else None,
+           "oracle_slice": {"rows": 2000, "active": int(active.size), "owner_rank": 1, "max_abs_err": float(v[1].item())}}
+    del pack, xn, xp2
+    if not res["ok"]:
+        raise RuntimeError(f"multi-GPU parity check failed: {res}")
+    return res
 
 
 class Coba(Workload):
@@ -213,6 +375,15 @@ class Coba(Workload):
             out = self.be.BinaryArray(pool[t % POOL]) @ csr
         return out
 
+    def reference_cuda_timestep(self, R, t):
+        # the reference's GPU default for spk @ csr: the hybrid scatter kernel (_csr/binary.py:564-621)
+        if getattr(self, "_ref", None) is None:
+            self._ref = [(R.HybridWorkspace(csr.indptr), csr.data.new_empty(4000)) for csr, _ in self.mats]
+        out = None
+        for (csr, pool), (ws, o) in zip(self.mats, self._ref):
+            out = R.binary_csrmv_t_hybrid(csr.data, csr.indices, csr.indptr, pool[t % POOL], 4000, ws, o)
+        return out
+
 
 class CubaJitc(Workload):
     name = "cuba_400k_jitc_scalar"
@@ -242,13 +413,26 @@ class CubaJitc(Workload):
             out = self.be.BinaryArray(pool[t % POOL]) @ m
         return out
 
+    def reference_cuda_timestep(self, R, t):
+        # spk @ M = operator call with transpose=True and corder = not M.corder (_jit_scalar/main.py:963-1011)
+        if getattr(self, "_ref", None) is None:
+            import torch
+            dev = self.mats[0][1].device
+            self._ref = [(torch.tensor([w], device=dev), torch.empty(400_000, device=dev)) for w in (1.62, -9.0)]
+        out = None
+        for (m, pool), (w, o), n_pre in zip(self.mats, self._ref, (320_000, 80_000)):
+            out = R.binary_jitsmv(w, 2e-4, pool[t % POOL], 42, shape=(n_pre, 400_000), transpose=True,
+                                  corder=not self.corder, out=o)
+        return out
+
 
 class CsrSpmm(Workload):
     name = "csr_1m_spmm_b64"
-    dominant_kernel = "scatter_mm_kernel"
+    dominant_kernel = "scatter_mm_bm_kernel"
 
     def __init__(self, torch, be, device, rate=0.01, batch=64):
         self.be = be
+        self.batch = batch
         n, nnz = 1_000_000, 100
         g = torch.Generator(device=device).manual_seed(7)
         self.indptr = torch.arange(0, (n + 1) * nnz, nnz, device=device, dtype=torch.int32)
@@ -268,6 +452,11 @@ class CsrSpmm(Workload):
     def timestep(self, t):
         return self.be.binary_csrmm(self.weights, self.indices, self.indptr, self.pool[t % 4], shape=(self.n, self.n),
                                     transpose=True)
+
+    def reference_cuda_timestep(self, R, t):
+        if getattr(self, "_ref", None) is None:
+            self._ref = (R.HybridWorkspace(self.indptr), self.weights.new_empty((self.batch, self.n)))
+        return R.binary_csrmm_t_hybrid(self.weights, self.indices, self.indptr, self.pool[t % 4], self.n, *self._ref)
 
 
 class CsrMv1M(Workload):
@@ -305,6 +494,15 @@ class CsrMv1M(Workload):
         return self.be.binary_csrmv(self.weights, self.indices, self.indptr, self.pool[t % POOL], shape=(self.n, self.n),
                                     transpose=not self.gather)
 
+    def reference_cuda_timestep(self, R, t):
+        if getattr(self, "_ref", None) is None:
+            import torch
+            self._ref = (R.HybridWorkspace(self.indptr), torch.empty(self.n, device=self.indices.device))
+        ws, out = self._ref
+        if self.gather:
+            return R.binary_csrmv_nt(self.weights, self.indices, self.indptr, self.pool[t % POOL], self.n, out)
+        return R.binary_csrmv_t_hybrid(self.weights, self.indices, self.indptr, self.pool[t % POOL], self.n, ws, out)
+
 
 class DenseMm(Workload):
     """BinaryArray @ dense at batch 64: the tcgen05 path (3 x bf16 split of the fp32 weights)."""
@@ -327,6 +525,11 @@ class DenseMm(Workload):
     def timestep(self, t):
         return self.be.binary_densemm(self.W, self.pool[t % 4], transpose=True)
 
+    def reference_cuda_timestep(self, R, t):
+        if getattr(self, "_ref", None) is None:
+            self._ref = self.W.new_empty((self.pool.shape[2], self.W.shape[1]))
+        return R.binary_densemm_transpose(self.W, self.pool[t % 4], self._ref)
+
 
 class Jitc1M(Workload):
     name = "jitc_normal_1m"
@@ -347,6 +550,15 @@ class Jitc1M(Workload):
     def timestep(self, t):
         return self.be.BinaryArray(self.pool[t % POOL]) @ self.m
 
+    def reference_cuda_timestep(self, R, t):
+        if getattr(self, "_ref", None) is None:
+            import torch
+            dev = self.pool.device
+            self._ref = (torch.tensor([1.0], device=dev), torch.tensor([0.1], device=dev), torch.empty(1_000_000, device=dev))
+        a, b, out = self._ref
+        return R.binary_jitnmv(a, b, 1e-3, self.pool[t % POOL], 123, shape=(1_000_000, 1_000_000), transpose=True,
+                               corder=not self.corder, out=out)
+
 
 class Jitc1MSharded(Workload):
     """BASELINE configs[3]: spk @ JITCNormalR 1 M x 1 M, prob 1e-3, post-sharded over the ranks with the
@@ -360,6 +572,7 @@ class Jitc1MSharded(Workload):
     def __init__(self, torch, be, rank, world, device, gather=False, rate=0.01):
         from brainevent_b200 import dist as bd
         self.world, n = world, 1_000_000
+        self.gather = gather
         self.dominant_kernel = "jit_mv_gather_kernel" if gather else "jit_mv_scatter_kernel"
         bounds = bd.post_block_bounds(n, world)
         lo, hi = bounds[rank]
@@ -464,16 +677,31 @@ def kernel_profile(torch, L, wl, T, kernels_per_timestep_filter=None):
     return ms
 
 
+def traffic_key(wl):
+    k = wl.name
+    if isinstance(wl, FcnSharded):
+        if wl.world > 1:
+            k += f"_w{wl.world}"
+        if wl.scaling == "strong":
+            k += "_full"
+    elif isinstance(wl, (CubaJitc, Jitc1M)):
+        k += "_scatter" if wl.corder else "_gather"
+    elif isinstance(wl, CsrMv1M):
+        k += ("_gather" if wl.gather else "_scatter") + ("_homo" if wl.weights.numel() == 1 else "_hetero")
+    elif isinstance(wl, Jitc1MSharded):
+        k += ("_gather" if wl.gather else "_scatter") + f"_w{wl.world}"
+    return k
+
+
 def measured_traffic(wl):
-    """DRAM bytes per launch of the dominant kernel from the committed ncu capture (None if this
-    workload has not been captured)."""
+    """DRAM bytes (dram__bytes_read.sum + dram__bytes_write.sum) per launch of the dominant kernel from the committed
+    ncu --set full capture of this workload (profiles/traffic.json, written by tools/summarize_ncu.py; multi-GPU
+    shards are captured on one GPU with the peers' exchange buffers emulated locally).  None if not captured."""
     try:
         with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
             t = json.load(f)
-        key = wl.name + ("_shard8" if getattr(wl, "emulate", 0) == 8 else "")
-        if getattr(wl, "world", 1) > 1:
-            return None
-        return t[key]["bytes_per_launch"] if key in t else None
+        e = t.get(traffic_key(wl))
+        return e["bytes_per_launch"] if e else None
     except Exception:
         return None
 
@@ -515,19 +743,21 @@ def run_reference(args):
     import oracle as O
     O.build()
     K, W = args.steps, args.warmup
+    world = max(args.gpus, 1)
+    n_total = FCN_NEURONS_PER_GPU * world
     reps_per_step = 4
-    times, sample = cpu_fcn_sample(reps=(K + W) * reps_per_step)
+    times, sample = cpu_fcn_sample(n_post=n_total, reps=(K + W) * reps_per_step)
     times = times[W * reps_per_step:]
     total_t = sum(t for t, _ in times)
     total_ev = sum(e for _, e in times)
     value = total_ev / total_t
+    cfg = fcn_config(n_total, FCN_CONN, RATE, world, args.timesteps)
     line = {"impl": "reference", "metric": "synaptic events/sec", "value": value, "unit": "events/s",
             "n_gpus": args.gpus, "steps": K, "warmup": W, "ms_per_step": 1e3 * total_t / K,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": fcn_workload_text(FCN_NEURONS_PER_GPU * max(args.gpus, 1), FCN_CONN, RATE, max(args.gpus, 1)),
-                       "neurons": FCN_NEURONS_PER_GPU * max(args.gpus, 1), "synapses_per_neuron": FCN_CONN, "spike_rate": RATE,
-                       "reference_arm": "reference algorithm (oracle port of _fcn/binary.py:156-253) on the host CPU, bounded "
-                                        "sample of the pre rows of the same projection"},
+            "config": cfg,
+            "reference_arm": "reference algorithm (oracle port of _fcn/binary.py:156-253, the numba scatter kernel) on the "
+                             "host CPU, one core (the kernel is serial in the reference), bounded sample of the pre rows",
             "cpu_baseline": {"value": value, "unit": "events/s", "cores": 1, "kind": "port", "sample": sample},
             "e2e": {"value": value, "unit": "events/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
@@ -548,6 +778,43 @@ def measure_workload(torch, dist, L, wl, K, W, T, world, peak, peak_src, sampler
             "events_per_step": total_events}
 
 
+def reference_cuda_us(torch, wl, T):
+    """Per-timestep time (us) of the reference's OWN CUDA kernels for this workload (unmodified sources recompiled
+    for sm_100a into oracle/_ref; test/bench infrastructure), same device buffers and spike vectors, replayed from a
+    CUDA graph of T timesteps like our side.  None when the library is absent or the workload has no twin."""
+    if not hasattr(wl, "reference_cuda_timestep"):
+        return None
+    try:
+        from oracle import ref_cuda as R
+        if wl.reference_cuda_timestep(R, 0) is None:
+            return None
+        s = torch.cuda.Stream()
+        s.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(s):
+            wl.reference_cuda_timestep(R, 1)
+        torch.cuda.current_stream().wait_stream(s)
+        torch.cuda.synchronize()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g, stream=s):
+            for t in range(T):
+                wl.reference_cuda_timestep(R, t)
+        for _ in range(2):
+            g.replay()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        reps = 3
+        e0.record()
+        for _ in range(reps):
+            g.replay()
+        e1.record()
+        torch.cuda.synchronize()
+        return round(e0.elapsed_time(e1) * 1e3 / (reps * T), 2)
+    except Exception as e:  # pragma: no cover - the comparison library is optional
+        sys.stderr.write(f"[bench] reference CUDA timing unavailable for {wl.name} ({type(e).__name__}: {e})\n")
+        torch.cuda.synchronize()
+        return None
+
+
 _REAL_STDOUT = None
 
 
@@ -566,6 +833,88 @@ def emit(line):
     out.flush()
 
 
+def e2e_leg(torch, dist, L, wl, world, device, K, T, numa_bound):
+    """Same metric end to end: per timestep this rank's spike block comes from pinned host memory and its output block
+    goes back to pinned host memory, through the C ABI (N = 1: be_b200_projection_submit_host/_wait; N > 1:
+    be_b200_sharded_run_host, csrc/sharded.cu -- the whole block of timesteps is ONE C call per rank)."""
+    n_in, n_out = wl.n_local, wl.n_local
+    host_spk = [torch.empty(n_in, dtype=torch.uint8).pin_memory() for _ in range(POOL)]
+    for i in range(POOL):
+        host_spk[i].copy_(wl.pool[i].to(torch.uint8))
+    host_out = [torch.empty(n_out, dtype=torch.float32).pin_memory() for _ in range(4)]
+    Te = min(T, 50)
+    sync_value = None
+    lib = L.lib()
+    if world == 1:
+        proj = lib.be_b200_projection_adopt_fcn(ctypes.c_void_p(wl.weights.data_ptr()), 0,
+                                                ctypes.c_void_p(wl.indices.data_ptr()), wl.n_total, wl.n_conn, wl.n_local)
+        assert proj, lib.be_b200_last_error()
+        proj = ctypes.c_void_p(proj)
+
+        def e2e_step_sync():
+            for t in range(Te):
+                rc = lib.be_b200_projection_apply_host(proj, ctypes.c_void_p(host_spk[t % POOL].data_ptr()),
+                                                       ctypes.c_void_p(host_out[0].data_ptr()))
+                assert rc == 0
+
+        def e2e_step():
+            # pipelined C-ABI entry: copy-in / hot path / copy-out of neighbouring timesteps overlap;
+            # every timestep still moves its own inputs in and its own result out
+            for t in range(Te):
+                rc = lib.be_b200_projection_submit_host(proj, ctypes.c_void_p(host_spk[t % POOL].data_ptr()),
+                                                        ctypes.c_void_p(host_out[t % 4].data_ptr()))
+                assert rc == 0
+            assert lib.be_b200_projection_wait(proj) == 0
+
+        for _ in range(2):
+            e2e_step_sync()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(3):
+            e2e_step_sync()
+        sync_value = wl.total_events_per_timestep() * Te * 3 / (time.perf_counter() - t0)
+        entry = ("be_b200_projection_submit_host/_wait (C ABI, 4 calls in flight; `sync_value` is the blocking "
+                 "be_b200_projection_apply_host)")
+    else:
+        from brainevent_b200 import dist as bd
+        pipe = bd.HostStepPipeline(wl.proj, n_in, slots=4)
+
+        def e2e_step():
+            pipe.run(Te, host_spk, host_out)
+        entry = ("be_b200_sharded_run_host (C ABI, csrc/sharded.cu: one call per block of timesteps, 4 in flight, a CUDA "
+                 "graph of the fused step per slot)" if pipe.native else
+                 "HostStepPipeline.submit/wait over PostShardedProjection.step (Python-driven, NCCL exchange)")
+    for _ in range(2):
+        e2e_step()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    Ke = max(3, min(K, 10))
+    t0 = time.perf_counter()
+    for _ in range(Ke):
+        e2e_step()
+    torch.cuda.synchronize()
+    dt = torch.tensor([time.perf_counter() - t0], device=device, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+    e2e_events = wl.total_events_per_timestep() * Te * Ke
+    e2e = {"value": e2e_events / float(dt.item()), "unit": "events/s",
+           "h2d_bytes_per_step": int(n_in * T), "d2h_bytes_per_step": int(4 * n_out * T),
+           "us_per_timestep": round(float(dt.item()) * 1e6 / (Te * Ke), 2), "numa_bound": bool(numa_bound),
+           "host_cpus": len(os.sched_getaffinity(0)),
+           "note": f"per timestep and rank: pinned host spikes (uint8[{n_in}]) -> device, hot path, fp32[{n_out}] result -> "
+                   f"pinned host; timed over {Ke}x{Te} timesteps with the host clock (max over ranks), bytes scaled to "
+                   f"{T} timesteps/step; entry point: " + entry}
+    if sync_value is not None:
+        e2e["sync_value"] = sync_value
+    if world == 1:
+        lib.be_b200_projection_destroy(proj)
+    else:
+        pipe.close()        # also raises on every rank if a spike-exchange wait ever timed out
+        del pipe
+    return e2e
+
+
 def main():
     _claim_stdout()
     ap = argparse.ArgumentParser()
@@ -573,14 +922,16 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default="fcn", choices=["fcn", "coba", "cuba_jitc", "csr_spmm", "jitc_1m", "csr_gather", "csr_scatter", "dense_mm", "jitc_1m_gather",
+    ap.add_argument("--workload", default="fcn", choices=["fcn", "fcn_full", "coba", "cuba_jitc", "cuba_jitc_gather", "csr_spmm", "jitc_1m",
+                                                           "csr_gather", "csr_gather_hetero", "csr_scatter", "dense_mm", "jitc_1m_gather",
                                                            "jitc_1m_sharded", "jitc_1m_sharded_gather"])
     ap.add_argument("--timesteps", type=int, default=100, help="simulated timesteps per step")
-    ap.add_argument("--no-extra", action="store_true", help="skip the other BASELINE configs at N=1")
+    ap.add_argument("--no-extra", action="store_true", help="skip the strong-scaling leg and the other BASELINE configs")
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--emulate-world", type=int, default=0,
-                    help="(profiling) run rank 0's shard of an N-GPU post-sharded fcn run on one GPU, no exchange")
+                    help="(profiling) rank 0's shard of an N-GPU post-sharded fcn run on ONE GPU, the peers' exchange buffers emulated locally")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     if args.impl == "reference":
@@ -608,16 +959,20 @@ def main():
     peak, peak_src = peaks()
     K, W, T = args.steps, args.warmup, args.timesteps
 
+    is_fcn = args.workload in ("fcn", "fcn_full")
     if args.workload == "fcn":
-        wl = FcnWeak(torch, be, rank, world, device, emulate_world=args.emulate_world)
+        n_total = FCN_NEURONS_PER_GPU * (args.emulate_world or world)
+        wl = FcnSharded(torch, be, rank, world, device, n_total, T=T, emulate_world=args.emulate_world)
+    elif args.workload == "fcn_full":
+        wl = FcnSharded(torch, be, rank, world, device, C5_NEURONS, T=T, scaling="strong", emulate_world=args.emulate_world)
     elif args.workload == "coba":
         wl = Coba(torch, be, device)
-    elif args.workload == "cuba_jitc":
-        wl = CubaJitc(torch, be, device, corder=True)
+    elif args.workload in ("cuba_jitc", "cuba_jitc_gather"):
+        wl = CubaJitc(torch, be, device, corder=not args.workload.endswith("gather"))
     elif args.workload == "csr_spmm":
         wl = CsrSpmm(torch, be, device)
-    elif args.workload == "csr_gather":
-        wl = CsrMv1M(torch, be, device, gather=True, homo=True)
+    elif args.workload in ("csr_gather", "csr_gather_hetero"):
+        wl = CsrMv1M(torch, be, device, gather=True, homo=not args.workload.endswith("hetero"))
     elif args.workload == "csr_scatter":
         wl = CsrMv1M(torch, be, device, gather=False)
     elif args.workload == "dense_mm":
@@ -629,104 +984,91 @@ def main():
     else:
         wl = Jitc1M(torch, be, device, corder=True)
 
+    # ---- multi-GPU parity: checked BEFORE anything is timed; the run fails if a block differs ----------
+    parity = None
+    if world > 1 and is_fcn and not args.emulate_world:
+        parity = parity_block(torch, dist, be, wl)
+
     sampler = ClockSampler(local_rank) if rank == 0 else None
     res = measure_workload(torch, dist, L, wl, K, W, T, world, peak, peak_src, sampler, not args.no_graph)
-    if world > 1 and hasattr(getattr(wl, "x", None), "timed_out"):
-        # the peer-memory exchange bounds its flag waits; a wait that gave up means a peer never
-        # published (results would be stale): fall back to NCCL on every rank and measure again
-        bad = torch.tensor([int(wl.x.timed_out())], device=device)
-        dist.all_reduce(bad, op=dist.ReduceOp.MAX)
-        if int(bad.item()) and args.workload != "fcn":
-            raise RuntimeError("peer-memory spike exchange timed out (a peer never published); rerun with BE_B200_EXCHANGE=nccl")
-        if int(bad.item()):
-            sys.stderr.write("[bench] peer-memory exchange timed out; re-measuring with the NCCL all-gather\n")
-            del wl
-            torch.cuda.empty_cache()
-            wl = FcnWeak(torch, be, rank, world, device, emulate_world=args.emulate_world, exchange="nccl")
-            sampler = ClockSampler(local_rank) if rank == 0 else None
-            res = measure_workload(torch, dist, L, wl, K, W, T, world, peak, peak_src, sampler, not args.no_graph)
+    if world > 1 and hasattr(getattr(wl, "x", None), "check"):
+        wl.x.check()        # a flag wait that gave up is fatal on every rank (results would be stale)
+    ref_main_us = None
+    if world == 1 and not args.no_extra and not args.emulate_world and not (is_fcn and wl.n_total > 2_000_000):
+        ref_main_us = reference_cuda_us(torch, wl, 16)     # (not on the 1e10-synapse network: the reference indexes in int32)
 
     # ---- e2e: host buffers in, host buffers out, every timestep -------------------------------
     e2e = None
-    if args.workload == "fcn" and not args.emulate_world:
-        n_in, n_out = wl.n_local, wl.n_local
-        host_spk = [torch.empty(n_in, dtype=torch.uint8).pin_memory() for _ in range(POOL)]
-        for i in range(POOL):
-            host_spk[i].copy_(wl.pool[i].to(torch.uint8))
-        host_out = [torch.empty(n_out, dtype=torch.float32).pin_memory() for _ in range(4)]
-        Te = min(T, 50)
-        sync_value = None
-        if world == 1:
-            lib = L.lib()
-            proj = lib.be_b200_projection_adopt_fcn(ctypes.c_void_p(wl.weights.data_ptr()), 0,
-                                                    ctypes.c_void_p(wl.indices.data_ptr()), wl.n_total,
-                                                    wl.conn_local, wl.n_local)
-            assert proj, lib.be_b200_last_error()
-            proj = ctypes.c_void_p(proj)
+    if is_fcn and not args.emulate_world and not args.no_e2e:
+        e2e = e2e_leg(torch, dist, L, wl, world, device, K, T, numa_bound)
 
-            def e2e_step_sync():
-                for t in range(Te):
-                    rc = lib.be_b200_projection_apply_host(proj, ctypes.c_void_p(host_spk[t % POOL].data_ptr()),
-                                                           ctypes.c_void_p(host_out[0].data_ptr()))
-                    assert rc == 0
-
-            def e2e_step():
-                # pipelined C-ABI entry: copy-in / hot path / copy-out of neighbouring timesteps overlap;
-                # every timestep still moves its own inputs in and its own result out
-                for t in range(Te):
-                    rc = lib.be_b200_projection_submit_host(proj, ctypes.c_void_p(host_spk[t % POOL].data_ptr()),
-                                                            ctypes.c_void_p(host_out[t % 4].data_ptr()))
-                    assert rc == 0
-                assert lib.be_b200_projection_wait(proj) == 0
-
-            for _ in range(2):
-                e2e_step_sync()
-            torch.cuda.synchronize()
-            t0 = time.perf_counter()
-            for _ in range(3):
-                e2e_step_sync()
-            sync_value = wl.total_events_per_timestep() * Te * 3 / (time.perf_counter() - t0)
+    # ---- strong scaling: the FULL 10 M x 1000 network on these N GPUs (all ranks take part) -----------
+    strong = None
+    if args.workload == "fcn" and not args.no_extra and not args.emulate_world:
+        if wl.n_total == C5_NEURONS:
+            strong = {"same_as_main_line": True, "value": res["value"], "us_per_timestep": round(res["ms_per_step"] * 1e3 / T, 2)}
         else:
-            from brainevent_b200 import dist as bd
-            pipe = bd.HostStepPipeline(wl.proj, n_in, slots=4)
+            wl.release()
+            try:
+                w_full = FcnSharded(torch, be, rank, world, device, C5_NEURONS, T=T, scaling="strong")
+                Ts = min(T, 50)
+                r_full = measure_workload(torch, dist, L, w_full, max(3, min(K, 5)), 3, Ts, world, peak, peak_src)
+                if world > 1 and hasattr(w_full.x, "check"):
+                    w_full.x.check()
+                strong = {"workload": w_full.config["workload"], "value": r_full["value"], "unit": "events/s",
+                          "us_per_timestep": round(r_full["ms_per_step"] * 1e3 / Ts, 2), "roofline": r_full["roofline"],
+                          "bytes_resident_per_gpu": int(w_full.indices.numel() * 8),
+                          "note": "strong scaling: the same 10 000 128 x 1000 matrix at every N (counter-based chunk seeds); "
+                                  "N = 8 is the main line itself"}
+                w_full.release()
+                del w_full
+            except Exception as e:  # pragma: no cover
+                strong = {"error": f"{type(e).__name__}: {e}"}
+                torch.cuda.synchronize()
+            torch.cuda.empty_cache()
 
-            def e2e_step():
-                # pipelined like the single-GPU C-ABI entry: four timesteps in flight per rank, each moving
-                # its own spike block in and its own output block out
-                for t in range(Te):
-                    pipe.submit(host_spk[t % POOL], host_out[t % 4])
-                pipe.wait()
-        for _ in range(2):
-            e2e_step()
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-        Ke = max(3, min(K, 10))
-        t0 = time.perf_counter()
-        for _ in range(Ke):
-            e2e_step()
-        torch.cuda.synchronize()
-        dt = torch.tensor([time.perf_counter() - t0], device=device, dtype=torch.float64)
-        if world > 1:
-            dist.all_reduce(dt, op=dist.ReduceOp.MAX)
-        e2e_events = wl.total_events_per_timestep() * Te * Ke
-        e2e = {"value": e2e_events / float(dt.item()), "unit": "events/s",
-               "h2d_bytes_per_step": int(n_in * T), "d2h_bytes_per_step": int(4 * n_out * T),
-               "numa_bound": bool(numa_bound),
-               "note": f"per timestep: pinned host spikes (uint8[{n_in}]) -> device, hot path, fp32[{n_out}] result -> "
-                       f"pinned host, stream sync; timed over {Ke}x{Te} timesteps with the host clock, bytes scaled to "
-                       f"{T} timesteps/step; entry point: " +
-                       ("be_b200_projection_submit_host/_wait (C ABI, 4 calls in flight; `sync_value` is the "
-                        "blocking be_b200_projection_apply_host)" if world == 1 else
-                        "HostStepPipeline.submit/wait over PostShardedProjection.step (per rank: its own spike block in, its "
-                        "own output block out, 4 timesteps in flight)")}
-        if sync_value is not None:
-            e2e["sync_value"] = sync_value
+    # ---- other BASELINE configs ---------------------------------------------------------------------------
+    others = []
+    if args.workload == "fcn" and not args.no_extra and not args.emulate_world:
+        if hasattr(wl, "release"):
+            wl.release()
         if world == 1:
-            L.lib().be_b200_projection_destroy(proj)
+            makers = (lambda: Coba(torch, be, device),
+                      lambda: CubaJitc(torch, be, device, corder=True),
+                      lambda: CubaJitc(torch, be, device, corder=False),
+                      lambda: Jitc1M(torch, be, device, corder=True),
+                      lambda: Jitc1M(torch, be, device, corder=False),
+                      lambda: CsrMv1M(torch, be, device, gather=False),
+                      lambda: CsrMv1M(torch, be, device, gather=True, homo=True),
+                      lambda: CsrMv1M(torch, be, device, gather=True, homo=False),
+                      lambda: CsrSpmm(torch, be, device),
+                      lambda: DenseMm(torch, be, device))
         else:
-            pipe.close()        # graphs that captured NCCL collectives must go before the group is destroyed
-            del pipe, e2e_step
+            # BASELINE configs[3] at N GPUs: the fixed 1 M x 1 M JITCNormalR matrix, post-sharded (strong scaling)
+            makers = (lambda: Jitc1MSharded(torch, be, rank, world, device, gather=False),
+                      lambda: Jitc1MSharded(torch, be, rank, world, device, gather=True))
+        for make in makers:
+            try:
+                w2 = make()
+                heavy = isinstance(w2, (CsrSpmm, DenseMm)) or (isinstance(w2, Jitc1M) and not w2.corder) or \
+                    (isinstance(w2, Jitc1MSharded) and w2.gather)
+                T2 = 4 if heavy else 50
+                r2 = measure_workload(torch, dist, L, w2, 3 if heavy else 5, 3, T2, world, peak, peak_src)
+                if world > 1 and hasattr(getattr(w2, "x", None), "check"):
+                    w2.x.check()
+                entry = {"workload": w2.config["workload"], "value": r2["value"], "unit": "events/s",
+                         "ms_per_timestep": r2["ms_per_step"] / T2, "cuda_graph": r2["graph"], "roofline": r2["roofline"]}
+                if world == 1:
+                    ref_us = reference_cuda_us(torch, w2, T2 if heavy else 16)
+                    entry["reference_cuda_us"] = ref_us
+                    if ref_us:
+                        entry["vs_reference_cuda"] = round(ref_us / (entry["ms_per_timestep"] * 1e3), 2)
+                others.append(entry)
+                del w2
+                torch.cuda.empty_cache()
+            except Exception as e:  # pragma: no cover
+                others.append({"workload": "failed", "error": f"{type(e).__name__}: {e}"})
+                torch.cuda.synchronize()
 
     if rank != 0:
         if world > 1:
@@ -741,42 +1083,24 @@ def main():
         tt, ee = sum(t for t, _ in times), sum(e for _, e in times)
         cpu = {"value": ee / tt, "unit": "events/s", "cores": 1, "kind": "port", "sample": sample}
 
-    others = []
-    if world == 1 and not args.no_extra and args.workload == "fcn":
-        del wl.weights, wl.indices, wl.proj
-        torch.cuda.empty_cache()
-        for make in (lambda: Coba(torch, be, device),
-                     lambda: CubaJitc(torch, be, device, corder=True),
-                     lambda: CubaJitc(torch, be, device, corder=False),
-                     lambda: Jitc1M(torch, be, device, corder=True),
-                     lambda: Jitc1M(torch, be, device, corder=False),
-                     lambda: CsrMv1M(torch, be, device, gather=False),
-                     lambda: CsrMv1M(torch, be, device, gather=True, homo=True),
-                     lambda: CsrMv1M(torch, be, device, gather=True, homo=False),
-                     lambda: CsrSpmm(torch, be, device),
-                     lambda: DenseMm(torch, be, device)):
-            try:
-                w2 = make()
-                heavy = isinstance(w2, (CsrSpmm, DenseMm)) or (isinstance(w2, Jitc1M) and not w2.corder)
-                r2 = measure_workload(torch, dist, L, w2, 3 if heavy else 5, 3, 4 if heavy else 50, 1, peak, peak_src)
-                others.append({"workload": w2.config["workload"], "value": r2["value"], "unit": "events/s",
-                               "ms_per_timestep": r2["ms_per_step"] / (4 if heavy else 50), "roofline": r2["roofline"]})
-                del w2
-                torch.cuda.empty_cache()
-            except Exception as e:  # pragma: no cover
-                others.append({"workload": "failed", "error": f"{type(e).__name__}: {e}"})
-
     cfg = dict(wl.config)
-    cfg.update({"timesteps_per_step": T, "cuda_graph": res["graph"],
-                "l2_policy": f"inputs larger than L2: {POOL} distinct spike vectors cycle, so the active-row "
-                             "working set of one cycle (~1.6 GB of a 10 GB matrix) exceeds the 126 MB L2",
-                "parallelism": f"post-sharded x{world}" if world > 1 else "single GPU"})
+    if "timesteps_per_step" not in cfg:
+        cfg.update({"timesteps_per_step": T,
+                    "l2_policy": f"inputs larger than L2: {POOL} distinct spike vectors cycle through the timesteps",
+                    "parallelism": f"post-sharded x{world}" if world > 1 else "single GPU"})
     line = {"metric": "synaptic events/sec", "value": res["value"], "unit": "events/s", "n_gpus": world,
             "steps": K, "warmup": W, "ms_per_step": res["ms_per_step"], "higher_is_better": True,
             "scaling": getattr(wl, "scaling", "weak"), "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": cfg,
-            "roofline": res["roofline"], "cpu_baseline": cpu, "e2e": e2e,
+            "cuda_graph": res["graph"], "roofline": res["roofline"], "cpu_baseline": cpu, "e2e": e2e,
             "gpu_launches": int(wl.launches_per_timestep * T * K), "clocks": res["clocks"],
             "events_per_step": res["events_per_step"]}
+    if ref_main_us:
+        line["reference_cuda_us"] = ref_main_us
+        line["vs_reference_cuda"] = round(ref_main_us / (res["ms_per_step"] * 1e3 / T), 2)
+    if parity is not None:
+        line["parity"] = parity
+    if strong is not None:
+        line["strong_scaling"] = strong
     if others:
         line["other_workloads"] = others
     emit(line)

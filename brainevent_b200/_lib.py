@@ -6,6 +6,7 @@ raises -- there is NO CPU or PyTorch fallback (north star: "no CPU fallback").
 import ctypes
 import os
 import subprocess
+import threading
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libbrainevent_b200.so")
@@ -18,6 +19,37 @@ SPK_COMPACT_CLEARED = 4      # COMPACT whose producer already cleared the consum
 JIT_SCALAR, JIT_NORMAL, JIT_UNIFORM = 0, 1, 2
 
 _lib = None
+_tls = threading.local()
+
+
+def note_device(index):
+    """_runtime.stream_ptr() records the device whose stream the next C call is enqueued on; the guarded
+    library below switches the current device for that one call if it differs (kernels, memsets and
+    function attributes apply to the CURRENT device, not to the stream's)."""
+    _tls.device = index
+
+
+class _GuardedLib:
+    """ctypes library whose calls run with the device recorded by note_device() current."""
+
+    def __init__(self, L):
+        self._L = L
+
+    def __getattr__(self, name):
+        fn = getattr(self._L, name)
+
+        def call(*args):
+            dev = _tls.__dict__.pop("device", None)
+            if dev is not None:
+                import torch
+                if dev != torch.cuda.current_device():
+                    with torch.cuda.device(dev):
+                        return fn(*args)
+            return fn(*args)
+
+        call.__name__ = name
+        setattr(self, name, call)
+        return call
 
 
 class KernelLoadError(RuntimeError):
@@ -86,6 +118,23 @@ _SIGNATURES = {
     "be_b200_wait_exchange": (_I, [_P, _P, _I, _L, _P, _P, _P]),
     "be_b200_pack_publish_reset": (_I, [_P, _I, _L, _P, _P, _I, _I, _L, _P, _P, _P]),
     "be_b200_wait_exchange_compact": (_I, [_P, _P, _I, _L, _L, _P, _P, _P, _Z, _P, _P]),
+    "be_b200_pack_publish_clear": (_I, [_P, _I, _L, _P, _P, _I, _I, _L, _P, _P, _P, _Z, _P]),
+    "be_b200_sharded_symm_bytes": (_Z, [_I, _L]),
+    "be_b200_sharded_create": (_P, [_I, _I, _L, _L, _L, _P, _P]),
+    "be_b200_sharded_set_fcn": (_I, [_P, _P, _I, _I, _P, _L, _L]),
+    "be_b200_sharded_set_csr": (_I, [_P, _P, _I, _I, _P, _P, _I, _L, _L]),
+    "be_b200_sharded_set_jitc": (_I, [_P, _I, _P, _P, _I, _P, _P, _L, _L, _I]),
+    "be_b200_sharded_set_dense": (_I, [_P, _P, _I]),
+    "be_b200_sharded_set_option": (_I, [_P, ctypes.c_char_p, _L]),
+    "be_b200_sharded_step": (_I, [_P, _P, _I, _P, _P]),
+    "be_b200_sharded_publish": (_I, [_P, _P, _I, _P, _P]),
+    "be_b200_sharded_consume": (_I, [_P, _P, _P]),
+    "be_b200_sharded_timed_out": (_I, [_P]),
+    "be_b200_sharded_host_init": (_I, [_P, _I, _I]),
+    "be_b200_sharded_submit_host": (_I, [_P, _P, _P]),
+    "be_b200_sharded_wait": (_I, [_P]),
+    "be_b200_sharded_run_host": (_I, [_P, _L, _P, _I, _P, _I]),
+    "be_b200_sharded_destroy": (None, [_P]),
     "be_b200_projection_create_csr": (_P, [_P, _I, _P, _P, _L, _L]),
     "be_b200_projection_create_fcn": (_P, [_P, _I, _P, _L, _L, _L]),
     "be_b200_projection_adopt_fcn": (_P, [_P, _I, _P, _L, _L, _L]),
@@ -116,7 +165,7 @@ def lib():
             fn = getattr(L, name)
             fn.restype = res
             fn.argtypes = args
-        _lib = L
+        _lib = _GuardedLib(L)
     return _lib
 
 

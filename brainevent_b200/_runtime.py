@@ -22,6 +22,12 @@ def ptr(t):
 
 
 def stream_ptr(device=None):
+    """Handle of the current stream of `device`; also tells the library binding which device the call that
+    takes this handle must run on (see _lib.note_device)."""
+    if device is not None:
+        idx = torch.device(device).index
+        if idx is not None:
+            _lib.note_device(idx)
     return ctypes.c_void_p(torch.cuda.current_stream(device).cuda_stream)
 
 

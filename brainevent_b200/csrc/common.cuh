@@ -38,7 +38,10 @@ int cuda_fail(cudaError_t e, const char* what);
         if (e__ != cudaSuccess) return ::be::cuda_fail(e__, name);      \
     } while (0)
 
-constexpr int kNumSM = 148;  // B200: 2 dies x 74 SMs
+// SM count of the CURRENT device, queried once per device (148 on B200: 2 dies x 74 SMs);
+// every persistent grid is sized from it.
+int sm_count();
+#define kNumSM (::be::sm_count())
 constexpr int kWarp = 32;
 
 __host__ __device__ static inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }

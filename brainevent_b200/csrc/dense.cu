@@ -212,12 +212,8 @@ static int run_dense_mm(const T* W, int64_t rows, int64_t cols, const Events& ev
         int slices = (int)std::max<int64_t>(1, std::min<int64_t>(32, (2 * kNumSM) / row_blocks));
         if (slices > 1) BE_CUDA(cudaMemsetAsync(out, 0, (size_t)(m * n) * sizeof(T), s));
         const size_t smem = (size_t)kDmmCols * 257 * sizeof(A);
-        static bool attr_set[4] = {false, false, false, false};
-        const int slot = sizeof(T) == 8 ? 1 : (std::is_same<T, __half>::value ? 2 : (std::is_same<T, __nv_bfloat16>::value ? 3 : 0));
-        if (!attr_set[slot]) {
-            BE_CUDA(cudaFuncSetAttribute(dense_mm_t_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            attr_set[slot] = true;
-        }
+        // the attribute is per device/context: set it on every call (cheap) rather than caching a process-wide flag
+        BE_CUDA(cudaFuncSetAttribute(dense_mm_t_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         dim3 grid((unsigned)row_blocks, (unsigned)slices);
         { ProfileScope prof(s); dense_mm_t_kernel<T><<<grid, 256, smem, s>>>(W, m, ev.packed, wpr, ev.active_ids, ev.n_active, n, out); }
         BE_LAUNCH_CHECK("dense_mm_t_kernel");

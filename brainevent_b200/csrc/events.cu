@@ -27,6 +27,18 @@ int cuda_fail(cudaError_t e, const char* what) {
     return BE_B200_EINTERNAL;
 }
 
+int sm_count() {
+    static int cached[64] = {0};      // benign race: every writer stores the same value
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 148;
+    int n = cached[dev];
+    if (n == 0) {
+        if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+        cached[dev] = n;
+    }
+    return n;
+}
+
 // ------------------------------------------------------------------------------------------
 // kernel-duration profiling (diagnostic; process-wide)
 // ------------------------------------------------------------------------------------------

@@ -17,58 +17,27 @@
 // that peer's step t consumption in stream order), so parity t never overwrites words of step t
 // that a slower peer is still reading.  The wait kernel copies the current half into a fixed
 // local buffer, so consumers (and CUDA graphs) see one static pointer.
-#include "common.cuh"
+#include "exchange.cuh"
 
 #include <algorithm>
 
 namespace be {
-
-__device__ __forceinline__ void st_release_sys(uint32_t* p, uint32_t v) {
-    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
-}
-__device__ __forceinline__ void st_relaxed_sys(uint32_t* p, uint32_t v) {
-    asm volatile("st.relaxed.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
-}
-__device__ __forceinline__ uint32_t ld_relaxed_sys(const uint32_t* p) {
-    uint32_t v;
-    asm volatile("ld.relaxed.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-    return v;
-}
-__device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* p) {
-    uint32_t v;
-    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-    return v;
-}
-
-struct ExchangeCtl {      // local (non-symmetric) control block, zero-initialised by the caller
-    uint32_t step;        // exchanges completed by this rank
-    uint32_t done;        // blocks of the pack kernel in flight that have finished their stores
-    uint32_t timeout;     // set when a wait gave up (peer never published): surfaced by the host
-    uint32_t pad;
-    // %globaltimer stamps of the last exchange (diagnostics, tools/mgpu_exchange_bench.py):
-    // [0] pack start, [1] last pack CTA after its fence, [2] flags published,
-    // [3] wait start, [4] all flags seen, [5] copy done
-    unsigned long long stamp[8];
-};
-__device__ __forceinline__ unsigned long long gtimer() {
-    unsigned long long t;
-    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
-    return t;
-}
 
 template <int KIND>
 __global__ void __launch_bounds__(256) pack_publish_kernel(const void* __restrict__ spikes, int64_t n_local,
                                                            uint32_t* const* __restrict__ peer_bufs,
                                                            uint32_t* const* __restrict__ peer_flags, int world,
                                                            int rank, int64_t words_per_rank, ExchangeCtl* ctl,
-                                                           int32_t* __restrict__ reset_counter) {
+                                                           int32_t* __restrict__ reset_counter,
+                                                           int4* __restrict__ zero_ptr, size_t zero_vec16) {
     const uint32_t t = ctl->step + 1;      // read by every block before the last one bumps it
     const int lane = threadIdx.x & 31;
     if (blockIdx.x == 0 && threadIdx.x == 0) {
         ctl->stamp[0] = gtimer();
-        // n_active of the fused wait + compaction below: the previous step's consumer is behind us in
-        // stream order, this step's wait kernel ahead of us
+        // n_active of the fused wait + compaction below / chunk cursor of the fused exchange + scatter:
+        // the previous step's consumer is behind us in stream order, this step's ahead of us
         if (reset_counter != nullptr) *reset_counter = 0;
+        ctl->next_chunk = 0u;
     }
     const int64_t slot0 = (int64_t)(t & 1u) * words_per_rank * world + (int64_t)rank * words_per_rank;
     for (int64_t h = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; (h - lane) < 2 * words_per_rank;
@@ -114,6 +83,13 @@ __global__ void __launch_bounds__(256) pack_publish_kernel(const void* __restric
             ctl->step = t;
         }
     }
+    // the consumer's output is cleared here, after this CTA's words are out and while the flags travel:
+    // the scatter that follows in stream order then needs neither a memset node nor a clearing prologue
+    if (zero_ptr != nullptr) {
+        const size_t per = (zero_vec16 + gridDim.x - 1) / gridDim.x;
+        const size_t z0 = (size_t)blockIdx.x * per, z1 = min(z0 + per, zero_vec16);
+        for (size_t z = z0 + threadIdx.x; z < z1; z += blockDim.x) zero_ptr[z] = make_int4(0, 0, 0, 0);
+    }
 }
 
 // every block waits until all peers have published this rank's current step, then pulls its share
@@ -124,14 +100,7 @@ __global__ void __launch_bounds__(256) wait_copy_kernel(const uint32_t* __restri
                                                         ExchangeCtl* ctl) {
     const uint32_t t = ctl->step;
     if (blockIdx.x == 0 && threadIdx.x == 0) ctl->stamp[3] = gtimer();
-    if ((int)threadIdx.x < world) {
-        unsigned long long spins = 0;
-        while ((int32_t)(ld_acquire_sys(my_flags + threadIdx.x) - t) < 0) {
-            if (++spins > (1ull << 26)) { ctl->timeout = 1u; break; }   // bounded: never hang the GPU
-            __nanosleep(20);
-        }
-    }
-    __syncthreads();
+    if (!wait_flags(my_flags, world, t, ctl)) return;      // timed out (now or earlier): no stale words consumed
     if (blockIdx.x == 0 && threadIdx.x == 0) ctl->stamp[4] = gtimer();
     const int64_t n = words_per_rank * world;
     const int64_t half = (int64_t)(t & 1u) * n;
@@ -177,14 +146,7 @@ __global__ void __launch_bounds__(256) wait_copy_compact_kernel(const uint32_t* 
         const size_t z0 = (size_t)blockIdx.x * per, z1 = min(z0 + per, zero_vec16);
         for (size_t z = z0 + threadIdx.x; z < z1; z += blockDim.x) zero_ptr[z] = make_int4(0, 0, 0, 0);
     }
-    if ((int)threadIdx.x < world) {
-        unsigned long long spins = 0;
-        while ((int32_t)(ld_acquire_sys(my_flags + threadIdx.x) - t) < 0) {
-            if (++spins > (1ull << 26)) { ctl->timeout = 1u; break; }   // bounded: never hang the GPU
-            __nanosleep(20);
-        }
-    }
-    __syncthreads();
+    if (!wait_flags(my_flags, world, t, ctl)) return;      // n_active stays 0: the consumer scatters nothing
     if (blockIdx.x == 0 && threadIdx.x == 0) ctl->stamp[4] = gtimer();
     const int64_t n = words_per_rank * world;
     const int64_t half = (int64_t)(t & 1u) * n;
@@ -248,36 +210,48 @@ using namespace be;
 
 extern "C" size_t be_b200_exchange_ctl_bytes(void) { return sizeof(ExchangeCtl); }
 
-extern "C" int be_b200_pack_publish_reset(const void* spikes_local, int spk_kind, int64_t n_local,
+extern "C" int be_b200_pack_publish_clear(const void* spikes_local, int spk_kind, int64_t n_local,
                                           void* const* peer_bufs, void* const* peer_flags, int world, int rank,
-                                          int64_t words_per_rank, void* ctl, int32_t* reset_counter, void* stream);
-
-extern "C" int be_b200_pack_publish(const void* spikes_local, int spk_kind, int64_t n_local,
-                                    void* const* peer_bufs, void* const* peer_flags, int world, int rank,
-                                    int64_t words_per_rank, void* ctl, void* stream) {
-    return be_b200_pack_publish_reset(spikes_local, spk_kind, n_local, peer_bufs, peer_flags, world, rank,
-                                      words_per_rank, ctl, nullptr, stream);
+                                          int64_t words_per_rank, void* ctl, int32_t* reset_counter,
+                                          void* clear_ptr, size_t clear_bytes, void* stream) {
+    cudaStream_t s = (cudaStream_t)stream;
+    BE_REQUIRE(peer_bufs && peer_flags && ctl, "pack_publish: NULL pointer");
+    BE_REQUIRE(spikes_local || n_local == 0, "pack_publish: spikes is NULL");   // a rank may own an empty block
+    BE_REQUIRE(world >= 1 && world <= 32 && rank >= 0 && rank < world, "pack_publish: bad rank/world");
+    BE_REQUIRE(n_local >= 0 && n_local <= words_per_rank * 32, "pack_publish: n_local exceeds the slot");
+    int4* zp = nullptr;
+    size_t zv = 0;
+    if (clear_ptr != nullptr && clear_bytes > 0) {
+        if ((((uintptr_t)clear_ptr) & 15u) == 0 && clear_bytes % 16 == 0) { zp = (int4*)clear_ptr; zv = clear_bytes / 16; }
+        else BE_CUDA(cudaMemsetAsync(clear_ptr, 0, clear_bytes, s));
+    }
+    int64_t want = ceil_div(2 * words_per_rank, 256);
+    if (zp) want = std::max<int64_t>(want, ceil_div((int64_t)zv, 1024));
+    const int blocks = (int)std::max<int64_t>(1, std::min<int64_t>(want, kNumSM * 4));
+#define BE_PACK(K)                                                                                              \
+    pack_publish_kernel<K><<<blocks, 256, 0, s>>>(spikes_local, n_local, (uint32_t* const*)peer_bufs,            \
+                                                  (uint32_t* const*)peer_flags, world, rank, words_per_rank,     \
+                                                  (ExchangeCtl*)ctl, reset_counter, zp, zv)
+    if (spk_kind == BE_B200_SPK_BOOL) BE_PACK(BE_B200_SPK_BOOL);
+    else if (spk_kind == BE_B200_SPK_F32) BE_PACK(BE_B200_SPK_F32);
+    else { set_error("pack_publish: unsupported event kind %d", spk_kind); return BE_B200_EINVAL; }
+#undef BE_PACK
+    BE_LAUNCH_CHECK("pack_publish_kernel");
+    return BE_B200_OK;
 }
 
 extern "C" int be_b200_pack_publish_reset(const void* spikes_local, int spk_kind, int64_t n_local,
                                           void* const* peer_bufs, void* const* peer_flags, int world, int rank,
                                           int64_t words_per_rank, void* ctl, int32_t* reset_counter, void* stream) {
-    cudaStream_t s = (cudaStream_t)stream;
-    BE_REQUIRE(spikes_local && peer_bufs && peer_flags && ctl, "pack_publish: NULL pointer");
-    BE_REQUIRE(world >= 1 && world <= 32 && rank >= 0 && rank < world, "pack_publish: bad rank/world");
-    BE_REQUIRE(n_local >= 0 && n_local <= words_per_rank * 32, "pack_publish: n_local exceeds the slot");
-    const int blocks = (int)std::max<int64_t>(1, std::min<int64_t>(ceil_div(2 * words_per_rank, 256), kNumSM * 4));
-    if (spk_kind == BE_B200_SPK_BOOL)
-        pack_publish_kernel<BE_B200_SPK_BOOL><<<blocks, 256, 0, s>>>(spikes_local, n_local, (uint32_t* const*)peer_bufs,
-                                                                      (uint32_t* const*)peer_flags, world, rank,
-                                                                      words_per_rank, (ExchangeCtl*)ctl, reset_counter);
-    else if (spk_kind == BE_B200_SPK_F32)
-        pack_publish_kernel<BE_B200_SPK_F32><<<blocks, 256, 0, s>>>(spikes_local, n_local, (uint32_t* const*)peer_bufs,
-                                                                     (uint32_t* const*)peer_flags, world, rank,
-                                                                     words_per_rank, (ExchangeCtl*)ctl, reset_counter);
-    else { set_error("pack_publish: unsupported event kind %d", spk_kind); return BE_B200_EINVAL; }
-    BE_LAUNCH_CHECK("pack_publish_kernel");
-    return BE_B200_OK;
+    return be_b200_pack_publish_clear(spikes_local, spk_kind, n_local, peer_bufs, peer_flags, world, rank,
+                                      words_per_rank, ctl, reset_counter, nullptr, 0, stream);
+}
+
+extern "C" int be_b200_pack_publish(const void* spikes_local, int spk_kind, int64_t n_local,
+                                    void* const* peer_bufs, void* const* peer_flags, int world, int rank,
+                                    int64_t words_per_rank, void* ctl, void* stream) {
+    return be_b200_pack_publish_clear(spikes_local, spk_kind, n_local, peer_bufs, peer_flags, world, rank,
+                                      words_per_rank, ctl, nullptr, nullptr, 0, stream);
 }
 
 extern "C" int be_b200_wait_exchange(const void* my_flags, void* const* peer_bufs, int world,

@@ -43,7 +43,10 @@ static be_b200_projection* proj_new(int kind, int64_t n_pre, int64_t n_post) {
     bool ok = cudaStreamCreateWithFlags(&p->stream, cudaStreamNonBlocking) == cudaSuccess;
     p->ws_bytes = be_b200_workspace_bytes(n_pre, 1);
     ok = ok && cudaMalloc(&p->d_ws, p->ws_bytes) == cudaSuccess;
-    ok = ok && cudaMemset(p->d_ws, 0, p->ws_bytes) == cudaSuccess;
+    // zeroed ON the compute stream and waited for: the non-blocking streams below never synchronise with
+    // the legacy default stream, so a plain cudaMemset would not be ordered before the first compaction
+    ok = ok && cudaMemsetAsync(p->d_ws, 0, p->ws_bytes, p->stream) == cudaSuccess;
+    ok = ok && cudaStreamSynchronize(p->stream) == cudaSuccess;
     ok = ok && cudaMalloc((void**)&p->d_events, (size_t)std::max<int64_t>(n_pre, 16)) == cudaSuccess;
     ok = ok && cudaMalloc((void**)&p->d_out, (size_t)std::max<int64_t>(n_post, 4) * sizeof(float)) == cudaSuccess;
     ok = ok && cudaStreamCreateWithFlags(&p->s_in, cudaStreamNonBlocking) == cudaSuccess;
@@ -59,11 +62,11 @@ static be_b200_projection* proj_new(int kind, int64_t n_pre, int64_t n_post) {
     return p;
 }
 
+// allocates at least 16 bytes but copies only `bytes`; the copy is complete (not merely staged) on return
 static bool upload(void** dst, const void* src, size_t bytes) {
-    if (bytes == 0) bytes = 16;
-    if (cudaMalloc(dst, bytes) != cudaSuccess) return false;
-    if (src && cudaMemcpy(*dst, src, bytes, cudaMemcpyHostToDevice) != cudaSuccess) return false;
-    return true;
+    if (cudaMalloc(dst, bytes ? bytes : 16) != cudaSuccess) return false;
+    if (src && bytes && cudaMemcpy(*dst, src, bytes, cudaMemcpyHostToDevice) != cudaSuccess) return false;
+    return cudaDeviceSynchronize() == cudaSuccess;     // pageable H2D may return before its DMA lands
 }
 
 extern "C" be_b200_projection* be_b200_projection_create_csr(const float* weights, int homo,

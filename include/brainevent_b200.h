@@ -316,6 +316,68 @@ int be_b200_wait_exchange_compact(const void* my_flags, void* const* peer_bufs, 
                                   int64_t words_per_rank, int64_t n_bits, uint32_t* gathered_out,
                                   int32_t* ids_and_count, void* clear_ptr, size_t clear_bytes,
                                   void* ctl, void* stream);
+/* pack + publish that also resets the compaction counter (nullable) and clears clear_ptr[0..clear_bytes)
+ * (nullable) after its own words are out -- the first kernel of the fused two-kernel step of
+ * be_b200_sharded_step. */
+int be_b200_pack_publish_clear(const void* spikes_local, int spk_kind, int64_t n_local,
+                               void* const* peer_bufs, void* const* peer_flags, int world, int rank,
+                               int64_t words_per_rank, void* ctl, int32_t* reset_counter,
+                               void* clear_ptr, size_t clear_bytes, void* stream);
+/* Flag waits are bounded by wall time: ctl word [3] (uint32 milliseconds, 0 = 20 s default).  A wait that
+ * gives up latches ctl word [2]; from then on every wait kernel of that exchange skips its pull (scatter
+ * consumers see n_active = 0) and the host entry points (be_b200_sharded_wait, dist.HostStepPipeline)
+ * fail: after a timeout a rank may have run ahead of a peer's double buffer, so nothing later is trusted. */
+
+/* ---- post-sharded projection: one rank's share as an object (net-new) ------------------------
+ * Rank g of `world` owns the post block [g*per, (g+1)*per), per = 32 * words_per_rank, and holds only the
+ * synapses that end there: rows = ALL n_neurons pre neurons, column ids LOCAL to the block.  The spikes of a
+ * timestep arrive as each rank's own block (n_local values) and are exchanged as bit-packed words over
+ * peer memory.  peer_bufs_host[p] = rank p's symmetric buffer mapped into this process
+ * (be_b200_sharded_symm_bytes() bytes, zeroed before the rendezvous; world == 1: any device buffer).
+ *   stored connectivity (set_fcn / set_csr): two kernels per timestep, the all-gather fused into the
+ *     scatter (own rows first, each peer's words as its flag arrives) -- csrc/sharded.cu;
+ *   set_jitc: the GLOBAL shape (n_neurons x n_post_global) keys the RNG; corder=1 (gather order, rows =
+ *     post) takes a row window, corder=0 (scatter order) a column window;
+ *   set_dense: W [n_neurons, n_out] row-major = this rank's post columns of the dense matrix.
+ * All connectivity pointers are DEVICE pointers that stay owned by the caller. */
+#define BE_B200_CONN_CSR 0
+#define BE_B200_CONN_FCN 1
+#define BE_B200_CONN_JITC 2
+#define BE_B200_CONN_DENSE 3
+typedef struct be_b200_sharded be_b200_sharded;
+size_t be_b200_sharded_symm_bytes(int world, int64_t words_per_rank);
+/* ctl: NULL, or a zeroed device block of be_b200_exchange_ctl_bytes() shared with direct
+ * be_b200_pack_publish / be_b200_wait_exchange calls on the same buffers (one step counter) */
+be_b200_sharded* be_b200_sharded_create(int world, int rank, int64_t n_neurons, int64_t n_out,
+                                        int64_t words_per_rank, void* const* peer_bufs_host, void* ctl);
+int be_b200_sharded_set_fcn(be_b200_sharded* h, const void* weights, int w_dtype, int homo,
+                            const int32_t* indices, int64_t n_rows, int64_t n_conn);
+int be_b200_sharded_set_csr(be_b200_sharded* h, const void* weights, int w_dtype, int homo,
+                            const int32_t* indices, const void* indptr, int indptr_is64,
+                            int64_t n_rows, int64_t nse);
+int be_b200_sharded_set_jitc(be_b200_sharded* h, int jit_kind, const void* p0, const void* p1, int w_dtype,
+                             const int32_t* clen, const int32_t* seed, int64_t n_post_global,
+                             int64_t chunk_size, int corder);
+int be_b200_sharded_set_dense(be_b200_sharded* h, const void* W, int w_dtype);
+/* options: "fused" (stored connectivity: 1 = two-kernel fused step, 0 = pack / wait+compact / scatter),
+ * "lanes_per_row" (0 auto, 8, 16, 32), "spin_ms" (flag-wait bound) */
+int be_b200_sharded_set_option(be_b200_sharded* h, const char* name, int64_t value);
+/* One timestep, device resident: spikes_local [n_local] (BOOL or F32) -> out [n_out] in the weight dtype.
+ * Enqueues on `stream`, never synchronises; collective (every rank calls it equally often). */
+int be_b200_sharded_step(be_b200_sharded* h, const void* spikes_local, int spk_kind, void* out, void* stream);
+/* The two phases of a step, for callers that publish early and consume later: publish = bit-pack + flag the
+ * peers (+ clear `out`); consume = pull the peers' words and propagate them into `out`.  step = both. */
+int be_b200_sharded_publish(be_b200_sharded* h, const void* spikes_local, int spk_kind, void* out, void* stream);
+int be_b200_sharded_consume(be_b200_sharded* h, void* out, void* stream);
+int be_b200_sharded_timed_out(be_b200_sharded* h);
+/* Host-buffer pipeline (float32): `slots` timesteps in flight, copy-in / graph of the step / copy-out on three
+ * streams.  Host buffers must be pinned and stay untouched until wait() or the slots-th next submit. */
+int be_b200_sharded_host_init(be_b200_sharded* h, int slots, int use_graph);
+int be_b200_sharded_submit_host(be_b200_sharded* h, const uint8_t* spikes_host, float* out_host);
+int be_b200_sharded_wait(be_b200_sharded* h);
+int be_b200_sharded_run_host(be_b200_sharded* h, int64_t n_steps, const uint8_t* const* spikes_host, int n_in,
+                             float* const* out_host, int n_out_bufs);
+void be_b200_sharded_destroy(be_b200_sharded* h);
 
 /* ---- host-buffer session (end-to-end entry: host spikes in, host result out) -----------------
  * A projection keeps its connectivity resident in HBM (uploaded once at creation, like the

@@ -1,7 +1,9 @@
-"""Multi-GPU correctness check (run under torchrun): the fused pack + peer-memory all-gather must
-deliver exactly the words NCCL's all-gather delivers, and the post-sharded product must equal the
-oracle's unsharded product on every rank's block.  Prints one OK line per rank."""
-import os, sys
+"""Multi-GPU correctness check (run under torchrun, N >= 2): the fused pack + peer-memory all-gather must
+deliver exactly the words NCCL's all-gather delivers, and every post-sharded product (CSR ragged shards
+behind the exchange fused into the scatter, the unfused three-kernel chain, FixedNumPerPre, dense, JITC in
+both orders, the C host pipeline) must equal the oracle's UNSHARDED product on every rank's block.
+Prints one `parity OK` line per rank; bench.py's own parity block covers the full-size networks."""
+import os, sys, time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np
 import torch
@@ -27,7 +29,9 @@ xn = bd.SpikeExchange(N, device=dev)
 xp = bd.P2PSpikeExchange(N, device=dev)
 assert (lo, hi) == xp.local == xn.local
 proj_n = bd.PostShardedProjection("csr", N, N, xn, data=t(dw), indices=t(ix), indptr=t(ip))
-proj_p = bd.PostShardedProjection("csr", N, N, xp, data=t(dw), indices=t(ix), indptr=t(ip))
+proj_p = bd.PostShardedProjection("csr", N, N, xp, data=t(dw), indices=t(ix), indptr=t(ip))     # fused (default)
+proj_u = bd.PostShardedProjection("csr", N, N, xp, data=t(dw), indices=t(ix), indptr=t(ip))
+proj_u.set_option("fused", 0)
 for step in range(7):          # odd count on purpose: parity lives on the device
     spikes = np.random.default_rng(100 + step).random(N) < 0.03
     mine = t(spikes[lo:hi])
@@ -35,12 +39,18 @@ for step in range(7):          # odd count on purpose: parity lives on the devic
     words_p = xp.exchange_spikes(mine).clone()
     assert torch.equal(words_n, words_p), f"rank {rank} step {step}: gathered words differ"
     np.testing.assert_array_equal(words_p.cpu().numpy().view(np.uint32), O.bitpack(spikes, 0))
-    out = proj_p.step(mine).cpu().numpy()
     ref = O.binary_fcnmv(w, idx, spikes, shape=(N, N), transpose=True)[lo:hi]
-    np.testing.assert_allclose(out, ref, rtol=1e-5, atol=2e-5)
-assert not xp.timed_out()
-# FixedNumPerPre shard behind the FUSED exchange (wait + pull + compaction + output clear in one kernel,
-# consumed as SPK_COMPACT_CLEARED): every pre neuron has c_loc targets inside this rank's block
+    np.testing.assert_allclose(proj_p.step(mine).cpu().numpy(), ref, rtol=1e-5, atol=2e-5)
+    np.testing.assert_allclose(proj_u.step(mine).cpu().numpy(), ref, rtol=1e-5, atol=2e-5)
+    scratch = torch.ones(hi - lo, device=dev)
+    _, ids_t = xp.exchange_compact(mine, scratch)     # the wait kernel's id list of the gathered vector + output clear
+    assert float(scratch.abs().max().item()) == 0.0
+    ids = ids_t.cpu().numpy()
+    assert ids[N] == spikes.sum(), f"rank {rank} step {step}: n_active {ids[N]} != {spikes.sum()}"
+    np.testing.assert_array_equal(np.sort(ids[: ids[N]]), np.nonzero(spikes)[0])
+    np.testing.assert_allclose(proj_n.step(mine).cpu().numpy(), ref, rtol=1e-5, atol=2e-5)
+xp.check()
+# FixedNumPerPre shard: every pre neuron has c_loc targets inside this rank's block
 n_loc, c_loc = hi - lo, 6
 rl = np.random.default_rng(50 + rank)
 idx_f = rl.integers(0, n_loc, (N, c_loc)).astype(np.int32)
@@ -49,13 +59,12 @@ proj_f = bd.PostShardedProjection("fcn", N, N, xp, weights=t(w_f), indices=t(idx
 for step, rate in enumerate([0.03, 0.0, 0.5, 0.01, 0.2]):
     spikes = np.random.default_rng(200 + step).random(N) < rate
     out = proj_f.step(t(spikes[lo:hi]))
-    ids = xp.ids.cpu().numpy()
-    assert ids[N] == spikes.sum(), f"rank {rank} step {step}: n_active {ids[N]} != {spikes.sum()}"
-    np.testing.assert_array_equal(np.sort(ids[: ids[N]]), np.nonzero(spikes)[0])
     ref = O.binary_fcnmv(w_f, idx_f, spikes, shape=(N, n_loc), transpose=True)
     np.testing.assert_allclose(out.cpu().numpy(), ref, rtol=1e-5, atol=2e-5)
-assert not xp.timed_out()
-pipe_f = bd.HostStepPipeline(proj_f, n_loc, slots=4)            # the fused step inside one CUDA graph per slot
+xp.check()
+# C host pipeline (be_b200_sharded_submit_host / _run_host): the fused step inside one CUDA graph per slot
+pipe_f = bd.HostStepPipeline(proj_f, n_loc, slots=4)
+assert pipe_f.native
 hf_in = [torch.empty(n_loc, dtype=torch.uint8).pin_memory() for _ in range(7)]
 hf_out = [torch.empty(n_loc, dtype=torch.float32).pin_memory() for _ in range(7)]
 refs_f = []
@@ -68,10 +77,14 @@ for q in range(7):
 pipe_f.wait()
 for q in range(7):
     np.testing.assert_allclose(hf_out[q].numpy(), refs_f[q], rtol=1e-5, atol=2e-5)
+for o in hf_out:
+    o.zero_()
+pipe_f.run(7, hf_in, hf_out)
+for q in range(7):
+    np.testing.assert_allclose(hf_out[q].numpy(), refs_f[q], rtol=1e-5, atol=2e-5)
 pipe_f.close()
 del pipe_f
-assert not xp.timed_out()
-# host-buffer pipeline (4 timesteps in flight, one CUDA graph per slot) == the plain step
+# host-buffer pipeline over the NCCL exchange (Python-driven, one CUDA graph per slot) == the plain step
 pipe = bd.HostStepPipeline(proj_n, hi - lo, slots=4)
 h_in = [torch.empty(hi - lo, dtype=torch.uint8).pin_memory() for _ in range(9)]
 h_out = [torch.empty(hi - lo, dtype=torch.float32).pin_memory() for _ in range(9)]
@@ -87,6 +100,14 @@ for q in range(9):
     np.testing.assert_allclose(h_out[q].numpy(), refs[q], rtol=1e-5, atol=2e-5)
 pipe.close()
 del pipe
+# dense event matvec, column (post) split of W
+Wd = np.random.default_rng(9).standard_normal((N, N)).astype(np.float32) if N <= 20_000 else None
+if Wd is not None:
+    pd = bd.PostShardedProjection("dense", N, N, xp, W=t(np.ascontiguousarray(Wd[:, lo:hi])))
+    for step, rate in enumerate([0.05, 0.0, 0.4]):
+        spikes = np.random.default_rng(600 + step).random(N) < rate
+        out = pd.step(t(spikes[lo:hi])).cpu().numpy()
+        np.testing.assert_allclose(out, O.binary_densemv(Wd, spikes, transpose=True)[lo:hi], rtol=1e-4, atol=2e-3)
 # JITC post-sharding (column window for scatter, row window for gather) against the oracle
 for corder in (False, True):
     pj = bd.PostShardedProjection("jitc", N, N, xp, family="normal", params=(1.0, 0.1), prob=0.01, seed=5, corder=corder)
@@ -94,7 +115,27 @@ for corder in (False, True):
     out = pj.step(t(spikes[lo:hi])).cpu().numpy()
     ref = O.binary_jitnmv(1.0, 0.1, 0.01, spikes, 5, shape=(N, N), transpose=True, corder=corder)[lo:hi]
     np.testing.assert_allclose(out, ref, rtol=1e-5, atol=2e-5)
+xp.check()
 torch.cuda.synchronize()
 dist.barrier()
-print(f"rank {rank}/{world}: exchange + post-sharded fcn/jitc parity OK", flush=True)
+# a rank that stalls past the spin limit: everyone must notice.  Separate exchange, 50 ms limit,
+# rank `world-1` sleeps 0.5 s before its step.
+xt = bd.P2PSpikeExchange(N, device=dev)
+xt.set_spin_limit_ms(50)
+pt = bd.PostShardedProjection("csr", N, N, xt, data=t(dw), indices=t(ix), indptr=t(ip))
+spikes = np.random.default_rng(1).random(N) < 0.03
+pt.step(t(spikes[lo:hi]))
+torch.cuda.synchronize()
+dist.barrier()
+if rank == world - 1:
+    time.sleep(0.5)
+pt.step(t(spikes[lo:hi]))
+torch.cuda.synchronize()
+try:
+    xt.check()
+    raise SystemExit(f"rank {rank}: the stalled exchange was not reported")
+except bd.ExchangeTimeout:
+    pass
+dist.barrier()
+print(f"rank {rank}/{world}: exchange + post-sharded csr(fused/unfused)/fcn/dense/jitc + host pipelines + timeout: parity OK", flush=True)
 dist.destroy_process_group()
