@@ -44,6 +44,16 @@ int sm_count();
 #define kNumSM (::be::sm_count())
 constexpr int kWarp = 32;
 
+// NVTX range around every C-ABI / XLA-FFI entry: visible in Nsight Systems / Compute timelines,
+// a null-pointer check when no tool is attached (header-only NVTX3, resolved lazily through dlopen).
+struct NvtxRange {
+    explicit NvtxRange(const char* name);
+    ~NvtxRange();
+};
+#define BE_NVTX_CAT2(a, b) a##b
+#define BE_NVTX_CAT(a, b) BE_NVTX_CAT2(a, b)
+#define BE_NVTX_RANGE(name) ::be::NvtxRange BE_NVTX_CAT(nvtx_range_, __LINE__)(name)
+
 __host__ __device__ static inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
 static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 

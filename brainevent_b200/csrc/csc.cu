@@ -95,7 +95,7 @@ extern "C" size_t be_b200_csc_workspace_bytes(int64_t m, int64_t n_post, int64_t
 extern "C" int be_b200_csr_to_csc(const void* indptr, int is64, const int32_t* indices, int64_t m,
                                   int64_t n_post, int64_t nse, void* csc_indptr,
                                   int32_t* csc_indices, void* perm, void* workspace,
-                                  size_t workspace_bytes, void* stream) {
+                                  size_t workspace_bytes, void* stream) { BE_NVTX_RANGE("be_b200_csr_to_csc");
     cudaStream_t s = (cudaStream_t)stream;
     BE_REQUIRE(m >= 0 && n_post >= 0 && nse >= 0, "csr_to_csc: negative size");
     BE_REQUIRE(indptr && csc_indptr && workspace, "csr_to_csc: NULL pointer");

@@ -361,7 +361,7 @@ extern "C" int be_b200_binary_csrmv(const void* weights, int w_dtype, int homo,
                                     const void* perm, int perm_is64, const void* spikes,
                                     const void* aux, int spk_kind, int64_t m, int64_t k,
                                     int64_t nse, int transpose, void* out, void* workspace,
-                                    size_t workspace_bytes, void* stream) {
+                                    size_t workspace_bytes, void* stream) { BE_NVTX_RANGE("be_b200_binary_csrmv");
     return csr_entry(weights, w_dtype, homo, indices, indptr, indptr_is64, perm, perm_is64, spikes,
                      aux, spk_kind, m, k, nse, 0, transpose, out, workspace, workspace_bytes, stream);
 }
@@ -374,7 +374,7 @@ extern "C" int be_b200_binary_csrmv_auto(const void* weights, int w_dtype, int h
                                          const void* perm, const void* spikes, const void* aux,
                                          int spk_kind, int64_t m, int64_t k, int64_t nse,
                                          float rate_threshold, void* out, void* workspace,
-                                         size_t workspace_bytes, void* stream) {
+                                         size_t workspace_bytes, void* stream) { BE_NVTX_RANGE("be_b200_binary_csrmv_auto");
     cudaStream_t s = (cudaStream_t)stream;
     BE_REQUIRE(m >= 0 && k >= 0 && m < (1ll << 31) && k < (1ll << 31), "csrmv_auto: shape out of range");
     BE_REQUIRE(weights && indptr && csc_indptr && out, "csrmv_auto: NULL pointer");
@@ -410,7 +410,7 @@ extern "C" int be_b200_binary_csrmm(const void* weights, int w_dtype, int homo,
                                     const void* perm, int perm_is64, const void* spikes,
                                     const void* aux, int spk_kind, int64_t m, int64_t k,
                                     int64_t nse, int64_t n, int transpose, int out_batch_major,
-                                    void* out, void* workspace, size_t workspace_bytes, void* stream) {
+                                    void* out, void* workspace, size_t workspace_bytes, void* stream) { BE_NVTX_RANGE("be_b200_binary_csrmm");
     BE_REQUIRE(n >= 1, "csrmm: batch must be >= 1");
     return csr_entry(weights, w_dtype, homo, indices, indptr, indptr_is64, perm, perm_is64, spikes,
                      aux, spk_kind, m, k, nse, n, transpose, out, workspace, workspace_bytes, stream, out_batch_major);
@@ -441,7 +441,7 @@ extern "C" int be_b200_binary_fcnmv(const void* weights, int w_dtype, int homo,
                                     const int32_t* indices, int64_t n_rows, int64_t n_conn,
                                     const void* spikes, const void* aux, int spk_kind,
                                     int64_t n_src, int64_t n_out, int transpose, void* out,
-                                    void* workspace, size_t workspace_bytes, void* stream) {
+                                    void* workspace, size_t workspace_bytes, void* stream) { BE_NVTX_RANGE("be_b200_binary_fcnmv");
     return fcn_entry(weights, w_dtype, homo, indices, n_rows, n_conn, spikes, aux, spk_kind, n_src,
                      n_out, 0, transpose, out, workspace, workspace_bytes, stream);
 }
@@ -451,7 +451,7 @@ extern "C" int be_b200_binary_fcnmm(const void* weights, int w_dtype, int homo,
                                     const void* spikes, const void* aux, int spk_kind,
                                     int64_t n_src, int64_t n_out, int64_t n, int transpose,
                                     int out_batch_major, void* out, void* workspace,
-                                    size_t workspace_bytes, void* stream) {
+                                    size_t workspace_bytes, void* stream) { BE_NVTX_RANGE("be_b200_binary_fcnmm");
     BE_REQUIRE(n >= 1, "fcnmm: batch must be >= 1");
     return fcn_entry(weights, w_dtype, homo, indices, n_rows, n_conn, spikes, aux, spk_kind, n_src,
                      n_out, n, transpose, out, workspace, workspace_bytes, stream, out_batch_major);

@@ -236,7 +236,7 @@ using namespace be;
 extern "C" int be_b200_binary_densemv(const void* W, int w_dtype, int64_t rows, int64_t cols,
                                       const void* spikes, const void* aux, int spk_kind,
                                       int transpose, void* out, void* workspace,
-                                      size_t workspace_bytes, void* stream) {
+                                      size_t workspace_bytes, void* stream) { BE_NVTX_RANGE("be_b200_binary_densemv");
     cudaStream_t s = (cudaStream_t)stream;
     BE_REQUIRE(rows >= 0 && cols >= 0 && rows < (1ll << 31) && cols < (1ll << 31), "densemv: shape out of range");
     BE_REQUIRE((W || rows * cols == 0) && out, "densemv: NULL pointer");
@@ -251,7 +251,7 @@ extern "C" int be_b200_binary_densemv(const void* W, int w_dtype, int64_t rows, 
 extern "C" int be_b200_binary_densemm(const void* W, int w_dtype, int64_t rows, int64_t cols,
                                       const void* spikes, const void* aux, int spk_kind, int64_t n,
                                       int transpose, void* out, void* workspace,
-                                      size_t workspace_bytes, void* stream) {
+                                      size_t workspace_bytes, void* stream) { BE_NVTX_RANGE("be_b200_binary_densemm");
     cudaStream_t s = (cudaStream_t)stream;
     BE_REQUIRE(rows >= 0 && cols >= 0 && rows < (1ll << 31) && cols < (1ll << 31) && n >= 1, "densemm: shape out of range");
     BE_REQUIRE((W || rows * cols == 0) && out, "densemm: NULL pointer");

@@ -112,7 +112,7 @@ using namespace be;
 
 extern "C" int be_b200_binary_2d_pair_stream_encode(const void* spikes, int spk_kind, int64_t n_src, int64_t n_batch,
                                                     int32_t* pair_stream, int32_t* n_pairs, void* workspace,
-                                                    size_t workspace_bytes, void* stream) {
+                                                    size_t workspace_bytes, void* stream) { BE_NVTX_RANGE("be_b200_binary_2d_pair_stream_encode");
     cudaStream_t s = (cudaStream_t)stream;
     if (int rc = check_2d(spikes, spk_kind, n_src, n_batch, "pair_stream_encode")) return rc;
     BE_REQUIRE(n_pairs && (pair_stream || n_src * n_batch == 0), "pair_stream_encode: NULL output");
@@ -128,7 +128,7 @@ extern "C" int be_b200_binary_2d_pair_stream_encode(const void* spikes, int spk_
 
 extern "C" int be_b200_binary_2d_csr_encode(const void* spikes, int spk_kind, int64_t n_src, int64_t n_batch,
                                             int32_t* indices, int32_t* indptr, void* workspace,
-                                            size_t workspace_bytes, void* stream) {
+                                            size_t workspace_bytes, void* stream) { BE_NVTX_RANGE("be_b200_binary_2d_csr_encode");
     cudaStream_t s = (cudaStream_t)stream;
     if (int rc = check_2d(spikes, spk_kind, n_src, n_batch, "csr_encode")) return rc;
     BE_REQUIRE(indptr && (indices || n_src * n_batch == 0), "csr_encode: NULL output");
@@ -144,7 +144,7 @@ extern "C" int be_b200_binary_2d_csr_encode(const void* spikes, int spk_kind, in
 
 extern "C" int be_b200_binary_2d_csc_encode(const void* spikes, int spk_kind, int64_t n_src, int64_t n_batch,
                                             int32_t* indices, int32_t* indptr, void* scratch, void* workspace,
-                                            size_t workspace_bytes, void* stream) {
+                                            size_t workspace_bytes, void* stream) { BE_NVTX_RANGE("be_b200_binary_2d_csc_encode");
     cudaStream_t s = (cudaStream_t)stream;
     if (int rc = check_2d(spikes, spk_kind, n_src, n_batch, "csc_encode")) return rc;
     BE_REQUIRE(indptr && (indices || n_src * n_batch == 0), "csc_encode: NULL output");
@@ -168,7 +168,7 @@ extern "C" int be_b200_binary_2d_csc_encode(const void* spikes, int spk_kind, in
 
 extern "C" int be_b200_binary_2d_row_sparse_encode(const void* spikes, int spk_kind, int64_t n_src, int64_t n_batch,
                                                    int64_t row_size, int32_t* spike_indices, int32_t* max_row_nnz,
-                                                   void* stream) {
+                                                   void* stream) { BE_NVTX_RANGE("be_b200_binary_2d_row_sparse_encode");
     cudaStream_t s = (cudaStream_t)stream;
     if (int rc = check_2d(spikes, spk_kind, n_src, n_batch, "row_sparse_encode")) return rc;
     BE_REQUIRE(row_size > 0 && row_size <= std::max<int64_t>(n_batch, 1) && row_size < (1ll << 31), "row_sparse_encode: row_size must be in [1, n_batch]");

@@ -7,6 +7,8 @@
 // ref: _event/compact.py:305-358) while reading the spikes exactly once with 128-bit loads.
 #include "common.cuh"
 
+#include <nvtx3/nvToolsExt.h>
+
 #include <algorithm>
 #include <cstring>
 
@@ -26,6 +28,9 @@ int cuda_fail(cudaError_t e, const char* what) {
     set_error("CUDA error %d (%s) at %s", (int)e, cudaGetErrorString(e), what);
     return BE_B200_EINTERNAL;
 }
+
+NvtxRange::NvtxRange(const char* name) { nvtxRangePushA(name); }
+NvtxRange::~NvtxRange() { nvtxRangePop(); }
 
 int sm_count() {
     static int cached[64] = {0};      // benign race: every writer stores the same value
@@ -600,7 +605,7 @@ extern "C" size_t be_b200_workspace_bytes(int64_t n_src, int64_t n_batch) {
 }
 
 extern "C" int be_b200_bitpack_1d(const void* spikes, int spk_kind, int64_t n, int nonzero_pred,
-                                  uint32_t* packed, void* stream) {
+                                  uint32_t* packed, void* stream) { BE_NVTX_RANGE("be_b200_bitpack_1d");
     cudaStream_t s = (cudaStream_t)stream;
     BE_REQUIRE(n >= 0, "n must be >= 0");
     if (n == 0) return BE_B200_OK;
@@ -613,7 +618,7 @@ extern "C" int be_b200_bitpack_1d(const void* spikes, int spk_kind, int64_t n, i
 
 extern "C" int be_b200_compact_1d(const void* spikes, int spk_kind, int64_t n, int nonzero_pred,
                                   int32_t* active_ids, int32_t* n_active, uint32_t* packed,
-                                  void* workspace, size_t workspace_bytes, void* stream) {
+                                  void* workspace, size_t workspace_bytes, void* stream) { BE_NVTX_RANGE("be_b200_compact_1d");
     cudaStream_t s = (cudaStream_t)stream;
     BE_REQUIRE(n >= 0 && n < (1ll << 31), "n out of range");
     BE_REQUIRE((active_ids || n == 0) && n_active, "NULL output");
@@ -627,7 +632,7 @@ extern "C" int be_b200_compact_1d(const void* spikes, int spk_kind, int64_t n, i
 extern "C" int be_b200_compact_2d(const void* spikes, int spk_kind, int64_t n, int64_t batch,
                                   int nonzero_pred, uint32_t* packed, int32_t* active_ids,
                                   int32_t* n_active, void* workspace, size_t workspace_bytes,
-                                  void* stream) {
+                                  void* stream) { BE_NVTX_RANGE("be_b200_compact_2d");
     cudaStream_t s = (cudaStream_t)stream;
     BE_REQUIRE(n >= 0 && n < (1ll << 31) && batch >= 1, "shape out of range");
     BE_REQUIRE((active_ids || n == 0) && n_active, "NULL output");

@@ -213,7 +213,7 @@ extern "C" size_t be_b200_exchange_ctl_bytes(void) { return sizeof(ExchangeCtl);
 extern "C" int be_b200_pack_publish_clear(const void* spikes_local, int spk_kind, int64_t n_local,
                                           void* const* peer_bufs, void* const* peer_flags, int world, int rank,
                                           int64_t words_per_rank, void* ctl, int32_t* reset_counter,
-                                          void* clear_ptr, size_t clear_bytes, void* stream) {
+                                          void* clear_ptr, size_t clear_bytes, void* stream) { BE_NVTX_RANGE("be_b200_pack_publish_clear");
     cudaStream_t s = (cudaStream_t)stream;
     BE_REQUIRE(peer_bufs && peer_flags && ctl, "pack_publish: NULL pointer");
     BE_REQUIRE(spikes_local || n_local == 0, "pack_publish: spikes is NULL");   // a rank may own an empty block
@@ -242,20 +242,20 @@ extern "C" int be_b200_pack_publish_clear(const void* spikes_local, int spk_kind
 
 extern "C" int be_b200_pack_publish_reset(const void* spikes_local, int spk_kind, int64_t n_local,
                                           void* const* peer_bufs, void* const* peer_flags, int world, int rank,
-                                          int64_t words_per_rank, void* ctl, int32_t* reset_counter, void* stream) {
+                                          int64_t words_per_rank, void* ctl, int32_t* reset_counter, void* stream) { BE_NVTX_RANGE("be_b200_pack_publish_reset");
     return be_b200_pack_publish_clear(spikes_local, spk_kind, n_local, peer_bufs, peer_flags, world, rank,
                                       words_per_rank, ctl, reset_counter, nullptr, 0, stream);
 }
 
 extern "C" int be_b200_pack_publish(const void* spikes_local, int spk_kind, int64_t n_local,
                                     void* const* peer_bufs, void* const* peer_flags, int world, int rank,
-                                    int64_t words_per_rank, void* ctl, void* stream) {
+                                    int64_t words_per_rank, void* ctl, void* stream) { BE_NVTX_RANGE("be_b200_pack_publish");
     return be_b200_pack_publish_clear(spikes_local, spk_kind, n_local, peer_bufs, peer_flags, world, rank,
                                       words_per_rank, ctl, nullptr, nullptr, 0, stream);
 }
 
 extern "C" int be_b200_wait_exchange(const void* my_flags, void* const* peer_bufs, int world,
-                                     int64_t words_per_rank, uint32_t* gathered_out, void* ctl, void* stream) {
+                                     int64_t words_per_rank, uint32_t* gathered_out, void* ctl, void* stream) { BE_NVTX_RANGE("be_b200_wait_exchange");
     BE_REQUIRE(my_flags && peer_bufs && gathered_out && ctl && world >= 1 && world <= 32, "wait_exchange: bad arguments");
     const int blocks = (int)std::max<int64_t>(1, std::min<int64_t>(ceil_div(words_per_rank * world, 1024), kNumSM));
     wait_copy_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>((const uint32_t*)my_flags, (uint32_t* const*)peer_bufs, world,
@@ -267,7 +267,7 @@ extern "C" int be_b200_wait_exchange(const void* my_flags, void* const* peer_buf
 extern "C" int be_b200_wait_exchange_compact(const void* my_flags, void* const* peer_bufs, int world,
                                              int64_t words_per_rank, int64_t n_bits, uint32_t* gathered_out,
                                              int32_t* ids_and_count, void* clear_ptr, size_t clear_bytes,
-                                             void* ctl, void* stream) {
+                                             void* ctl, void* stream) { BE_NVTX_RANGE("be_b200_wait_exchange_compact");
     BE_REQUIRE(my_flags && peer_bufs && gathered_out && ids_and_count && ctl && world >= 1 && world <= 32,
                "wait_exchange_compact: bad arguments");
     BE_REQUIRE(n_bits >= 0 && n_bits <= words_per_rank * world * 32 && n_bits < ((int64_t)1 << 31),

@@ -228,26 +228,26 @@ using namespace be;
 
 extern "C" int be_b200_csrmv(const void* weights, int w_dtype, int homo, const int32_t* indices,
                              const void* indptr, int indptr_is64, const void* x, int64_t m, int64_t k,
-                             int64_t nse, int transpose, void* out, void* stream) {
+                             int64_t nse, int transpose, void* out, void* stream) { BE_NVTX_RANGE("be_b200_csrmv");
     return csr_val_entry(weights, w_dtype, homo, indices, indptr, indptr_is64, x, m, k, nse, 0, transpose, out, stream);
 }
 
 extern "C" int be_b200_csrmm(const void* weights, int w_dtype, int homo, const int32_t* indices,
                              const void* indptr, int indptr_is64, const void* X, int64_t m, int64_t k,
-                             int64_t nse, int64_t n, int transpose, void* out, void* stream) {
+                             int64_t nse, int64_t n, int transpose, void* out, void* stream) { BE_NVTX_RANGE("be_b200_csrmm");
     BE_REQUIRE(n >= 1, "csrmm: n must be >= 1");
     return csr_val_entry(weights, w_dtype, homo, indices, indptr, indptr_is64, X, m, k, nse, n, transpose, out, stream);
 }
 
 extern "C" int be_b200_fcnmv(const void* weights, int w_dtype, int homo, const int32_t* indices,
                              int64_t n_rows, int64_t n_conn, const void* x, int64_t n_other,
-                             int transpose, void* out, void* stream) {
+                             int transpose, void* out, void* stream) { BE_NVTX_RANGE("be_b200_fcnmv");
     return fcn_val_entry(weights, w_dtype, homo, indices, n_rows, n_conn, x, n_other, 0, transpose, out, stream);
 }
 
 extern "C" int be_b200_fcnmm(const void* weights, int w_dtype, int homo, const int32_t* indices,
                              int64_t n_rows, int64_t n_conn, const void* X, int64_t n_other, int64_t n,
-                             int transpose, void* out, void* stream) {
+                             int transpose, void* out, void* stream) { BE_NVTX_RANGE("be_b200_fcnmm");
     BE_REQUIRE(n >= 1, "fcnmm: n must be >= 1");
     return fcn_val_entry(weights, w_dtype, homo, indices, n_rows, n_conn, X, n_other, n, transpose, out, stream);
 }

@@ -599,7 +599,7 @@ extern "C" int be_b200_binary_jitmv(int kind, const void* p0, const void* p1, in
                                     const void* aux, int spk_kind, int64_t vec_len, int64_t out_len,
                                     int64_t chunk_size, int corder, int64_t row_offset,
                                     int64_t row_count, int64_t col_begin, int64_t col_end, void* out,
-                                    void* workspace, size_t workspace_bytes, void* stream) {
+                                    void* workspace, size_t workspace_bytes, void* stream) { BE_NVTX_RANGE("be_b200_binary_jitmv");
     cudaStream_t s = (cudaStream_t)stream;
     BE_REQUIRE(p0 && clen && seed && out, "jitmv: NULL pointer");
     BE_REQUIRE(kind == BE_B200_JIT_SCALAR || p1, "jitmv: p1 is NULL");
@@ -631,7 +631,7 @@ extern "C" int be_b200_binary_jitmm(int kind, const void* p0, const void* p1, in
                                     const int32_t* clen, const int32_t* seed, const void* spikes,
                                     const void* aux, int spk_kind, int64_t vec_len, int64_t out_len,
                                     int64_t n, int64_t chunk_size, int corder, void* out,
-                                    void* workspace, size_t workspace_bytes, void* stream) {
+                                    void* workspace, size_t workspace_bytes, void* stream) { BE_NVTX_RANGE("be_b200_binary_jitmm");
     cudaStream_t s = (cudaStream_t)stream;
     BE_REQUIRE(p0 && clen && seed && out, "jitmm: NULL pointer");
     BE_REQUIRE(kind == BE_B200_JIT_SCALAR || p1, "jitmm: p1 is NULL");
@@ -653,7 +653,7 @@ extern "C" int be_b200_binary_jitmm(int kind, const void* p0, const void* p1, in
 extern "C" int be_b200_jitc_row_connections(const int32_t* clen, const int32_t* seed,
                                             int64_t row_begin, int64_t n_rows, int64_t k,
                                             int64_t chunk_size, int stride, int32_t* counts,
-                                            int32_t* cols, int64_t cap, void* stream) {
+                                            int32_t* cols, int64_t cap, void* stream) { BE_NVTX_RANGE("be_b200_jitc_row_connections");
     cudaStream_t s = (cudaStream_t)stream;
     BE_REQUIRE(clen && seed && counts, "jitc_row_connections: NULL pointer");
     BE_REQUIRE(stride == 32 || stride == 4, "jitc_row_connections: stride must be 32 (mv) or 4 (mm)");
@@ -668,13 +668,13 @@ extern "C" int be_b200_jitc_row_connections(const int32_t* clen, const int32_t* 
 
 extern "C" int be_b200_jitmv(int kind, const void* p0, const void* p1, int w_dtype, const int32_t* clen,
                              const int32_t* seed, const void* x, int64_t vec_len, int64_t out_len,
-                             int64_t chunk_size, int corder, void* out, void* stream) {
+                             int64_t chunk_size, int corder, void* out, void* stream) { BE_NVTX_RANGE("be_b200_jitmv");
     return jit_val_entry(kind, p0, p1, w_dtype, clen, seed, x, vec_len, out_len, 0, chunk_size, corder, out, stream);
 }
 
 extern "C" int be_b200_jitmm(int kind, const void* p0, const void* p1, int w_dtype, const int32_t* clen,
                              const int32_t* seed, const void* X, int64_t vec_len, int64_t out_len, int64_t n,
-                             int64_t chunk_size, int corder, void* out, void* stream) {
+                             int64_t chunk_size, int corder, void* out, void* stream) { BE_NVTX_RANGE("be_b200_jitmm");
     BE_REQUIRE(n >= 1, "jitmm: n must be >= 1");
     return jit_val_entry(kind, p0, p1, w_dtype, clen, seed, X, vec_len, out_len, n, chunk_size, corder, out, stream);
 }

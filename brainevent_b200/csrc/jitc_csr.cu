@@ -160,7 +160,7 @@ extern "C" size_t be_b200_jitc_csr_workspace_bytes(int64_t n_rows, int64_t nnz) 
 extern "C" int be_b200_jitc_csr_count(const int32_t* clen, const int32_t* seed, int64_t n_rows,
                                       int64_t n_cols, int64_t chunk_size, int stride, int corder,
                                       int64_t* indptr, void* workspace, size_t workspace_bytes,
-                                      void* stream) {
+                                      void* stream) { BE_NVTX_RANGE("be_b200_jitc_csr_count");
     cudaStream_t s = (cudaStream_t)stream;
     BE_REQUIRE(clen && seed && indptr && workspace, "jitc_csr_count: NULL pointer");
     BE_REQUIRE(stride == 32 || stride == 4, "jitc_csr_count: stride must be 32 (mv) or 4 (mm)");
@@ -186,7 +186,7 @@ extern "C" int be_b200_jitc_csr_fill(int kind, const void* p0, const void* p1, i
                                      const int32_t* clen, const int32_t* seed, int64_t n_rows,
                                      int64_t n_cols, int64_t chunk_size, int stride, int corder,
                                      const int64_t* indptr, int64_t nnz, int32_t* indices, void* data,
-                                     void* workspace, size_t workspace_bytes, void* stream) {
+                                     void* workspace, size_t workspace_bytes, void* stream) { BE_NVTX_RANGE("be_b200_jitc_csr_fill");
     cudaStream_t s = (cudaStream_t)stream;
     BE_REQUIRE(p0 && clen && seed && indptr && workspace, "jitc_csr_fill: NULL pointer");
     BE_REQUIRE(kind == BE_B200_JIT_SCALAR || p1, "jitc_csr_fill: p1 is NULL");

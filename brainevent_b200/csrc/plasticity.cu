@@ -115,7 +115,7 @@ extern "C" int be_b200_plasticity_rows(void* weights, int w_dtype, const int32_t
                                        int indptr_is64, int64_t n_conn, const void* perm, int perm_is64,
                                        const void* spikes, const void* aux, int spk_kind, const void* trace,
                                        int64_t n_rows, int64_t n_trace, int64_t nse, double w_min, double w_max,
-                                       void* workspace, size_t workspace_bytes, void* stream) {
+                                       void* workspace, size_t workspace_bytes, void* stream) { BE_NVTX_RANGE("be_b200_plasticity_rows");
     cudaStream_t s = (cudaStream_t)stream;
     BE_REQUIRE(n_rows >= 0 && n_trace >= 0 && nse >= 0 && n_rows < (1ll << 31) && n_trace < (1ll << 31), "plasticity_rows: shape out of range");
     BE_REQUIRE((weights && indices && trace) || nse == 0, "plasticity_rows: NULL pointer");
@@ -139,7 +139,7 @@ extern "C" int be_b200_plasticity_rows(void* weights, int w_dtype, const int32_t
 extern "C" int be_b200_plasticity_dense(void* W, int w_dtype, int64_t rows, int64_t cols, const void* spikes,
                                         const void* aux, int spk_kind, const void* trace, int on_post,
                                         double w_min, double w_max, void* workspace, size_t workspace_bytes,
-                                        void* stream) {
+                                        void* stream) { BE_NVTX_RANGE("be_b200_plasticity_dense");
     cudaStream_t s = (cudaStream_t)stream;
     BE_REQUIRE(rows >= 0 && cols >= 0 && rows < (1ll << 31) && cols < (1ll << 31), "plasticity_dense: shape out of range");
     BE_REQUIRE((W && trace) || rows * cols == 0, "plasticity_dense: NULL pointer");
@@ -159,7 +159,7 @@ extern "C" int be_b200_plasticity_dense(void* W, int w_dtype, int64_t rows, int6
     return BE_B200_OK;
 }
 
-extern "C" int be_b200_clip(void* w, int w_dtype, int64_t n, double w_min, double w_max, void* stream) {
+extern "C" int be_b200_clip(void* w, int w_dtype, int64_t n, double w_min, double w_max, void* stream) { BE_NVTX_RANGE("be_b200_clip");
     cudaStream_t s = (cudaStream_t)stream;
     BE_REQUIRE(n >= 0 && (w || n == 0), "clip: bad arguments");
     BE_REQUIRE(!(w_min > w_max), "clip: w_min > w_max");

@@ -145,7 +145,7 @@ static int proj_compute(be_b200_projection* p, const uint8_t* d_events, float* d
 // untouched until be_b200_projection_wait() (or the kSlots-th next submit) returns; at most
 // kSlots = 4 calls are in flight, the next submit first waits for the oldest one.
 extern "C" int be_b200_projection_submit_host(be_b200_projection* p, const uint8_t* events_host,
-                                              float* out_host) {
+                                              float* out_host) { BE_NVTX_RANGE("be_b200_projection_submit_host");
     BE_REQUIRE(p && events_host && out_host, "projection_submit_host: NULL pointer");
     const int i = p->slot;
     if (p->inflight[i]) { BE_CUDA(cudaEventSynchronize(p->ev_out[i])); p->inflight[i] = 0; }
@@ -164,7 +164,7 @@ extern "C" int be_b200_projection_submit_host(be_b200_projection* p, const uint8
 }
 
 // Blocks until every submitted call has delivered its result to host memory.
-extern "C" int be_b200_projection_wait(be_b200_projection* p) {
+extern "C" int be_b200_projection_wait(be_b200_projection* p) { BE_NVTX_RANGE("be_b200_projection_wait");
     BE_REQUIRE(p, "projection_wait: NULL pointer");
     for (int i = 0; i < kSlots; ++i)
         if (p->inflight[i]) { BE_CUDA(cudaEventSynchronize(p->ev_out[i])); p->inflight[i] = 0; }
@@ -172,7 +172,7 @@ extern "C" int be_b200_projection_wait(be_b200_projection* p) {
 }
 
 extern "C" int be_b200_projection_apply_host(be_b200_projection* p, const uint8_t* events_host,
-                                             float* out_host) {
+                                             float* out_host) { BE_NVTX_RANGE("be_b200_projection_apply_host");
     BE_REQUIRE(p && events_host && out_host, "projection_apply_host: NULL pointer");
     cudaStream_t s = p->stream;
     if (p->n_pre > 0) BE_CUDA(cudaMemcpyAsync(p->d_events, events_host, (size_t)p->n_pre, cudaMemcpyHostToDevice, s));

@@ -248,7 +248,7 @@ extern "C" size_t be_b200_sharded_symm_bytes(int world, int64_t words_per_rank) 
 }
 
 extern "C" int be_b200_sharded_set_fcn(be_b200_sharded* h, const void* weights, int w_dtype, int homo,
-                                       const int32_t* indices, int64_t n_rows, int64_t n_conn) {
+                                       const int32_t* indices, int64_t n_rows, int64_t n_conn) { BE_NVTX_RANGE("be_b200_sharded_set_fcn");
     BE_REQUIRE(h && weights && (indices || n_rows * n_conn == 0), "sharded_set_fcn: NULL pointer");
     BE_REQUIRE(n_rows == h->n_neurons, "sharded_set_fcn: %lld rows but the exchange carries %lld neurons",
                (long long)n_rows, (long long)h->n_neurons);
@@ -260,7 +260,7 @@ extern "C" int be_b200_sharded_set_fcn(be_b200_sharded* h, const void* weights, 
 
 extern "C" int be_b200_sharded_set_csr(be_b200_sharded* h, const void* weights, int w_dtype, int homo,
                                        const int32_t* indices, const void* indptr, int indptr_is64,
-                                       int64_t n_rows, int64_t nse) {
+                                       int64_t n_rows, int64_t nse) { BE_NVTX_RANGE("be_b200_sharded_set_csr");
     BE_REQUIRE(h && weights && indptr && (indices || nse == 0), "sharded_set_csr: NULL pointer");
     BE_REQUIRE(n_rows == h->n_neurons, "sharded_set_csr: %lld rows but the exchange carries %lld neurons",
                (long long)n_rows, (long long)h->n_neurons);
@@ -272,7 +272,7 @@ extern "C" int be_b200_sharded_set_csr(be_b200_sharded* h, const void* weights, 
 
 extern "C" int be_b200_sharded_set_jitc(be_b200_sharded* h, int jit_kind, const void* p0, const void* p1,
                                         int w_dtype, const int32_t* clen, const int32_t* seed,
-                                        int64_t n_post_global, int64_t chunk_size, int corder) {
+                                        int64_t n_post_global, int64_t chunk_size, int corder) { BE_NVTX_RANGE("be_b200_sharded_set_jitc");
     BE_REQUIRE(h && p0 && clen && seed && (jit_kind == BE_B200_JIT_SCALAR || p1), "sharded_set_jitc: NULL pointer");
     BE_REQUIRE(chunk_size >= 1 && n_post_global >= h->n_out, "sharded_set_jitc: bad shape");
     h->conn = BE_B200_CONN_JITC; h->jit_kind = jit_kind; h->p0 = p0; h->p1 = p1; h->w_dtype = w_dtype;
@@ -280,7 +280,7 @@ extern "C" int be_b200_sharded_set_jitc(be_b200_sharded* h, int jit_kind, const 
     return BE_B200_OK;
 }
 
-extern "C" int be_b200_sharded_set_dense(be_b200_sharded* h, const void* W, int w_dtype) {
+extern "C" int be_b200_sharded_set_dense(be_b200_sharded* h, const void* W, int w_dtype) { BE_NVTX_RANGE("be_b200_sharded_set_dense");
     BE_REQUIRE(h && (W || h->n_neurons * h->n_out == 0), "sharded_set_dense: NULL pointer");
     h->conn = BE_B200_CONN_DENSE; h->weights = W; h->w_dtype = w_dtype;
     return BE_B200_OK;
@@ -373,7 +373,7 @@ static bool sharded_is_fused(const be_b200_sharded* h) {
 }
 
 extern "C" int be_b200_sharded_publish(be_b200_sharded* h, const void* spikes_local, int spk_kind, void* out,
-                                       void* stream) {
+                                       void* stream) { BE_NVTX_RANGE("be_b200_sharded_publish");
     BE_REQUIRE(h && out && h->conn >= 0, "sharded_publish: projection not configured");
     cudaStream_t s = (cudaStream_t)stream;
     const size_t out_bytes = (size_t)h->n_out * wt_bytes(h->w_dtype);
@@ -395,7 +395,7 @@ extern "C" int be_b200_sharded_publish(be_b200_sharded* h, const void* spikes_lo
                                 h->wpr, h->ctl, s);
 }
 
-extern "C" int be_b200_sharded_consume(be_b200_sharded* h, void* out, void* stream) {
+extern "C" int be_b200_sharded_consume(be_b200_sharded* h, void* out, void* stream) { BE_NVTX_RANGE("be_b200_sharded_consume");
     BE_REQUIRE(h && out && h->conn >= 0, "sharded_consume: projection not configured");
     cudaStream_t s = (cudaStream_t)stream;
     const size_t out_bytes = (size_t)h->n_out * wt_bytes(h->w_dtype);
@@ -443,7 +443,7 @@ extern "C" int be_b200_sharded_consume(be_b200_sharded* h, void* out, void* stre
 }
 
 extern "C" int be_b200_sharded_step(be_b200_sharded* h, const void* spikes_local, int spk_kind, void* out,
-                                    void* stream) {
+                                    void* stream) { BE_NVTX_RANGE("be_b200_sharded_step");
     const int rc = be_b200_sharded_publish(h, spikes_local, spk_kind, out, stream);
     return rc ? rc : be_b200_sharded_consume(h, out, stream);
 }
@@ -458,7 +458,7 @@ extern "C" int be_b200_sharded_timed_out(be_b200_sharded* h) {
 }
 
 // ---- host-buffer pipeline ---------------------------------------------------------------------------------
-extern "C" int be_b200_sharded_host_init(be_b200_sharded* h, int slots, int use_graph) {
+extern "C" int be_b200_sharded_host_init(be_b200_sharded* h, int slots, int use_graph) { BE_NVTX_RANGE("be_b200_sharded_host_init");
     BE_REQUIRE(h && h->conn >= 0 && slots >= 1 && slots <= 16, "sharded_host_init: bad arguments");
     BE_REQUIRE(h->w_dtype == BE_B200_F32, "sharded_host_init: the host pipeline carries float32 outputs");
     BE_REQUIRE(h->slots == 0, "sharded_host_init: already initialised");
@@ -503,7 +503,7 @@ extern "C" int be_b200_sharded_host_init(be_b200_sharded* h, int slots, int use_
 // spikes_host: pinned uint8[n_local]; out_host: pinned float[n_out].  Both must stay untouched until
 // be_b200_sharded_wait() (or the `slots`-th next submit) returns.  Collective: every rank submits the
 // same number of timesteps.
-extern "C" int be_b200_sharded_submit_host(be_b200_sharded* h, const uint8_t* spikes_host, float* out_host) {
+extern "C" int be_b200_sharded_submit_host(be_b200_sharded* h, const uint8_t* spikes_host, float* out_host) { BE_NVTX_RANGE("be_b200_sharded_submit_host");
     BE_REQUIRE(h && h->slots > 0 && out_host && (spikes_host || h->n_local == 0), "sharded_submit_host: bad arguments");
     const int i = h->slot;
     if (h->inflight[i]) { BE_CUDA(cudaEventSynchronize(h->ev_out[i])); h->inflight[i] = 0; }
@@ -524,7 +524,7 @@ extern "C" int be_b200_sharded_submit_host(be_b200_sharded* h, const uint8_t* sp
     return BE_B200_OK;
 }
 
-extern "C" int be_b200_sharded_wait(be_b200_sharded* h) {
+extern "C" int be_b200_sharded_wait(be_b200_sharded* h) { BE_NVTX_RANGE("be_b200_sharded_wait");
     BE_REQUIRE(h, "sharded_wait: NULL pointer");
     for (int i = 0; i < h->slots; ++i)
         if (h->inflight[i]) { BE_CUDA(cudaEventSynchronize(h->ev_out[i])); h->inflight[i] = 0; }
@@ -538,7 +538,7 @@ extern "C" int be_b200_sharded_wait(be_b200_sharded* h) {
 // n timesteps back to back without returning to the caller: timestep t reads spikes_host[t % n_in] and
 // writes out_host[t % n_out_bufs]; returns after the last result has landed.
 extern "C" int be_b200_sharded_run_host(be_b200_sharded* h, int64_t n_steps, const uint8_t* const* spikes_host,
-                                        int n_in, float* const* out_host, int n_out_bufs) {
+                                        int n_in, float* const* out_host, int n_out_bufs) { BE_NVTX_RANGE("be_b200_sharded_run_host");
     BE_REQUIRE(h && spikes_host && out_host && n_in >= 1 && n_out_bufs >= 1, "sharded_run_host: bad arguments");
     BE_REQUIRE(n_out_bufs >= h->slots, "sharded_run_host: needs at least `slots` output buffers (results in flight)");
     for (int64_t t = 0; t < n_steps; ++t) {

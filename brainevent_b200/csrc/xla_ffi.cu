@@ -323,6 +323,251 @@ XLA_FFI_Error* jit_val_common(XLA_FFI_CallFrame* frame, bool matmat, const char*
     return fr.finish(rc, name);
 }
 
+
+// ==========================================================================================================
+// Reference-name-compatible decoders (SURVEY 8(b) last row / Appendix D): same argument order, result order,
+// aliasing and attributes as the reference's `// @BE` entry points, one generic decoder per family.  The
+// per-name symbols are generated into xla_ref_aliases.inc (tools/gen_ffi_aliases.py).
+// ==========================================================================================================
+size_t xla_dtype_size(int dt) {
+    switch (dt) {
+        case BE_XLA_PRED: case BE_XLA_S8: case BE_XLA_U8: return 1;
+        case BE_XLA_F16: case BE_XLA_BF16: return 2;
+        case BE_XLA_S32: case BE_XLA_U32: case BE_XLA_F32: return 4;
+        case BE_XLA_S64: case BE_XLA_F64: return 8;
+        default: return 0;
+    }
+}
+
+// out[c, r] = in[r, c]   (the reference's dense / JITC mm kernels write a physical batch-major buffer)
+template <typename T>
+__global__ void transpose_2d_kernel(const T* __restrict__ in, T* __restrict__ out, int64_t rows, int64_t cols) {
+    __shared__ T tile[32][33];
+    const int64_t c0 = (int64_t)blockIdx.x * 32, r0 = (int64_t)blockIdx.y * 32;
+    for (int i = threadIdx.y; i < 32; i += 8) {
+        const int64_t r = r0 + i, c = c0 + threadIdx.x;
+        if (r < rows && c < cols) tile[i][threadIdx.x] = in[r * cols + c];
+    }
+    __syncthreads();
+    for (int i = threadIdx.y; i < 32; i += 8) {
+        const int64_t c = c0 + i, r = r0 + threadIdx.x;
+        if (r < rows && c < cols) out[c * rows + r] = tile[threadIdx.x][i];
+    }
+}
+int launch_transpose(const void* in, void* out, int64_t rows, int64_t cols, size_t elem, cudaStream_t s) {
+    if (rows == 0 || cols == 0) return BE_B200_OK;
+    dim3 grid((unsigned)((cols + 31) / 32), (unsigned)((rows + 31) / 32)), block(32, 8);
+    if (elem == 4) transpose_2d_kernel<uint32_t><<<grid, block, 0, s>>>((const uint32_t*)in, (uint32_t*)out, rows, cols);
+    else if (elem == 8) transpose_2d_kernel<uint64_t><<<grid, block, 0, s>>>((const uint64_t*)in, (uint64_t*)out, rows, cols);
+    else if (elem == 2) transpose_2d_kernel<uint16_t><<<grid, block, 0, s>>>((const uint16_t*)in, (uint16_t*)out, rows, cols);
+    else return BE_B200_EUNIMPL;
+    return cudaGetLastError() == cudaSuccess ? BE_B200_OK : BE_B200_EINTERNAL;
+}
+
+// reference jit*mm `pack`: B int8 [k, n] -> packed[n, n_words], bit b of word w of column c = B[32w + b, c] != 0
+// (ref: _jit_scalar/binary_jitsmm.cu:130-154)
+__global__ void pack_cols_kernel(const int8_t* __restrict__ B, uint32_t* __restrict__ packed, int64_t k, int64_t n,
+                                 int64_t n_words) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n * n_words) return;
+    const int64_t c = i / n_words, w = i - c * n_words;
+    uint32_t bits = 0;
+    for (int b = 0; b < 32; ++b) {
+        const int64_t r = w * 32 + b;
+        if (r < k && B[r * n + c] != 0) bits |= 1u << b;
+    }
+    packed[i] = bits;
+}
+// column-major packing -> this library's row-major packing [k, ceil(n/32)] (bit c of word cw of row r)
+__global__ void repack_rows_kernel(const uint32_t* __restrict__ cols, uint32_t* __restrict__ rows_out, int64_t k, int64_t n,
+                                   int64_t n_words) {
+    const int64_t wpr = (n + 31) / 32;
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= k * wpr) return;
+    const int64_t r = i / wpr, cw = i - r * wpr;
+    uint32_t bits = 0;
+    for (int b = 0; b < 32; ++b) {
+        const int64_t c = cw * 32 + b;
+        if (c < n && ((cols[c * n_words + (r >> 5)] >> (r & 31)) & 1u)) bits |= 1u << b;
+    }
+    rows_out[i] = bits;
+}
+
+XLA_FFI_Error* ref_csr(XLA_FFI_CallFrame* frame, bool mm, bool hybrid, bool has_perm) {
+    const int na = 4 + (has_perm ? 1 : 0) + (hybrid ? 3 : 0);
+    BE_XLA_PROLOGUE(na, hybrid ? 4 : 1, "csr");
+    XLA_FFI_Buffer *w = fr.arg(0), *idx = fr.arg(1), *ptr = fr.arg(2), *perm = has_perm ? fr.arg(3) : nullptr,
+                   *ev = fr.arg(3 + (has_perm ? 1 : 0)), *out = fr.ret(0);
+    const int wt = wt_of(w->dtype), sk = spk_of(ev->dtype);
+    if (wt < 0 || sk < 0 || sk == BE_B200_SPK_PACKED) return fr.fail(BE_B200_EUNIMPL, "csr: unsupported weight / event dtype");
+    if (idx->dtype != BE_XLA_S32) return fr.fail(BE_B200_EINVAL, "csr: indices must be int32");
+    const int64_t m = ptr->dims[0] - 1, nse = numel(idx);
+    int64_t k, n = 0;
+    if (hybrid) {                       // scatter over active rows: events [m] or [m, n]
+        if (mm) { n = out->dims[0]; k = out->dims[1]; } else k = out->dims[0];
+        // the reference's task_begin / task_end / status scratch is aliased in -> out; this library needs none of it
+        // (the active-row list replaces the task list), so it is passed through untouched
+        for (int i = 0; i < 3; ++i) {
+            XLA_FFI_Buffer *a = fr.arg(na - 3 + i), *r = fr.ret(1 + i);
+            const size_t bytes = (size_t)numel(a) * xla_dtype_size(a->dtype);
+            if (r && a->data != r->data && bytes &&
+                cudaMemcpyAsync(r->data, a->data, bytes, cudaMemcpyDeviceToDevice, (cudaStream_t)fr.stream) != cudaSuccess)
+                return fr.fail(BE_B200_EINTERNAL, "csr: workspace pass-through copy failed");
+        }
+    } else {                            // gather over all rows: events [k] or [k, n]
+        k = ev->dims[0];
+        if (mm) n = ev->dims[1];
+    }
+    const int transpose = hybrid ? 1 : 0;
+    if (XLA_FFI_Error* e = fr.get_scratch(transpose ? m : k, mm ? n : 1)) return e;
+    int rc;
+    if (mm)
+        rc = be_b200_binary_csrmm(w->data, wt, numel(w) == 1, (const int32_t*)idx->data, ptr->data, ptr->dtype == BE_XLA_S64,
+                                  perm ? perm->data : nullptr, perm && perm->dtype == BE_XLA_S64, ev->data, nullptr, sk, m, k, nse,
+                                  n, transpose, /*out_batch_major=*/transpose, out->data, fr.scratch, fr.scratch_bytes, fr.stream);
+    else
+        rc = be_b200_binary_csrmv(w->data, wt, numel(w) == 1, (const int32_t*)idx->data, ptr->data, ptr->dtype == BE_XLA_S64,
+                                  perm ? perm->data : nullptr, perm && perm->dtype == BE_XLA_S64, ev->data, nullptr, sk, m, k, nse,
+                                  transpose, out->data, fr.scratch, fr.scratch_bytes, fr.stream);
+    return fr.finish(rc, "csr");
+}
+
+XLA_FFI_Error* ref_fcnmv_scatter(XLA_FFI_CallFrame* frame) {
+    BE_XLA_PROLOGUE(3, 1, "fcnmv_scatter");
+    XLA_FFI_Buffer *w = fr.arg(0), *idx = fr.arg(1), *ev = fr.arg(2), *out = fr.ret(0);
+    const int wt = wt_of(w->dtype), sk = spk_of(ev->dtype);
+    if (wt < 0 || sk < 0 || idx->dtype != BE_XLA_S32 || idx->rank != 2) return fr.fail(BE_B200_EUNIMPL, "fcnmv_scatter: unsupported operands");
+    const int64_t n_rows = idx->dims[0], n_conn = idx->dims[1];
+    if (XLA_FFI_Error* e = fr.get_scratch(n_rows, 1)) return e;
+    return fr.finish(be_b200_binary_fcnmv(w->data, wt, numel(w) == 1, (const int32_t*)idx->data, n_rows, n_conn, ev->data, nullptr, sk,
+                                          n_rows, out->dims[0], 1, out->data, fr.scratch, fr.scratch_bytes, fr.stream), "fcnmv_scatter");
+}
+
+// scatter ("sraw"): matrix [n_pre, n_batch] -> out [n_batch, n_post] (batch first, ref: _fcn/binary.py:1123-1124)
+// gather: matrix [n_post, n_batch] or packed uint32 [n_post, ceil(n_batch/32)] -> out [n_pre, n_batch]
+XLA_FFI_Error* ref_fcnmm(XLA_FFI_CallFrame* frame, bool scatter, bool packed) {
+    BE_XLA_PROLOGUE(3, 1, "fcnmm");
+    XLA_FFI_Buffer *w = fr.arg(0), *idx = fr.arg(1), *ev = fr.arg(2), *out = fr.ret(0);
+    const int wt = wt_of(w->dtype), sk = packed ? BE_B200_SPK_PACKED : spk_of(ev->dtype);
+    if (wt < 0 || sk < 0 || idx->dtype != BE_XLA_S32 || idx->rank != 2 || ev->rank != 2 || out->rank != 2)
+        return fr.fail(BE_B200_EUNIMPL, "fcnmm: unsupported operands");
+    const int64_t n_rows = idx->dims[0], n_conn = idx->dims[1];
+    const int64_t n = scatter ? out->dims[0] : out->dims[1];
+    const int64_t n_out = scatter ? out->dims[1] : n_rows, n_src = scatter ? n_rows : ev->dims[0];
+    if (XLA_FFI_Error* e = fr.get_scratch(n_src, n)) return e;
+    return fr.finish(be_b200_binary_fcnmm(w->data, wt, numel(w) == 1, (const int32_t*)idx->data, n_rows, n_conn, ev->data, nullptr, sk,
+                                          n_src, n_out, n, scatter ? 1 : 0, scatter ? 1 : 0, out->data, fr.scratch, fr.scratch_bytes,
+                                          fr.stream), "fcnmm");
+}
+
+XLA_FFI_Error* ref_fcnmm_pack(XLA_FFI_CallFrame* frame) {
+    BE_XLA_PROLOGUE(1, 1, "fcnmm_pack");
+    XLA_FFI_Buffer *ev = fr.arg(0), *packed = fr.ret(0);
+    const int sk = spk_of(ev->dtype);
+    if (sk < 0 || sk == BE_B200_SPK_PACKED || ev->rank != 2) return fr.fail(BE_B200_EUNIMPL, "fcnmm_pack: spikes must be bool / int8 / float32 [rows, batch]");
+    const int64_t n = ev->dims[0], b = ev->dims[1];
+    if (XLA_FFI_Error* e = fr.get_scratch(n, b)) return e;
+    void* ids = nullptr;
+    const size_t ids_bytes = (size_t)(n + 1) * 4 + 16;
+    if (XLA_FFI_Error* e = fr.alloc_bytes(ids_bytes, &ids)) { fr.release(); return e; }
+    const int rc = be_b200_compact_2d(ev->data, sk, n, b, /*nonzero_pred=*/0, (uint32_t*)packed->data, (int32_t*)ids, (int32_t*)ids + n,
+                                      fr.scratch, fr.scratch_bytes, fr.stream);
+    fr.free_bytes(ids_bytes, ids);
+    return fr.finish(rc, "fcnmm_pack");
+}
+
+XLA_FFI_Error* ref_jit_pack_bool(XLA_FFI_CallFrame* frame) {
+    BE_XLA_PROLOGUE(1, 1, "pack_bool");
+    XLA_FFI_Buffer *ev = fr.arg(0), *packed = fr.ret(0);
+    if (spk_of(ev->dtype) != BE_B200_SPK_BOOL) return fr.fail(BE_B200_EUNIMPL, "pack_bool: spikes must be int8 / bool");
+    return fr.finish(be_b200_bitpack_1d(ev->data, BE_B200_SPK_BOOL, numel(ev), 1, (uint32_t*)packed->data, fr.stream), "pack_bool");
+}
+
+// args: scalar (weight, clen, seed, packed); normal (w_loc, w_scale, clen, seed, packed); uniform (w_low, w_high, ...)
+// attrs vector_size, chunk_size (int32)   ref: _jit_scalar/binary.py:452-457
+XLA_FFI_Error* ref_jitmv(XLA_FFI_CallFrame* frame, int kind, int corder) {
+    const int np = kind == BE_B200_JIT_SCALAR ? 1 : 2;
+    BE_XLA_PROLOGUE(np + 3, 1, "jitmv");
+    XLA_FFI_Buffer *p0 = fr.arg(0), *p1 = np == 2 ? fr.arg(1) : nullptr, *clen = fr.arg(np), *seed = fr.arg(np + 1),
+                   *packed = fr.arg(np + 2), *out = fr.ret(0);
+    int64_t vec_len = 0, chunk = 0;
+    if (!fr.attr_i64("vector_size", &vec_len) || !fr.attr_i64("chunk_size", &chunk))
+        return fr.fail(BE_B200_EINVAL, "jitmv: attrs vector_size and chunk_size are required");
+    const int wt = wt_of(p0->dtype);
+    if (wt < 0 || packed->dtype != BE_XLA_U32) return fr.fail(BE_B200_EUNIMPL, "jitmv: unsupported operands");
+    if (XLA_FFI_Error* e = fr.get_scratch(vec_len, 1)) return e;
+    return fr.finish(be_b200_binary_jitmv(kind, p0->data, p1 ? p1->data : nullptr, wt, (const int32_t*)clen->data, (const int32_t*)seed->data,
+                                          packed->data, nullptr, BE_B200_SPK_PACKED, vec_len, out->dims[0], chunk, corder, 0, -1, 0, -1,
+                                          out->data, fr.scratch, fr.scratch_bytes, fr.stream), "jitmv");
+}
+
+XLA_FFI_Error* ref_jit_pack_mm(XLA_FFI_CallFrame* frame) {
+    BE_XLA_PROLOGUE(1, 1, "pack");
+    XLA_FFI_Buffer *B = fr.arg(0), *packed = fr.ret(0);
+    int64_t k = 0, n = 0, n_words = 0;
+    if (!fr.attr_i64("k", &k) || !fr.attr_i64("n", &n) || !fr.attr_i64("n_words", &n_words))
+        return fr.fail(BE_B200_EINVAL, "pack: attrs k, n, n_words are required");
+    if (spk_of(B->dtype) != BE_B200_SPK_BOOL) return fr.fail(BE_B200_EUNIMPL, "pack: spikes must be int8 / bool");
+    const int64_t total = n * n_words;
+    if (total > 0)
+        pack_cols_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)fr.stream>>>((const int8_t*)B->data, (uint32_t*)packed->data,
+                                                                                             k, n, n_words);
+    return fr.finish(cudaGetLastError() == cudaSuccess ? BE_B200_OK : BE_B200_EINTERNAL, "pack");
+}
+
+// attrs m, k, n, n_words, chunk_size; notrans: out [m, n] walks k = packed rows; trans: events m, out [k, n]
+// (ref: _jit_scalar/binary.py:978-997)
+XLA_FFI_Error* ref_jitmm(XLA_FFI_CallFrame* frame, int kind, int corder) {
+    const int np = kind == BE_B200_JIT_SCALAR ? 1 : 2;
+    BE_XLA_PROLOGUE(np + 3, 1, "jitmm");
+    XLA_FFI_Buffer *p0 = fr.arg(0), *p1 = np == 2 ? fr.arg(1) : nullptr, *clen = fr.arg(np), *seed = fr.arg(np + 1),
+                   *packed = fr.arg(np + 2), *out = fr.ret(0);
+    int64_t m = 0, k = 0, n = 0, n_words = 0, chunk = 0;
+    if (!fr.attr_i64("m", &m) || !fr.attr_i64("k", &k) || !fr.attr_i64("n", &n) || !fr.attr_i64("n_words", &n_words) ||
+        !fr.attr_i64("chunk_size", &chunk))
+        return fr.fail(BE_B200_EINVAL, "jitmm: attrs m, k, n, n_words, chunk_size are required");
+    const int wt = wt_of(p0->dtype);
+    if (wt < 0 || packed->dtype != BE_XLA_U32) return fr.fail(BE_B200_EUNIMPL, "jitmm: unsupported operands");
+    const int64_t vec_len = corder ? k : m, out_len = corder ? m : k;
+    const int64_t wpr = (n + 31) / 32;
+    void* rows = nullptr;
+    const size_t rows_bytes = (size_t)std::max<int64_t>(vec_len * wpr, 4) * 4;
+    if (XLA_FFI_Error* e = fr.alloc_bytes(rows_bytes, &rows)) return e;
+    if (vec_len * wpr > 0)
+        repack_rows_kernel<<<(unsigned)((vec_len * wpr + 255) / 256), 256, 0, (cudaStream_t)fr.stream>>>((const uint32_t*)packed->data,
+                                                                                                        (uint32_t*)rows, vec_len, n, n_words);
+    if (XLA_FFI_Error* e = fr.get_scratch(vec_len, n)) { fr.free_bytes(rows_bytes, rows); return e; }
+    const int rc = be_b200_binary_jitmm(kind, p0->data, p1 ? p1->data : nullptr, wt, (const int32_t*)clen->data, (const int32_t*)seed->data,
+                                        rows, nullptr, BE_B200_SPK_PACKED, vec_len, out_len, n, chunk, corder, out->data, fr.scratch,
+                                        fr.scratch_bytes, fr.stream);
+    fr.free_bytes(rows_bytes, rows);
+    return fr.finish(rc, "jitmm");
+}
+
+// mv: (weights [rows, cols], spikes) -> out.  mm: spikes [k, n] -> PHYSICAL out [n, m] (batch-major; the reference's
+// Python transposes it back, ref: _dense/binary.py:980-988)
+XLA_FFI_Error* ref_dense(XLA_FFI_CallFrame* frame, bool mm, int transpose) {
+    BE_XLA_PROLOGUE(2, 1, "dense");
+    XLA_FFI_Buffer *w = fr.arg(0), *ev = fr.arg(1), *out = fr.ret(0);
+    const int wt = wt_of(w->dtype), sk = spk_of(ev->dtype);
+    if (wt < 0 || sk < 0 || sk == BE_B200_SPK_PACKED || w->rank != 2) return fr.fail(BE_B200_EUNIMPL, "dense: unsupported operands");
+    const int64_t rows = w->dims[0], cols = w->dims[1], n_src = transpose ? rows : cols, m = transpose ? cols : rows;
+    if (!mm) {
+        if (XLA_FFI_Error* e = fr.get_scratch(n_src, 1)) return e;
+        return fr.finish(be_b200_binary_densemv(w->data, wt, rows, cols, ev->data, nullptr, sk, transpose, out->data, fr.scratch,
+                                                fr.scratch_bytes, fr.stream), "densemv");
+    }
+    const int64_t n = ev->dims[1];
+    if (XLA_FFI_Error* e = fr.get_scratch(n_src, n)) return e;
+    void* tmp = nullptr;
+    const size_t elem = xla_dtype_size(w->dtype), tmp_bytes = (size_t)std::max<int64_t>(m * n, 4) * elem;
+    if (XLA_FFI_Error* e = fr.alloc_bytes(tmp_bytes, &tmp)) { fr.release(); return e; }
+    int rc = be_b200_binary_densemm(w->data, wt, rows, cols, ev->data, nullptr, sk, n, transpose, tmp, fr.scratch, fr.scratch_bytes, fr.stream);
+    if (rc == BE_B200_OK) rc = launch_transpose(tmp, out->data, m, n, elem, (cudaStream_t)fr.stream);
+    fr.free_bytes(tmp_bytes, tmp);
+    return fr.finish(rc, "densemm");
+}
+
 }  // namespace
 
 extern "C" {
@@ -473,5 +718,7 @@ XLA_FFI_Error* be_b200_xla_binary_2d_row_sparse_encode(XLA_FFI_CallFrame* frame)
     return fr.finish(be_b200_binary_2d_row_sparse_encode(ev->data, sk, ev->dims[0], ev->dims[1], out->dims[1], (int32_t*)out->data,
                                                          (int32_t*)mx->data, fr.stream), "be_b200_xla_binary_2d_row_sparse_encode");
 }
+
+#include "xla_ref_aliases.inc"
 
 }  // extern "C"

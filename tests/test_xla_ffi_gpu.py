@@ -143,13 +143,13 @@ class FakeXla:
         self.keep += [types, ptrs]
         return Args(C.sizeof(Args), None, n, types, ptrs)
 
-    def frame(self, ins, outs, attrs, packed_u32=()):
+    def frame(self, ins, outs, attrs, packed_u32=(), packed_u32_out=()):
         f = CallFrame()
         f.struct_size = C.sizeof(CallFrame)
         f.api = C.pointer(self.api)
         f.stage = 3
         f.args = self._buffers(ins, packed_u32)
-        f.rets = self._buffers(outs)
+        f.rets = self._buffers(outs, packed_u32_out)
         names = sorted(attrs)
         n = len(names)
         types = (C.c_int * max(n, 1))(*([3] * n))
