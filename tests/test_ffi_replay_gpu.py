@@ -67,7 +67,7 @@ def test_replay_reference_ffi_calls(backend, ci):
                     u32_in.append(j)
                 ins.append(src[0])
         outs, u32_out = [], []
-        alias_of = {v: k for k, v in call["aliases"].items()}          # result index -> operand index
+        alias_of = {int(v): int(k) for k, v in call["aliases"].items()}          # result index -> operand index
         for j, (shape, dt) in enumerate(call["outs"]):
             if j in alias_of:
                 outs.append(ins[alias_of[j]])                           # XLA hands the operand's buffer back
