@@ -17,6 +17,7 @@ struct CsrRows {
         s = (int64_t)__ldg(indptr + r);
         e = (int64_t)__ldg(indptr + r + 1);
     }
+    __device__ __forceinline__ int64_t total(int64_t n_rows) const { return (int64_t)__ldg(indptr + n_rows); }
 };
 struct FcnRows {
     int64_t n_conn;
@@ -24,6 +25,7 @@ struct FcnRows {
         s = r * n_conn;
         e = s + n_conn;
     }
+    __device__ __forceinline__ int64_t total(int64_t n_rows) const { return n_rows * n_conn; }
 };
 
 template <typename T, bool HOMO, int PERM>

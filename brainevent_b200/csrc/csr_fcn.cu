@@ -18,6 +18,7 @@
 #include "conn.cuh"
 
 #include <algorithm>
+#include <cstdlib>
 #include <type_traits>
 
 namespace be {
@@ -240,7 +241,12 @@ static int launch_scatter_mv(const Rows& rows, const ConnArgs& c, const Events& 
     return BE_B200_OK;
 }
 
-constexpr size_t kL2TileBytes = 48u << 20;   // output tile kept L2-resident per scatter pass (L2 = 126 MB)
+constexpr size_t kL2TileBytesDefault = 48u << 20;   // output tile kept L2-resident per scatter pass (L2 = 126 MB)
+static size_t l2_tile_bytes() {
+    if (const char* e = getenv("BE_B200_SPMM_TILE_MB")) { const long v = atol(e); if (v >= 1 && v <= 4096) return (size_t)v << 20; }   // A/B switch
+    return kL2TileBytesDefault;
+}
+#define kL2TileBytes (l2_tile_bytes())
 
 template <typename T, bool HOMO, int PERM, typename Rows>
 static int launch_scatter_mm(const Rows& rows, const ConnArgs& c, const Events& ev, int64_t n_src,

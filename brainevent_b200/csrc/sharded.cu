@@ -26,58 +26,57 @@
 #include "exchange.cuh"
 
 #include <algorithm>
+#include <cstdlib>
 #include <new>
 #include <string_view>
 #include <type_traits>
 
 namespace be {
 
-constexpr int kChunkWords = 128;             // 4096 source neurons per work item
-constexpr int kShHeavyRow = 8192;
-constexpr int kShHeavyCap = 32;
+constexpr int kChunkWords = 64;              // 2048 source neurons per work item (two words per producer lane)
 
+// Chunk pipeline inside a CTA: warp 0 PRODUCES the row list of chunk k+1 (cursor draw, flag wait for a peer's
+// first chunk, pull of 64 words, ballot-free compaction: two words per lane, one warp scan) into one half of a
+// double-buffered shared-memory list while ALL warps -- warp 0 joins when it is done -- CONSUME chunk k: groups of
+// LPR lanes take rows from the list through a shared ticket counter (no static row -> warp assignment, so the
+// only barrier is the one per chunk swap) and keep the next row's extent in flight.
 template <typename T, bool HOMO, int VEC, int LPR, typename Rows>
-__global__ void __launch_bounds__(256) exchange_scatter_kernel(Rows rows, const int32_t* __restrict__ indices,
+__global__ void __launch_bounds__(256, 8) exchange_scatter_kernel(Rows rows, const int32_t* __restrict__ indices,
                                                                const T* __restrict__ weights,
                                                                const uint32_t* __restrict__ my_flags,
                                                                uint32_t* const* __restrict__ peer_bufs, int world,
                                                                int rank, int64_t wpr, int64_t n_bits,
                                                                T* __restrict__ out, ExchangeCtl* ctl) {
     using A = typename Acc<T>::type;
-    __shared__ int s_ids[kChunkWords * 32];
-    __shared__ int s_wsum[kChunkWords / 32];
-    __shared__ int s_heavy[kShHeavyCap];
-    __shared__ int s_nheavy, s_chunk, s_bad;
+    __shared__ int s_ids[2][kChunkWords * 32];
+    __shared__ int s_n[2];                 // rows in the list; -1 = no more chunks / exchange gave up
+    __shared__ int s_ticket[2];
     __shared__ uint32_t s_seen;
     const uint32_t t = ctl->step;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    if (threadIdx.x == 0) {
-        s_seen = 1u << rank;                                  // my own words were packed earlier in stream order
-        s_bad = (int)*(volatile uint32_t*)&ctl->timeout;      // sticky: an earlier exchange gave up
-        s_nheavy = 0;
-    }
-    __syncthreads();
-    if (s_bad) return;
     const A w0 = HOMO ? to_acc<T>(__ldg(weights)) : A(0);
     const int chunks_per_rank = (int)ceil_div(wpr, kChunkWords);
     const int total_chunks = chunks_per_rank * world;
     const int64_t half = (int64_t)(t & 1u) * wpr * world;
-    constexpr int GROUPS = 256 / LPR;
-    const int g = threadIdx.x / LPR, gl = threadIdx.x % LPR;
-    for (;;) {
-        if (threadIdx.x == 0) s_chunk = (int)atomicAdd(&ctl->next_chunk, 1u);
-        __syncthreads();
-        const int c = s_chunk;
-        if (c >= total_chunks) break;
+    constexpr int GPW = 32 / LPR;          // row groups per warp
+    const int gl = lane % LPR;
+    const unsigned gmask = (LPR >= 32) ? 0xffffffffu : (((1u << LPR) - 1u) << ((lane / LPR) * LPR));
+
+    // warp 0: build list `b` from the next chunk of the cursor
+    auto produce = [&](int b) {
+        int c = 0;
+        if (lane == 0) c = (int)atomicAdd(&ctl->next_chunk, 1u);
+        c = __shfl_sync(0xffffffffu, c, 0);
+        if (c >= total_chunks) { if (lane == 0) s_n[b] = -1; return; }
         const int o = c / chunks_per_rank, lc = c - o * chunks_per_rank;
         int p = rank + o;
         if (p >= world) p -= world;
-        if (!((s_seen >> p) & 1u)) {                          // block-uniform
-            if (threadIdx.x == 0) {
+        if (!((s_seen >> p) & 1u)) {       // this CTA's first chunk of peer p: wait for its flag (bounded by wall time)
+            int bad = 0;
+            if (lane == 0) {
                 const unsigned long long limit = (unsigned long long)(ctl->spin_ms ? ctl->spin_ms : kDefaultSpinMs) * 1000000ull;
                 unsigned long long t0 = 0;
                 unsigned int polls = 0;
-                int bad = 0;
                 while ((int32_t)(ld_acquire_sys(my_flags + p) - t) < 0) {
                     if ((++polls & 1023u) == 0) {
                         const unsigned long long now = gtimer();
@@ -86,79 +85,82 @@ __global__ void __launch_bounds__(256) exchange_scatter_kernel(Rows rows, const 
                     }
                     __nanosleep(20);
                 }
-                if (bad) s_bad = 1; else s_seen |= 1u << p;
+                if (!bad) s_seen |= 1u << p;
             }
-            __syncthreads();
-            if (s_bad) return;
+            bad = __shfl_sync(0xffffffffu, bad, 0);
+            if (bad) { if (lane == 0) s_n[b] = -1; return; }
         }
-        // pull the chunk's words and list its active rows in shared memory
-        const int64_t w_first = (int64_t)lc * kChunkWords;
-        uint32_t word = 0;
-        int cnt = 0, incl = 0;
-        if (threadIdx.x < kChunkWords) {
-            const int64_t wi = w_first + threadIdx.x;
+        const int64_t w_first = (int64_t)lc * kChunkWords + 2 * lane;
+        uint32_t wd[2];
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
+            const int64_t wi = w_first + q;
+            uint32_t v = 0;
             if (wi < wpr) {
-                word = ld_relaxed_sys(peer_bufs[p] + half + (int64_t)p * wpr + wi);
+                v = ld_relaxed_sys(peer_bufs[p] + half + (int64_t)p * wpr + wi);
                 const int64_t bit0 = ((int64_t)p * wpr + wi) * 32;
-                if (bit0 + 32 > n_bits) word = (bit0 >= n_bits) ? 0u : (word & ((1u << (int)(n_bits - bit0)) - 1u));
+                if (bit0 + 32 > n_bits) v = (bit0 >= n_bits) ? 0u : (v & ((1u << (int)(n_bits - bit0)) - 1u));
             }
-            cnt = __popc(word);
-            incl = cnt;
+            wd[q] = v;
+        }
+        const int cnt = __popc(wd[0]) + __popc(wd[1]);
+        int incl = cnt;
 #pragma unroll
-            for (int d = 1; d < 32; d <<= 1) {
-                const int v = __shfl_up_sync(0xffffffffu, incl, d);
-                if (lane >= d) incl += v;
-            }
-            if (lane == 31) s_wsum[warp] = incl;
+        for (int d = 1; d < 32; d <<= 1) {
+            const int v = __shfl_up_sync(0xffffffffu, incl, d);
+            if (lane >= d) incl += v;
         }
-        __syncthreads();
-        int n_rows = 0;
+        int pos = incl - cnt;
 #pragma unroll
-        for (int w = 0; w < kChunkWords / 32; ++w) n_rows += s_wsum[w];
-        if (threadIdx.x < kChunkWords && word) {
-            int pos = incl - cnt;
-            for (int w = 0; w < warp; ++w) pos += s_wsum[w];
-            const int base = (int)(((int64_t)p * wpr + w_first + threadIdx.x) * 32);
-            while (word) {
-                const int b = __ffs(word) - 1;
-                word &= word - 1;
-                s_ids[pos++] = base + b;
+        for (int q = 0; q < 2; ++q) {
+            uint32_t v = wd[q];
+            const int base = (int)(((int64_t)p * wpr + w_first + q) * 32);
+            while (v) {
+                const int bb = __ffs(v) - 1;
+                v &= v - 1;
+                s_ids[b][pos++] = base + bb;
             }
         }
-        __syncthreads();
-        // scatter the listed rows: LPR lanes per row, the next row's extent in flight
-        int a = g;
-        int64_t s_n = 0, e_n = 0;
-        int r_n = 0;
-        if (a < n_rows) { r_n = s_ids[a]; rows.get(r_n, s_n, e_n); }
-        for (; a < n_rows; a += GROUPS) {
-            const int r = r_n;
-            const int64_t s = s_n, e = e_n;
-            if (a + GROUPS < n_rows) { r_n = s_ids[a + GROUPS]; rows.get(r_n, s_n, e_n); }
-            if (e - s > kShHeavyRow) {
-                int slot = -1;
-                if (gl == 0) slot = atomicAdd(&s_nheavy, 1);
-                const int leader = (lane / LPR) * LPR;
-                const unsigned gmask = (LPR >= 32) ? 0xffffffffu : (((1u << LPR) - 1u) << leader);
-                slot = __shfl_sync(gmask, slot, leader);
-                if (slot < kShHeavyCap) { if (gl == 0) s_heavy[slot] = r; continue; }
-            }
-            for_each_synapse<T, HOMO, 0, VEC, LPR>(s, e, gl, indices, weights, nullptr, w0,
-                                                   [&](int col, A w) { red_add(out + col, w); });
-        }
-        __syncthreads();
-        const int nh = min(s_nheavy, kShHeavyCap);
-        if (nh > 0) {
-            for (int h = 0; h < nh; ++h) {
-                int64_t s, e;
-                rows.get(s_heavy[h], s, e);
-                for_each_synapse<T, HOMO, 0, VEC, 256>(s, e, (int)threadIdx.x, indices, weights, nullptr, w0,
+        if (lane == 31) { s_n[b] = incl; s_ticket[b] = 0; }
+    };
+
+    if (threadIdx.x == 0) s_seen = 1u << rank;               // my own words were packed earlier in stream order
+    __syncthreads();
+    if (warp == 0) {
+        // sticky: an earlier exchange gave up -> no list at all
+        int bad = 0;
+        if (lane == 0) bad = (int)*(volatile uint32_t*)&ctl->timeout;
+        bad = __shfl_sync(0xffffffffu, bad, 0);
+        if (bad) { if (lane == 0) s_n[0] = -1; }
+        else produce(0);
+    }
+    int cur = 0;
+    for (;;) {
+        __syncthreads();                                      // list `cur` is complete; list `cur ^ 1` is free again
+        const int n_rows = s_n[cur];
+        if (n_rows < 0) break;
+        if (warp == 0) produce(cur ^ 1);
+        // consume: tickets of GPW rows per warp draw, the next draw's row extents requested before this one is scattered
+        const int sub = lane / LPR;
+        int a = 0;
+        if (lane == 0) a = atomicAdd(&s_ticket[cur], GPW);
+        a = __shfl_sync(0xffffffffu, a, 0) + sub;
+        int64_t s_nx = 0, e_nx = 0;
+        if (a < n_rows) rows.get(s_ids[cur][a], s_nx, e_nx);
+        while (a - sub < n_rows) {                            // warp-uniform
+            const int64_t s = s_nx, e = e_nx;
+            const bool mine = a < n_rows;
+            int an = 0;
+            if (lane == 0) an = atomicAdd(&s_ticket[cur], GPW);
+            an = __shfl_sync(0xffffffffu, an, 0) + sub;
+            if (an < n_rows) rows.get(s_ids[cur][an], s_nx, e_nx);
+            if (mine)
+                for_each_synapse<T, HOMO, 0, VEC, LPR>(s, e, gl, indices, weights, nullptr, w0,
                                                        [&](int col, A w) { red_add(out + col, w); });
-            }
-            __syncthreads();
-            if (threadIdx.x == 0) s_nheavy = 0;
+            a = an;
         }
-        // s_chunk / s_ids are rewritten only after the barrier at the top of the next trip
+        (void)gmask;
+        cur ^= 1;
     }
 }
 
@@ -305,7 +307,8 @@ namespace {
 template <typename T, bool HOMO, typename Rows>
 int launch_exchange_scatter(be_b200_sharded* h, const Rows& rows, int vec, T* out, cudaStream_t s) {
     const double avg = h->n_neurons > 0 ? (double)h->nse / (double)h->n_neurons : 0.0;
-    const int lpr = h->lpr ? h->lpr : (avg < 40.0 ? 8 : (avg < 96.0 ? 16 : 32));
+    int lpr = h->lpr ? h->lpr : (avg < 40.0 ? 8 : (avg < 96.0 ? 16 : 32));
+    if (const char* e = getenv("BE_B200_SHARDED_LPR")) { const int v = atoi(e); if (v == 8 || v == 16 || v == 32) lpr = v; }   // A/B switch
     const int chunks = (int)ceil_div(h->wpr, kChunkWords) * h->world;
     const int blocks = std::max(1, std::min(chunks, kNumSM * 8));
 #define BE_XS(VEC, LPR)                                                                                       \

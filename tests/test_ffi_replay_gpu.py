@@ -94,7 +94,7 @@ def test_replay_reference_ffi_calls(backend, ci):
     got = produced[tuple(case["result"])][0].cpu().numpy()
     if case["transposed"]:
         got = got.T
-    want = Z[f"case{ci}_expected"]
+    want = _array(f"case{ci}_expected")
     if want.dtype == np.uint32:
         got = got.view(np.uint32)
     if case["exact"]:
