@@ -898,13 +898,38 @@ def e2e_leg(torch, dist, L, wl, world, device, K, T, numa_bound):
     if world > 1:
         dist.all_reduce(dt, op=dist.ReduceOp.MAX)
     e2e_events = wl.total_events_per_timestep() * Te * Ke
+    # the host link's own floor: the same bytes per timestep and rank, every rank at once, copies only (no kernels)
+    d_i = torch.empty(n_in, dtype=torch.uint8, device=device)
+    d_o = torch.empty(n_out, dtype=torch.float32, device=device)
+    s_i, s_o = torch.cuda.Stream(), torch.cuda.Stream()
+
+    def copies(reps):
+        for r in range(reps):
+            with torch.cuda.stream(s_i):
+                d_i.copy_(host_spk[r % POOL], non_blocking=True)
+            with torch.cuda.stream(s_o):
+                host_out[r % 4].copy_(d_o, non_blocking=True)
+        torch.cuda.synchronize()
+    copies(20)
+    if world > 1:
+        dist.barrier()
+    t0 = time.perf_counter()
+    copies(200)
+    ct = torch.tensor([time.perf_counter() - t0], device=device, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(ct, op=dist.ReduceOp.MAX)
+    copy_floor_us = float(ct.item()) * 1e6 / 200
     e2e = {"value": e2e_events / float(dt.item()), "unit": "events/s",
            "h2d_bytes_per_step": int(n_in * T), "d2h_bytes_per_step": int(4 * n_out * T),
-           "us_per_timestep": round(float(dt.item()) * 1e6 / (Te * Ke), 2), "numa_bound": bool(numa_bound),
+           "us_per_timestep": round(float(dt.item()) * 1e6 / (Te * Ke), 2),
+           "copy_only_us_per_timestep": round(copy_floor_us, 2),
+           "host_link_GBps_all_ranks": round((n_in + 4 * n_out) * world / copy_floor_us / 1e3, 1),
+           "numa_bound": bool(numa_bound),
            "host_cpus": len(os.sched_getaffinity(0)),
            "note": f"per timestep and rank: pinned host spikes (uint8[{n_in}]) -> device, hot path, fp32[{n_out}] result -> "
                    f"pinned host; timed over {Ke}x{Te} timesteps with the host clock (max over ranks), bytes scaled to "
-                   f"{T} timesteps/step; entry point: " + entry}
+                   f"{T} timesteps/step; copy_only_us_per_timestep = the same host<->device bytes with no kernel at all, every "
+                   f"rank at once (the host link's floor for this leg; tools/e2e_host_probe.py); entry point: " + entry}
     if sync_value is not None:
         e2e["sync_value"] = sync_value
     if world == 1:

@@ -33,7 +33,9 @@
 
 namespace be {
 
-constexpr int kChunkWords = 64;              // 2048 source neurons per work item (two words per producer lane)
+constexpr int kChunkWords = 64;              // LARGEST work item: 2048 source neurons (two words per producer lane); the launch
+                                             // halves it (32, 16 words) until every CTA can expect >= 4 draws from the cursor --
+                                             // with one chunk per CTA the Poisson spread of active rows per chunk is the runtime
 
 // Chunk pipeline inside a CTA: warp 0 PRODUCES the row list of chunk k+1 (cursor draw, flag wait for a peer's
 // first chunk, pull of 64 words, ballot-free compaction: two words per lane, one warp scan) into one half of a
@@ -45,7 +47,7 @@ __global__ void __launch_bounds__(256, 8) exchange_scatter_kernel(Rows rows, con
                                                                const T* __restrict__ weights,
                                                                const uint32_t* __restrict__ my_flags,
                                                                uint32_t* const* __restrict__ peer_bufs, int world,
-                                                               int rank, int64_t wpr, int64_t n_bits,
+                                                               int rank, int64_t wpr, int64_t n_bits, int cw,
                                                                T* __restrict__ out, ExchangeCtl* ctl) {
     using A = typename Acc<T>::type;
     __shared__ int s_ids[2][kChunkWords * 32];
@@ -55,7 +57,7 @@ __global__ void __launch_bounds__(256, 8) exchange_scatter_kernel(Rows rows, con
     const uint32_t t = ctl->step;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const A w0 = HOMO ? to_acc<T>(__ldg(weights)) : A(0);
-    const int chunks_per_rank = (int)ceil_div(wpr, kChunkWords);
+    const int chunks_per_rank = (int)ceil_div(wpr, cw);       // cw = words per chunk: 16, 32 or 64
     const int total_chunks = chunks_per_rank * world;
     const int64_t half = (int64_t)(t & 1u) * wpr * world;
     constexpr int GPW = 32 / LPR;          // row groups per warp
@@ -90,13 +92,13 @@ __global__ void __launch_bounds__(256, 8) exchange_scatter_kernel(Rows rows, con
             bad = __shfl_sync(0xffffffffu, bad, 0);
             if (bad) { if (lane == 0) s_n[b] = -1; return; }
         }
-        const int64_t w_first = (int64_t)lc * kChunkWords + 2 * lane;
+        const int64_t w_first = (int64_t)lc * cw + 2 * lane;
         uint32_t wd[2];
 #pragma unroll
         for (int q = 0; q < 2; ++q) {
             const int64_t wi = w_first + q;
             uint32_t v = 0;
-            if (wi < wpr) {
+            if (2 * lane + q < cw && wi < wpr) {
                 v = ld_relaxed_sys(peer_bufs[p] + half + (int64_t)p * wpr + wi);
                 const int64_t bit0 = ((int64_t)p * wpr + wi) * 32;
                 if (bit0 + 32 > n_bits) v = (bit0 >= n_bits) ? 0u : (v & ((1u << (int)(n_bits - bit0)) - 1u));
@@ -187,6 +189,7 @@ struct be_b200_sharded {
     void* ws; size_t ws_bytes;
     int fused;                // stored connectivity: 1 = exchange fused into the scatter (default)
     int lpr;                  // lanes per row of the fused scatter (0 = by mean row length)
+    int chunk_words;          // words per work item of the fused scatter (0 = by network size; 16, 32, 64)
     // host pipeline
     int slots, slot;
     uint8_t** d_in; float** d_out;
@@ -295,6 +298,9 @@ extern "C" int be_b200_sharded_set_option(be_b200_sharded* h, const char* name, 
     else if (n == "lanes_per_row") {
         BE_REQUIRE(value == 0 || value == 8 || value == 16 || value == 32, "sharded_set_option: lanes_per_row must be 0, 8, 16 or 32");
         h->lpr = (int)value;
+    } else if (n == "chunk_words") {
+        BE_REQUIRE(value == 0 || value == 16 || value == 32 || value == 64, "sharded_set_option: chunk_words must be 0, 16, 32 or 64");
+        h->chunk_words = (int)value;
     } else if (n == "spin_ms") {
         const uint32_t ms = (uint32_t)std::max<int64_t>(0, value);
         BE_CUDA(cudaMemcpy(&h->ctl->spin_ms, &ms, 4, cudaMemcpyHostToDevice));
@@ -309,12 +315,16 @@ int launch_exchange_scatter(be_b200_sharded* h, const Rows& rows, int vec, T* ou
     const double avg = h->n_neurons > 0 ? (double)h->nse / (double)h->n_neurons : 0.0;
     int lpr = h->lpr ? h->lpr : (avg < 40.0 ? 8 : (avg < 96.0 ? 16 : 32));
     if (const char* e = getenv("BE_B200_SHARDED_LPR")) { const int v = atoi(e); if (v == 8 || v == 16 || v == 32) lpr = v; }   // A/B switch
-    const int chunks = (int)ceil_div(h->wpr, kChunkWords) * h->world;
+    if (const char* e = getenv("BE_B200_SHARDED_CW")) { const int v = atoi(e); if (v == 16 || v == 32 || v == 64) h->chunk_words = v; }
+    int cw = kChunkWords;
+    if (h->chunk_words) cw = h->chunk_words;
+    else while (cw > 16 && ceil_div(h->wpr, cw) * h->world < (int64_t)4 * kNumSM * 8) cw >>= 1;
+    const int chunks = (int)ceil_div(h->wpr, cw) * h->world;
     const int blocks = std::max(1, std::min(chunks, kNumSM * 8));
 #define BE_XS(VEC, LPR)                                                                                       \
     exchange_scatter_kernel<T, HOMO, VEC, LPR, Rows><<<blocks, 256, 0, s>>>(                                   \
         rows, h->indices, (const T*)h->weights, h->my_flags, (uint32_t* const*)h->d_peer_bufs, h->world,       \
-        h->rank, h->wpr, h->n_neurons, out, h->ctl)
+        h->rank, h->wpr, h->n_neurons, cw, out, h->ctl)
 #define BE_XS_L(VEC)                                                                                           \
     do { if (lpr == 8) BE_XS(VEC, 8); else if (lpr == 16) BE_XS(VEC, 16); else BE_XS(VEC, 32); } while (0)
     {

@@ -360,7 +360,8 @@ int be_b200_sharded_set_jitc(be_b200_sharded* h, int jit_kind, const void* p0, c
                              int64_t chunk_size, int corder);
 int be_b200_sharded_set_dense(be_b200_sharded* h, const void* W, int w_dtype);
 /* options: "fused" (stored connectivity: 1 = two-kernel fused step, 0 = pack / wait+compact / scatter),
- * "lanes_per_row" (0 auto, 8, 16, 32), "spin_ms" (flag-wait bound) */
+ * "lanes_per_row" (0 auto, 8, 16, 32), "chunk_words" (0 auto, 16, 32, 64: spike words per work item of the fused
+ * scatter), "spin_ms" (flag-wait bound) */
 int be_b200_sharded_set_option(be_b200_sharded* h, const char* name, int64_t value);
 /* One timestep, device resident: spikes_local [n_local] (BOOL or F32) -> out [n_out] in the weight dtype.
  * Enqueues on `stream`, never synchronises; collective (every rank calls it equally often). */
