@@ -569,8 +569,11 @@ class Jitc1MSharded(Workload):
     bytes_per_event = 8.0
     scaling = "strong"
 
-    def __init__(self, torch, be, rank, world, device, gather=False, rate=0.01):
+    def __init__(self, torch, be, rank, world, device, gather=False, rate=0.01, emulate_world=0):
         from brainevent_b200 import dist as bd
+        self.emulate = emulate_world      # (profiling) rank 0's window of an N-GPU run on ONE GPU
+        if emulate_world:
+            world, rank = emulate_world, 0
         self.world, n = world, 1_000_000
         self.gather = gather
         self.dominant_kernel = "jit_mv_gather_kernel" if gather else "jit_mv_scatter_kernel"
@@ -579,7 +582,11 @@ class Jitc1MSharded(Workload):
         self.n_local = hi - lo
         self.pool = spike_pool(torch, self.n_local, rate, 5 + rank, device)       # spikes of the neurons I own
         self.x = None
-        if world > 1 and os.environ.get("BE_B200_EXCHANGE", DEFAULT_EXCHANGE) == "p2p":
+        if emulate_world:
+            self.peers = bd.P2PSpikeExchange.emulate(n, world, device)
+            self.x = self.peers[0]
+            self.peer_pools = [spike_pool(torch, b[1] - b[0], rate, 5 + r, device) for r, b in enumerate(bounds)]
+        elif world > 1 and os.environ.get("BE_B200_EXCHANGE", DEFAULT_EXCHANGE) == "p2p":
             try:
                 self.x = bd.P2PSpikeExchange(n, device=device)
             except Exception as e:  # pragma: no cover
@@ -600,6 +607,9 @@ class Jitc1MSharded(Workload):
                                    "(BASELINE configs[3]; strong scaling)"}
 
     def timestep(self, t):
+        if self.emulate:
+            for r in range(1, self.world):
+                self.peers[r].publish_only(self.peer_pools[r][t % POOL])
         return self.proj.step(self.pool[t % POOL])
 
     def total_events_per_timestep(self):
@@ -1005,7 +1015,7 @@ def main():
     elif args.workload == "jitc_1m_gather":
         wl = Jitc1M(torch, be, device, corder=False)
     elif args.workload in ("jitc_1m_sharded", "jitc_1m_sharded_gather"):
-        wl = Jitc1MSharded(torch, be, rank, world, device, gather=args.workload.endswith("gather"))
+        wl = Jitc1MSharded(torch, be, rank, world, device, gather=args.workload.endswith("gather"), emulate_world=args.emulate_world)
     else:
         wl = Jitc1M(torch, be, device, corder=True)
 

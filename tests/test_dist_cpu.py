@@ -83,3 +83,41 @@ def test_partition_csr_preserves_everything():
                           for ip, ix, d, (lo, hi) in shards])
     np.testing.assert_allclose(got, full, rtol=1e-6, atol=1e-6)
     assert sum(ix.size for _, ix, _, _ in shards) == c["indices"].size
+
+
+def test_c5_generator_shards_union_is_the_single_gpu_matrix():
+    """bench.py's SURVEY 8(d) generator: every rank draws the same chunk stream and keeps its post block; the union of
+    the ragged CSR shards is the FixedNumPerPre matrix a single GPU builds (strong scaling compares the same network)."""
+    import bench
+    old = bench.C5_CHUNK_ROWS
+    bench.C5_CHUNK_ROWS = 128
+    try:
+        n, conn = 1000, 12
+        idx, w = bench.build_c5_ell(torch, "cpu", n, conn)
+        assert idx.shape == (n, conn) and int(idx.min()) >= 0 and int(idx.max()) < n
+        total = 0
+        for lo, hi in bd.post_block_bounds(n, 3):
+            ip, ix, ww, counts = bench.build_c5_shard(torch, "cpu", n, conn, lo, hi)
+            m = (idx >= lo) & (idx < hi)
+            assert torch.equal(ix, idx[m] - lo) and torch.equal(ww, w[m]) and torch.equal(counts, m.sum(1))
+            assert ip.dtype == torch.int32 and int(ip[-1]) == ix.numel()
+            # the shard's product equals the block of the unsharded product (oracle on both sides)
+            v = cases.spikes(9, n, 0.1)
+            full = O.binary_fcnmv(w.numpy(), idx.numpy(), v, shape=(n, n), transpose=True)
+            part = O.binary_csrmv(ww.numpy(), ix.numpy(), ip.numpy(), v, shape=(n, hi - lo), transpose=True)
+            np.testing.assert_allclose(part, full[lo:hi], rtol=1e-6, atol=1e-6)
+            total += ix.numel()
+        assert total == n * conn
+    finally:
+        bench.C5_CHUNK_ROWS = old
+
+
+def test_sharded_projection_refuses_mismatched_layouts():
+    """the exchange and the projection must agree on the neuron count (checked before any device work)"""
+    x = bd.SpikeExchange(4096, device="cpu", world=2, rank=1)
+    assert x.local == (2048, 4096) and x.words_per_rank == 64
+    with pytest.raises(AssertionError):
+        bd.PostShardedProjection("csr", 4000, 4096, x, data=None, indices=None, indptr=None)
+    p = bd.PostShardedProjection("csr", 4096, 4096, x, data=None, indices=None, indptr=None)
+    with pytest.raises(AssertionError):
+        p.pack_local(torch.zeros(100, dtype=torch.bool))
