@@ -264,8 +264,6 @@ class PostShardedProjection:
         self._h = None
         self._jit_dev = None
         if isinstance(exchange, P2PSpikeExchange):
-            assert post_block_bounds(n_post, exchange.world) == exchange.bounds or kind == "jitc" or n_post == n_pre, \
-                "post blocks must follow the exchange's neuron blocks"
             self._h = self._make_handle()
 
     # ---- C object ---------------------------------------------------------------------------------

@@ -145,3 +145,37 @@ def test_compact_same_id_set(be, n):
     k = int(rcnt.item())
     assert int(cnt.reshape(-1)[0].item()) == k
     assert torch.equal(ids[:k], torch.sort(rids[:k]).values)     # the reference's GPU order is unspecified (F7)
+
+
+# ---- the BASELINE configs at FULL size, element by element against the reference's own CUDA kernels (VERDICT r1:
+# test_gpu_parity checks C3 / C5 at full size by checksum and linearity only; here every output element is compared) ----
+@needs("csrmm_hybrid")
+def test_baseline_c3_spmm_full_size_vs_reference_cuda(be):
+    n, nnz, batch = 1_000_000, 100, 64
+    g = _g(31)
+    indptr = torch.arange(0, (n + 1) * nnz, nnz, device="cuda", dtype=torch.int32)
+    indices = torch.randint(0, n, (n * nnz,), device="cuda", dtype=torch.int32, generator=g)
+    w = torch.rand(n * nnz, device="cuda", generator=g)
+    B = torch.rand((n, batch), device="cuda", generator=g) < 0.01
+    ours = be.binary_csrmm(w, indices, indptr, B, shape=(n, n), transpose=True)            # logical [n, batch]
+    ref = R.binary_csrmm_t_hybrid(w, indices, indptr, B, n, R.HybridWorkspace(indptr))      # physical [batch, n]
+    _close(ours, ref.t(), terms=nnz * 0.01 * 64)
+    assert float(ref.abs().max()) > 1.0
+
+
+@needs("fcnmv")
+def test_baseline_c5_shard_full_size_vs_reference_cuda(be):
+    """one GPU's ELL shard of the 10 M x 1000 network over 8 GPUs (10 M pre rows x 125 local targets)"""
+    n_total, n_local, conn = 10_000_128, 1_250_016, 125
+    g = _g(32)
+    idx = torch.randint(0, n_local, (n_total, conn), device="cuda", dtype=torch.int32, generator=g)
+    w = torch.rand((n_total, conn), device="cuda", generator=g)
+    spk = torch.rand(n_total, device="cuda", generator=g) < 0.01
+    ours = be.binary_fcnmv(w, idx, spk, shape=(n_total, n_local), transpose=True)
+    ref = R.binary_fcnmv_scatter(w, idx, spk, n_local)
+    _close(ours, ref, terms=10.0)
+    # and the same shard through the sharded object (world 1: pack + fused exchange/scatter kernels)
+    from brainevent_b200 import dist as bd
+    x = bd.P2PSpikeExchange(n_total, world=1, rank=0)
+    proj = bd.PostShardedProjection("fcn", n_total, n_local, x, weights=w, indices=idx)     # feed-forward: posts != pres
+    _close(proj.step(spk), ref, terms=10.0)
