@@ -9,7 +9,7 @@ import subprocess
 import threading
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libbrainevent_b200.so")
+LIB_PATH = os.environ.get("BE_B200_LIBPATH", os.path.join(_HERE, "libbrainevent_b200.so"))   # the env override serves A/B builds only
 CSRC = os.path.join(_HERE, "csrc")
 
 # dtype / event-kind codes (include/brainevent_b200.h)

@@ -146,6 +146,22 @@ __device__ __forceinline__ T warp_sum(T v) {
 }
 
 // streaming 128-bit loads that do not pollute L1 (connectivity is read once per step)
+#ifdef BE_STREAM_EVICT_FIRST
+// experiment: connectivity streams marked evict-first in L2 so that they do not displace the L2-resident output
+// tile the reductions land in (make EXTRA=-DBE_STREAM_EVICT_FIRST)
+__device__ __forceinline__ uint64_t l2_evict_first() {
+    uint64_t p;
+    asm("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+__device__ __forceinline__ int4 ldg_stream(const int4* p) {
+    int4 r;
+    asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v4.s32 {%0,%1,%2,%3}, [%4], %5;"
+                 : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
+                 : "l"(p), "l"(l2_evict_first()));
+    return r;
+}
+#else
 __device__ __forceinline__ int4 ldg_stream(const int4* p) {
     int4 r;
     asm volatile("ld.global.nc.L1::no_allocate.v4.s32 {%0,%1,%2,%3}, [%4];"
@@ -153,6 +169,7 @@ __device__ __forceinline__ int4 ldg_stream(const int4* p) {
                  : "l"(p));
     return r;
 }
+#endif
 __device__ __forceinline__ int2 ldg_stream(const int2* p) {
     int2 r;
     asm volatile("ld.global.nc.L1::no_allocate.v2.s32 {%0,%1}, [%2];"

@@ -11,8 +11,11 @@ cap() {   # tag kernel-regex skip bench-args...
   local TAG=$1 KRE=$2 SKIP=$3; shift 3
   local CMD="python bench.py $COMMON $*"
   if $CMD > gpurun_out/${P}_${TAG}_plain.log 2>&1; then
-    ncu --set full --clock-control none --import-source on -k regex:${KRE} -s ${SKIP} -c 3 -o gpurun_out/${P}_${TAG}_prof -f $CMD > gpurun_out/${P}_${TAG}_ncu.log 2>&1
-    echo "$TAG: $(tail -1 gpurun_out/${P}_${TAG}_ncu.log | cut -c1-120)"
+    ncu --set full --clock-control none -k regex:${KRE} -s ${SKIP} -c 3 -o gpurun_out/${P}_${TAG}_prof -f $CMD > gpurun_out/${P}_${TAG}_ncu.log 2>&1
+    # gpurun brings back at most 64 MiB: keep the raw metric table (text), drop the report
+    ncu -i gpurun_out/${P}_${TAG}_prof.ncu-rep --page raw --csv > gpurun_out/${P}_${TAG}_raw.csv 2>/dev/null
+    rm -f gpurun_out/${P}_${TAG}_prof.ncu-rep gpurun_out/${P}_${TAG}_plain.log
+    echo "$TAG: $(tail -1 gpurun_out/${P}_${TAG}_ncu.log | cut -c1-100) raw=$(wc -c < gpurun_out/${P}_${TAG}_raw.csv)"
   else
     echo "$TAG: plain run failed"; tail -3 gpurun_out/${P}_${TAG}_plain.log
   fi
@@ -38,4 +41,4 @@ for N in 2 4 8; do
   cap jitc_scatter_w$N jit_mv_scatter 8 --workload jitc_1m_sharded --emulate-world $N
   cap jitc_gather_w$N jit_mv_gather 4 --workload jitc_1m_sharded_gather --emulate-world $N
 done
-ls gpurun_out/${P}_*_prof.ncu-rep | wc -l
+ls gpurun_out/${P}_*_raw.csv | wc -l; du -sh gpurun_out

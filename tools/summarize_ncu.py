@@ -35,8 +35,11 @@ if rows:
         f.write(f"{sum(v) / tot:6.1%}  n={len(v):4d}  avg={sum(v) / len(v) / 1e3:9.2f} us  {k[:110]}\n")
   print(open(f"{out_dir}/{tag}_launches.txt").read())
 
-raw = subprocess.run(["ncu", "-i", f"{src}/{tag}_prof.ncu-rep", "--page", "raw", "--csv"],
-                     capture_output=True, text=True).stdout
+if os.path.exists(f"{src}/{tag}_raw.csv"):       # converted on the GPU box (tools/ncu_all.sh): the reports exceed gpurun's 64 MiB
+    raw = open(f"{src}/{tag}_raw.csv").read()
+else:
+    raw = subprocess.run(["ncu", "-i", f"{src}/{tag}_prof.ncu-rep", "--page", "raw", "--csv"],
+                         capture_output=True, text=True).stdout
 rows = list(csv.reader(raw.splitlines()))
 hdr, units, data = rows[0], rows[1], rows[2:]
 want = ["Kernel Name", "launch__grid_size", "launch__block_size", "launch__registers_per_thread",
@@ -52,7 +55,7 @@ want = ["Kernel Name", "launch__grid_size", "launch__block_size", "launch__regis
         "smsp__average_warps_issue_stalled_lg_throttle_per_issue_active.ratio",
         "smsp__average_warps_issue_stalled_long_scoreboard_per_issue_active.ratio"]
 with open(f"{out_dir}/{tag}_full.txt", "w") as f:
-    f.write(f"# ncu --set full --clock-control none --import-source on; source gpurun_out/{tag}_prof.ncu-rep\n")
+    f.write(f"# ncu --set full --clock-control none, 3 launches; source gpurun_out/{tag}_prof.ncu-rep (raw metric page)\n")
     for w in want:
         if w in hdr:
             i = hdr.index(w)
