@@ -616,6 +616,95 @@ class Jitc1MSharded(Workload):
         return self._total
 
 
+class DenseSharded(Workload):
+    """SURVEY 8(e) dense row: BinaryArray[k] @ W[k, m] (binary_densemv, transpose=True), W split by post columns over
+    the ranks (each rank holds W[:, lo:hi]) with the spike exchange; strong scaling (the matrix is fixed, every rank
+    draws its own column block from a generator seeded by the block's first column)."""
+    name = "dense_mv_sharded"
+    bytes_per_event = 4.0
+    scaling = "strong"
+    dominant_kernel = "dense_mv_t_kernel"
+
+    def __init__(self, torch, be, rank, world, device, n=65_536, rate=0.01, emulate_world=0):
+        from brainevent_b200 import dist as bd
+        self.emulate = emulate_world
+        if emulate_world:
+            world, rank = emulate_world, 0
+        self.world, self.rank, self.n = world, rank, n
+        bounds = bd.post_block_bounds(n, world)
+        lo, hi = bounds[rank]
+        self.lo, self.hi, self.n_local = lo, hi, hi - lo
+        self.pool = spike_pool(torch, self.n_local, rate, 11 + rank, device)
+        self.x = None
+        if emulate_world:
+            self.peers = bd.P2PSpikeExchange.emulate(n, world, device)
+            self.x = self.peers[0]
+            self.peer_pools = [spike_pool(torch, b[1] - b[0], rate, 11 + r, device) for r, b in enumerate(bounds)]
+        elif world > 1 and os.environ.get("BE_B200_EXCHANGE", DEFAULT_EXCHANGE) == "p2p":
+            try:
+                self.x = bd.P2PSpikeExchange(n, device=device)
+            except Exception as e:  # pragma: no cover
+                sys.stderr.write(f"[bench] P2P exchange unavailable ({type(e).__name__}: {e}); using NCCL\n")
+        if self.x is None:
+            self.x = bd.SpikeExchange(n, device=device)
+        g = torch.Generator(device=device).manual_seed(7_000_003 + lo)
+        self.W = torch.randn((n, self.n_local), device=device, generator=g)
+        self.proj = bd.PostShardedProjection("dense", n, n, self.x, W=self.W)
+        act = sum(float(spike_pool(torch, b[1] - b[0], rate, 11 + r, device).sum(1).double().mean().item())
+                  for r, b in enumerate(bounds))
+        self.events_per_timestep = act * self.n_local                              # this rank's share
+        self._total = act * n
+        self.extra_bytes_per_timestep = n / 8.0 + 4.0 * self.n_local
+        self.launches_per_timestep = 3 if world > 1 else 2
+        self.config = {"workload": f"BinaryArray[{n}] @ dense W[{n},{n}] fp32 (binary_densemv transpose=True), {rate:.0%} spikes, "
+                                   f"W split by post columns over {world} GPU(s) with the spike exchange (SURVEY 8e; strong scaling)"}
+
+    def timestep(self, t):
+        if self.emulate:
+            for r in range(1, self.world):
+                self.peers[r].publish_only(self.peer_pools[r][t % POOL])
+        return self.proj.step(self.pool[t % POOL])
+
+    def total_events_per_timestep(self):
+        return self._total
+
+
+def parity_sharded_other(torch, dist, be, w2):
+    """N > 1, before the JITC / dense sharded lines are timed: two timesteps of the measured step against NCCL
+    all-gather of the bit-packed spikes + the UNSHARDED operator on the global shape (JITC: the 1 M x 1 M matrix
+    without any window, sliced to this rank's post block afterwards -- this also proves the shard windows are
+    index-for-index the single-GPU matrix; dense: binary_densemv on this rank's column block)."""
+    from brainevent_b200 import dist as bd
+    dev = w2.pool.device
+    n = w2.proj.n_pre
+    lo, hi = w2.proj.lo, w2.proj.hi
+    xn = bd.SpikeExchange(n, device=dev)
+    packer = bd.PostShardedProjection(w2.proj.kind, n, n, xn, **w2.proj.conn)
+    max_err, max_ref = 0.0, 0.0
+    for t in range(2):
+        mine = w2.pool[t]
+        out = w2.proj.step(mine).clone()
+        words = xn.exchange(packer.pack_local(mine)).clone()
+        ev = be.BitPackedBinary(packed=words, shape=(n,))
+        if isinstance(w2, Jitc1MSharded):
+            full = be.JITCNormalR((1.0, 0.1, 1e-3, 123), shape=(n, n), corder=not w2.gather)
+            ref = (ev @ full)[lo:hi]
+        else:
+            ref = be.binary_densemv(w2.W, ev, transpose=True)
+        max_err = max(max_err, float((out - ref).abs().max().item()))
+        max_ref = max(max_ref, float(ref.abs().max().item()))
+    timed_out = bool(w2.x.timed_out()) if hasattr(w2.x, "timed_out") else False
+    ok = max_err <= 1e-5 * max(max_ref, 1.0) + 2e-5 and not timed_out
+    v = torch.tensor([max_err, 0.0 if ok else 1.0], device=dev, dtype=torch.float64)
+    dist.all_reduce(v, op=dist.ReduceOp.MAX)
+    res = {"checked": True, "ok": bool(v[1].item() == 0.0), "timesteps": 2, "max_abs_err": float(v[0].item()),
+           "against": "NCCL all_gather of bit-packed spikes + the unsharded operator, sliced to this rank's post block"}
+    del packer, xn
+    if not res["ok"]:
+        raise RuntimeError(f"multi-GPU parity check failed ({w2.name}): {res}")
+    return res
+
+
 # ------------------------------------------------------------------------------------------------
 # timing helpers
 # ------------------------------------------------------------------------------------------------
@@ -700,6 +789,8 @@ def traffic_key(wl):
         k += ("_gather" if wl.gather else "_scatter") + ("_homo" if wl.weights.numel() == 1 else "_hetero")
     elif isinstance(wl, Jitc1MSharded):
         k += ("_gather" if wl.gather else "_scatter") + f"_w{wl.world}"
+    elif isinstance(wl, DenseSharded):
+        k += f"_w{wl.world}"
     return k
 
 
@@ -755,7 +846,7 @@ def run_reference(args):
     K, W = args.steps, args.warmup
     world = max(args.gpus, 1)
     n_total = FCN_NEURONS_PER_GPU * world
-    reps_per_step = 4
+    reps_per_step = 40      # ~0.15 s of CPU work per step
     times, sample = cpu_fcn_sample(n_post=n_total, reps=(K + W) * reps_per_step)
     times = times[W * reps_per_step:]
     total_t = sum(t for t, _ in times)
@@ -959,7 +1050,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="fcn", choices=["fcn", "fcn_full", "coba", "cuba_jitc", "cuba_jitc_gather", "csr_spmm", "jitc_1m",
                                                            "csr_gather", "csr_gather_hetero", "csr_scatter", "dense_mm", "jitc_1m_gather",
-                                                           "jitc_1m_sharded", "jitc_1m_sharded_gather"])
+                                                           "jitc_1m_sharded", "jitc_1m_sharded_gather", "dense_sharded"])
     ap.add_argument("--timesteps", type=int, default=100, help="simulated timesteps per step")
     ap.add_argument("--no-extra", action="store_true", help="skip the strong-scaling leg and the other BASELINE configs")
     ap.add_argument("--no-graph", action="store_true")
@@ -1016,6 +1107,8 @@ def main():
         wl = Jitc1M(torch, be, device, corder=False)
     elif args.workload in ("jitc_1m_sharded", "jitc_1m_sharded_gather"):
         wl = Jitc1MSharded(torch, be, rank, world, device, gather=args.workload.endswith("gather"), emulate_world=args.emulate_world)
+    elif args.workload == "dense_sharded":
+        wl = DenseSharded(torch, be, rank, world, device, emulate_world=args.emulate_world)
     else:
         wl = Jitc1M(torch, be, device, corder=True)
 
@@ -1081,18 +1174,22 @@ def main():
         else:
             # BASELINE configs[3] at N GPUs: the fixed 1 M x 1 M JITCNormalR matrix, post-sharded (strong scaling)
             makers = (lambda: Jitc1MSharded(torch, be, rank, world, device, gather=False),
-                      lambda: Jitc1MSharded(torch, be, rank, world, device, gather=True))
+                      lambda: Jitc1MSharded(torch, be, rank, world, device, gather=True),
+                      lambda: DenseSharded(torch, be, rank, world, device))
         for make in makers:
             try:
                 w2 = make()
                 heavy = isinstance(w2, (CsrSpmm, DenseMm)) or (isinstance(w2, Jitc1M) and not w2.corder) or \
                     (isinstance(w2, Jitc1MSharded) and w2.gather)
                 T2 = 4 if heavy else 50
+                par2 = parity_sharded_other(torch, dist, be, w2) if world > 1 else None
                 r2 = measure_workload(torch, dist, L, w2, 3 if heavy else 5, 3, T2, world, peak, peak_src)
                 if world > 1 and hasattr(getattr(w2, "x", None), "check"):
                     w2.x.check()
                 entry = {"workload": w2.config["workload"], "value": r2["value"], "unit": "events/s",
                          "ms_per_timestep": r2["ms_per_step"] / T2, "cuda_graph": r2["graph"], "roofline": r2["roofline"]}
+                if par2 is not None:
+                    entry["parity"] = par2
                 if world == 1:
                     ref_us = reference_cuda_us(torch, w2, T2 if heavy else 16)
                     entry["reference_cuda_us"] = ref_us
@@ -1114,7 +1211,7 @@ def main():
     # ---- CPU baseline (rank 0, N = 1 only) ----------------------------------------------------
     cpu = None
     if world == 1 and not args.no_cpu and args.workload == "fcn":
-        times, sample = cpu_fcn_sample(reps=12)
+        times, sample = cpu_fcn_sample(reps=3000)      # ~10 s of CPU work
         tt, ee = sum(t for t, _ in times), sum(e for _, e in times)
         cpu = {"value": ee / tt, "unit": "events/s", "cores": 1, "kind": "port", "sample": sample}
 

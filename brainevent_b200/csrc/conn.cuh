@@ -12,15 +12,24 @@ namespace be {
 // ------------------------------------------------------------------------------------------
 template <typename PT>
 struct CsrRows {
+    using ptr_t = PT;
     const PT* indptr;
     __device__ __forceinline__ void get(int64_t r, int64_t& s, int64_t& e) const {
         s = (int64_t)__ldg(indptr + r);
         e = (int64_t)__ldg(indptr + r + 1);
     }
+    // the extent in the stored width: callers that prefetch a row's extent keep the raw values and widen them
+    // where they are used, so no instruction consumes the load right behind it
+    __device__ __forceinline__ void get_raw(int64_t r, PT& s, PT& e) const {
+        s = __ldg(indptr + r);
+        e = __ldg(indptr + r + 1);
+    }
     __device__ __forceinline__ int64_t total(int64_t n_rows) const { return (int64_t)__ldg(indptr + n_rows); }
 };
 struct FcnRows {
+    using ptr_t = int64_t;
     int64_t n_conn;
+    __device__ __forceinline__ void get_raw(int64_t r, int64_t& s, int64_t& e) const { get(r, s, e); }
     __device__ __forceinline__ void get(int64_t r, int64_t& s, int64_t& e) const {
         s = r * n_conn;
         e = s + n_conn;
@@ -116,6 +125,7 @@ struct ConnArgs {
     const void* perm;
     int perm_kind;  // 0 none, 1 int32, 2 int64
     double avg_row;  // mean synapses per row (launch-shape heuristic only)
+    int64_t nse = 0; // stored entries (0 = unknown: bulk-copy paths that need the array's end stay off)
 };
 
 // type-erased row structure so the gather TU can be entered without templates

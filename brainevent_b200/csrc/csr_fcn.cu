@@ -371,7 +371,7 @@ static int csr_entry(const void* weights, int w_dtype, int homo, const int32_t* 
     BE_REQUIRE(weights && indptr && out, "csr: NULL pointer");
     BE_REQUIRE(indices || nse == 0, "csr: indices is NULL");
     ConnArgs c{weights, w_dtype, homo, indices, homo ? nullptr : perm,
-               (homo || !perm) ? 0 : (perm_is64 ? 2 : 1), m > 0 ? (double)nse / (double)m : 0.0};
+               (homo || !perm) ? 0 : (perm_is64 ? 2 : 1), m > 0 ? (double)nse / (double)m : 0.0, nse};
     const int64_t n_src = transpose ? m : k, n_out = transpose ? k : m;
     BE_DISPATCH_WT(w_dtype, T, {
         if (indptr_is64) {
@@ -419,7 +419,7 @@ extern "C" int be_b200_binary_csrmv_auto(const void* weights, int w_dtype, int h
     ev.sel_thr = (int)std::min<double>((double)rate_threshold * (double)m, 2147483647.0);
     ConnArgs cs{weights, w_dtype, homo, indices, nullptr, 0, m > 0 ? (double)nse / (double)m : 0.0};
     ConnArgs cg{weights, w_dtype, homo, csc_indices, homo ? nullptr : perm, homo ? 0 : (indptr_is64 ? 2 : 1),
-                k > 0 ? (double)nse / (double)k : 0.0};
+                k > 0 ? (double)nse / (double)k : 0.0, nse};
     RowsDesc rg{indptr_is64 ? 1 : 0, csc_indptr, 0};
     BE_DISPATCH_WT(w_dtype, T, {
         if (indptr_is64) {

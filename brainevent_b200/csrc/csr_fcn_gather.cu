@@ -27,10 +27,21 @@ __global__ void __launch_bounds__(SMEM ? 1024 : 256) gather_mv_kernel(Rows rows,
                                                                       int64_t n_words, int64_t n_rows,
                                                                       T* __restrict__ out,
                                                                       const int* __restrict__ sel_n_active, int sel_thr,
-                                                                      const uint8_t* __restrict__ raw_bool, int64_t raw_n) {
+                                                                      const uint8_t* __restrict__ raw_bool, int64_t raw_n,
+                                                                      int pend_off_words) {
     using A = typename Acc<T>::type;
     if (sel_thr >= 0 && *sel_n_active <= sel_thr) return;   // the scatter variant owns this call
     extern __shared__ __align__(16) uint32_t s_bits[];
+    // fp32 weights of the hits travel global -> shared memory by 4-byte cp.async into per-lane slots and are summed
+    // when the lane's NEXT row is done: ncu (r2, source page) had 36 % of the hetero kernel's samples waiting on the
+    // weight quads it had just requested.  pend_off_words == 0: no room beside the spike bits, load in place.
+    constexpr int NP = 4;                                   // deferred hits per lane and row; more are summed in place
+    constexpr bool ASYNCW_T = SMEM && VEC && !HOMO && PERM == 0 && std::is_same<T, float>::value;
+    const bool asyncw = ASYNCW_T && pend_off_words > 0;
+    float* const s_pend = reinterpret_cast<float*>(s_bits + pend_off_words);    // [2][blockDim.x][NP]
+    A pend_acc = A(0);
+    int pend_n = 0, pend_buf = 0;
+    int64_t pend_row = -1;
     // the first row's extent (and the homogeneous weight) are requested before the spike vector is
     // staged, so their latency overlaps the staging instead of following it
     const A w0 = HOMO ? to_acc<T>(__ldg(weights)) : A(0);
@@ -39,8 +50,8 @@ __global__ void __launch_bounds__(SMEM ? 1024 : 256) gather_mv_kernel(Rows rows,
     const int64_t row_stride = (int64_t)gridDim.x * GROUPS;
     const int64_t row_iters = ceil_div(n_rows, row_stride);
     int64_t r = (int64_t)blockIdx.x * GROUPS + g;
-    int64_t s_n = 0, e_n = 0;
-    if (r < n_rows) rows.get(r, s_n, e_n);
+    typename Rows::ptr_t s_n = 0, e_n = 0;      // raw (stored-width) extent of the next row, widened where it is used:
+    if (r < n_rows) rows.get_raw(r, s_n, e_n);  // no instruction consumes the load right behind it (ncu: 16 % of the samples)
     if (SMEM && raw_bool != nullptr) {
         // small bool vector: every CTA packs the raw bytes itself (no separate pack kernel)
         for (int64_t w = threadIdx.x; w < n_words; w += blockDim.x) {
@@ -103,10 +114,10 @@ __global__ void __launch_bounds__(SMEM ? 1024 : 256) gather_mv_kernel(Rows rows,
     };
     for (int64_t it = 0; it < row_iters; ++it, r += row_stride) {
         A acc = A(0);
-        int cnt = 0;
-        const int64_t s = s_n, e = e_n;
+        int cnt = 0, nh = 0;
+        const int64_t s = (int64_t)s_n, e = (int64_t)e_n;
         const bool live = r < n_rows;
-        if (r + row_stride < n_rows) rows.get(r + row_stride, s_n, e_n);   // next row's extent in flight
+        if (r + row_stride < n_rows) rows.get_raw(r + row_stride, s_n, e_n);   // next row's extent in flight
         if (live) {
             if (VEC) {
                 int64_t a = (s + 3) & ~(int64_t)3;
@@ -135,7 +146,22 @@ __global__ void __launch_bounds__(SMEM ? 1024 : 256) gather_mv_kernel(Rows rows,
                             hm |= ((uint32_t)bit(ix[u].x) | ((uint32_t)bit(ix[u].y) << 1) | ((uint32_t)bit(ix[u].z) << 2) |
                                    ((uint32_t)bit(ix[u].w) << 3)) << (4 * u);
                         }
-                        if (hm) {
+                        if (hm && asyncw) {
+                            // one 4-byte async copy per hit into this lane's slots of the row's buffer
+                            const uint32_t pdst = (uint32_t)__cvta_generic_to_shared(
+                                s_pend + ((size_t)(it & 1) * blockDim.x + threadIdx.x) * NP);
+                            while (hm) {
+                                const int b = __ffs(hm) - 1;
+                                hm &= hm - 1;
+                                const float* wp = (const float*)weights + j0 + (int64_t)(b >> 2) * LPR * 4 + (b & 3);
+                                if (nh < NP) {
+                                    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(pdst + 4u * (uint32_t)nh), "l"(wp) : "memory");
+                                    ++nh;
+                                } else {
+                                    acc += (A)__ldg(wp);
+                                }
+                            }
+                        } else if (hm) {
                             int4 wq[U];
 #pragma unroll
                             for (int u = 0; u < U; ++u) {
@@ -181,6 +207,21 @@ __global__ void __launch_bounds__(SMEM ? 1024 : 256) gather_mv_kernel(Rows rows,
                     }
             }
         }
+        if (ASYNCW_T && asyncw) {
+            // this row's copies form one group; the PREVIOUS row's group is complete once at most one is pending
+            asm volatile("cp.async.commit_group;" ::: "memory");
+            asm volatile("cp.async.wait_group 1;" ::: "memory");
+            A tot = pend_acc;
+            const float* pw = s_pend + ((size_t)pend_buf * blockDim.x + threadIdx.x) * NP;
+#pragma unroll
+            for (int q = 0; q < NP; ++q)
+                if (q < pend_n) tot += (A)pw[q];
+#pragma unroll
+            for (int o = LPR / 2; o > 0; o >>= 1) tot += __shfl_xor_sync(0xffffffffu, tot, o);
+            if (gl == 0 && pend_row >= 0) out[pend_row] = from_acc<T>(tot);
+            pend_acc = acc; pend_n = nh; pend_buf = (int)(it & 1); pend_row = live ? r : -1;
+            continue;
+        }
         if (HOMO) {
 #pragma unroll
             for (int o = LPR / 2; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
@@ -190,6 +231,17 @@ __global__ void __launch_bounds__(SMEM ? 1024 : 256) gather_mv_kernel(Rows rows,
             for (int o = LPR / 2; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
         }
         if (gl == 0 && live) out[r] = from_acc<T>(acc);
+    }
+    if (ASYNCW_T && asyncw) {                      // the last row of every lane group
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+        A tot = pend_acc;
+        const float* pw = s_pend + ((size_t)pend_buf * blockDim.x + threadIdx.x) * NP;
+#pragma unroll
+        for (int q = 0; q < NP; ++q)
+            if (q < pend_n) tot += (A)pw[q];
+#pragma unroll
+        for (int o = LPR / 2; o > 0; o >>= 1) tot += __shfl_xor_sync(0xffffffffu, tot, o);
+        if (gl == 0 && pend_row >= 0) out[pend_row] = from_acc<T>(tot);
     }
 }
 
@@ -280,13 +332,19 @@ static int launch_gather_mv(const Rows& rows, const ConnArgs& c, const Events& e
         // handful of 1024-thread ones -- the call is launch/latency-bound there
         const int threads = (n_rows * lpr <= (int64_t)kNumSM * 256) ? 256 : 1024;
         const int blocks = (int)std::min<int64_t>(kNumSM, ceil_div(n_rows, threads / lpr));
+        // deferred-weight slots (fp32 hetero): 2 buffers x threads x 4 floats behind the spike bits, if they fit
+        const bool defer_ok = !HOMO && PERM == 0 && std::is_same<T, float>::value && getenv("BE_B200_GATHER_DEFER_W") == nullptr;
+        const size_t bits_pad = ((size_t)n_words + 3) & ~(size_t)3;
+        size_t pend_bytes = defer_ok ? (bits_pad - (size_t)n_words) * 4 + (size_t)threads * 2 * 4 * 4 : 0;
+        if (smem + pend_bytes > (227u << 10) - 1024) pend_bytes = 0;
+        const int pend_off = pend_bytes ? (int)bits_pad : 0;
 #define BE_GAS(LPR)                                                                                           \
         do {                                                                                                  \
             BE_CUDA(cudaFuncSetAttribute(gather_mv_kernel<T, HOMO, PERM, true, LPR, true, Rows>,              \
-                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kGatherSmemMax));  \
-            gather_mv_kernel<T, HOMO, PERM, true, LPR, true, Rows><<<blocks, threads, smem, s>>>(                \
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(227u << 10) - 1024));  \
+            gather_mv_kernel<T, HOMO, PERM, true, LPR, true, Rows><<<blocks, threads, smem + pend_bytes, s>>>(   \
                 rows, c.indices, (const T*)c.weights, c.perm, evl.packed, n_words, n_rows, out, evl.n_active, evl.sel_thr, \
-                evl.raw_bool, evl.raw_n);                                                                     \
+                evl.raw_bool, evl.raw_n, pend_off);                                                           \
         } while (0)
         switch (lpr) { case 4: BE_GAS(4); break; case 8: BE_GAS(8); break; case 16: BE_GAS(16); break; default: BE_GAS(32); }
 #undef BE_GAS
@@ -295,7 +353,7 @@ static int launch_gather_mv(const Rows& rows, const ConnArgs& c, const Events& e
 #define BE_GA(VEC, LPR)                                                                      \
         gather_mv_kernel<T, HOMO, PERM, VEC, LPR, false, Rows><<<blocks, 256, 0, s>>>(       \
             rows, c.indices, (const T*)c.weights, c.perm, evl.packed, n_words, n_rows, out, evl.n_active, evl.sel_thr, \
-            nullptr, 0)
+            nullptr, 0, 0)
 #define BE_GA2(VEC) switch (lpr) { case 4: BE_GA(VEC, 4); break; case 8: BE_GA(VEC, 8); break; \
                                    case 16: BE_GA(VEC, 16); break; default: BE_GA(VEC, 32); }
         if (vec) { BE_GA2(true) } else { BE_GA2(false) }

@@ -111,7 +111,7 @@ __device__ __forceinline__ void split3(float a, float b, uint32_t& hi, uint32_t&
 template <int TC_BN>
 __global__ void __launch_bounds__(TC_THREADS, (TC_BN == 64) ? 3 : 2)
 dense_mm_t_tc_kernel(const float* __restrict__ W, int64_t k, int64_t m, const uint32_t* __restrict__ packed, int wpr,
-                     int64_t n, float* __restrict__ out, int kb_per_split, int split_k, int lane_map) {
+                     int64_t n, float* __restrict__ out, int kb_per_split, int split_k, int lane_map, int pf_dist) {
     extern __shared__ __align__(1024) uint8_t smem[];
     __shared__ uint64_t empty_bar[TC_STAGES];
     __shared__ uint64_t done_bar;
@@ -151,8 +151,14 @@ dense_mm_t_tc_kernel(const float* __restrict__ W, int64_t k, int64_t m, const ui
     __shared__ uint16_t s_off[TC_CHUNK_PASSES * (TC_THREADS / 32)];
     __shared__ int s_total;
     constexpr int B_CELLS = TC_BK * (TC_BN / 8) / TC_THREADS;      // (k, n-octet) cells per thread
-    const int k8_l = (lane_map & 1) ? (lane & 7) : (lane >> 2);
-    const int quad_l = (lane_map & 1) ? (lane >> 3) : (lane & 3);
+    // lane -> (source slot k8, column quad) of a patch.  Map 2 (default): bit 0 = quad parity, bits 1-3 = k8, bit 4 = quad / 2.
+    // A half-warp then owns all 8 slots x 2 quads of ONE core-matrix column pair, so its 64-bit plane stores cover
+    // 128 distinct bytes (16 bank pairs) -- with map 0 (k8 = lane / 4) a half-warp held slots 0-3 of two core matrices,
+    // which sit on the same banks: every plane store took two wavefronts (ncu r2_dense: 13.9 M store bank conflicts
+    // in 28.3 M store wavefronts, LSU data pipe 71 % busy).  Global side: a quarter-warp reads 4 rows x 32 B = 4 full
+    // sectors, as before (2 rows x 64 B).
+    const int k8_l = lane_map == 2 ? ((lane >> 1) & 7) : (lane_map == 1 ? (lane & 7) : (lane >> 2));
+    const int quad_l = lane_map == 2 ? ((lane & 1) | ((lane >> 4) << 1)) : (lane_map == 1 ? (lane >> 3) : (lane & 3));
     // with TC_ITEMS == 4 the four patches of a warp share their source slot (kk = warp / 2) and sit
     // 16 columns apart, so one list lookup and one 64-bit multiply address all four 128-bit loads
     static_assert(TC_ITEMS == 4 && TC_BK == 32 && TC_THREADS == 256, "patch mapping below assumes 4 items per warp");
@@ -181,6 +187,12 @@ dense_mm_t_tc_kernel(const float* __restrict__ W, int64_t k, int64_t m, const ui
     const bool mn_interior = (m0 + TC_BM <= m) && (n0 + TC_BN <= n);
     const int64_t row_begin = (int64_t)kb_begin * TC_BK;
     const int64_t row_end = min(k, (int64_t)kb_end * TC_BK);
+
+    // L2 prefetch of the W row segments `pf_dist` k-blocks ahead (cp.async.bulk.prefetch.L2, one 512-byte row segment
+    // per lane of one warp): the bytes in flight towards HBM then no longer depend on the registers of the 256
+    // converter threads -- their 128-bit loads find the rows in L2 (~1/3 of the DRAM latency)
+    const bool pf_ok = pf_dist > 0 && (m & 3) == 0 && ((reinterpret_cast<uintptr_t>(W) & 15u) == 0) && m0 < m;
+    const uint32_t pf_bytes = (uint32_t)(min((int64_t)TC_BM, m - m0) * 4);
 
     int n_issued = 0;      // k-blocks that actually reached the tensor core (uniform across the CTA)
     for (int64_t c_begin = row_begin; c_begin < row_end; c_begin += TC_CHUNK) {
@@ -242,6 +254,14 @@ dense_mm_t_tc_kernel(const float* __restrict__ W, int64_t k, int64_t m, const ui
         __syncthreads();
         const int n_vkb = (total + TC_BK - 1) / TC_BK;
 
+        auto prefetch_tile = [&](int vkb) {      // called by ONE warp: lane = source slot of k-block vkb
+            const uint32_t rid = s_rows[vkb * TC_BK + lane];
+            if (rid != 0xffffu)
+                asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(Wc + (int64_t)rid * m + m0), "r"(pf_bytes) : "memory");
+        };
+        if (pf_ok)
+            for (int v = 1 + warp; v < min(n_vkb, pf_dist); v += TC_THREADS / 32) prefetch_tile(v);
+
         auto load_tile = [&](int vkb, float4 (&wv)[TC_ITEMS], uint32_t (&bw)[B_CELLS]) {
             const uint16_t* rows = s_rows + vkb * TC_BK;
             if (mn_interior && (vkb + 1) * TC_BK <= total) {
@@ -281,6 +301,7 @@ dense_mm_t_tc_kernel(const float* __restrict__ W, int64_t k, int64_t m, const ui
         // the next block are always issued BEFORE the wait on the current one (two blocks in flight)
         auto step = [&](int vkb, float4 (&cur)[TC_ITEMS], uint32_t (&cur_b)[B_CELLS], float4 (&nxt)[TC_ITEMS],
                         uint32_t (&nxt_b)[B_CELLS]) {
+            if (pf_ok && vkb + pf_dist < n_vkb && warp == (vkb & 7)) prefetch_tile(vkb + pf_dist);
             if (vkb + 1 < n_vkb) load_tile(vkb + 1, nxt, nxt_b);
 
             const int stage = n_issued % TC_STAGES;
@@ -390,7 +411,9 @@ int launch_dense_mm_t_tc(const float* W, int64_t k, int64_t m, const uint32_t* p
                          float* out, cudaStream_t s) {
     if (m == 0 || n == 0) return BE_B200_OK;
     const char* lm = getenv("BE_B200_TC_LANEMAP");
-    const int lane_map = lm ? (lm[0] != '0') : 0;   // 0: row-quad lanes (measured faster), 1: half-warp per core matrix
+    const int lane_map = lm ? atoi(lm) : 2;         // 2: conflict-free plane stores (see the kernel); 0 / 1: earlier maps (A/B)
+    const char* pfe = getenv("BE_B200_TC_PREFETCH");
+    const int pf_dist = pfe ? atoi(pfe) : 0;        // k-blocks of L2 prefetch distance; measured 8 % SLOWER at every distance 2..16, off
     // widest batch tile that the batch fills: W is read once per batch tile
     const int bn = n > 128 ? 256 : (n > 64 ? 128 : 64);
     const int total_kb = (int)ceil_div(k, TC_BK);
@@ -406,7 +429,7 @@ int launch_dense_mm_t_tc(const float* W, int64_t k, int64_t m, const uint32_t* p
         dim3 grid((unsigned)ceil_div(m, TC_BM), (unsigned)split_k, (unsigned)ceil_div(n, BN));                 \
         ProfileScope prof(s);                                                                                  \
         dense_mm_t_tc_kernel<BN><<<grid, TC_THREADS, tc_smem_bytes(BN), s>>>(W, k, m, packed, wpr, n, out,     \
-                                                                            kb_per_split, split_k, lane_map); \
+                                                                            kb_per_split, split_k, lane_map, pf_dist); \
     } while (0)
     if (bn == 64) BE_TC_LAUNCH(64); else if (bn == 128) BE_TC_LAUNCH(128); else BE_TC_LAUNCH(256);
 #undef BE_TC_LAUNCH
