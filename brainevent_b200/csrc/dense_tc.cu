@@ -85,6 +85,9 @@ __device__ __forceinline__ void umma_commit(uint64_t* bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
                  : "memory");
 }
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
 __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
@@ -113,8 +116,8 @@ __global__ void __launch_bounds__(TC_THREADS, (TC_BN == 64) ? 3 : 2)
 dense_mm_t_tc_kernel(const float* __restrict__ W, int64_t k, int64_t m, const uint32_t* __restrict__ packed, int wpr,
                      int64_t n, float* __restrict__ out, int kb_per_split, int split_k, int lane_map, int pf_dist) {
     extern __shared__ __align__(1024) uint8_t smem[];
-    __shared__ uint64_t empty_bar[TC_STAGES];
-    __shared__ uint64_t done_bar;
+    __shared__ uint64_t empty_bar[TC_STAGES];     // MMAs of a stage have finished reading it (tcgen05.commit)
+    __shared__ uint64_t full_bar[TC_STAGES];      // all 8 warps have stored their part of a stage
     __shared__ uint32_t tmem_base_s;
 
     constexpr int TC_STAGE_BYTES = tc_stage_bytes(TC_BN);
@@ -128,8 +131,7 @@ dense_mm_t_tc_kernel(const float* __restrict__ W, int64_t k, int64_t m, const ui
     const int kb_end = min(total_kb, kb_begin + kb_per_split);
 
     if (tid == 0) {
-        for (int s = 0; s < TC_STAGES; ++s) mbar_init(&empty_bar[s], 1);
-        mbar_init(&done_bar, 1);
+        for (int s = 0; s < TC_STAGES; ++s) { mbar_init(&empty_bar[s], 1); mbar_init(&full_bar[s], TC_THREADS / 32); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 0) {
@@ -151,12 +153,12 @@ dense_mm_t_tc_kernel(const float* __restrict__ W, int64_t k, int64_t m, const ui
     __shared__ uint16_t s_off[TC_CHUNK_PASSES * (TC_THREADS / 32)];
     __shared__ int s_total;
     constexpr int B_CELLS = TC_BK * (TC_BN / 8) / TC_THREADS;      // (k, n-octet) cells per thread
-    // lane -> (source slot k8, column quad) of a patch.  Map 2 (default): bit 0 = quad parity, bits 1-3 = k8, bit 4 = quad / 2.
-    // A half-warp then owns all 8 slots x 2 quads of ONE core-matrix column pair, so its 64-bit plane stores cover
+    // lane -> (source slot k8, column quad) of a patch.  Map 0 (default): k8 = lane / 4, quad = lane % 4.  Map 2: bit 0 = quad
+    // parity, bits 1-3 = k8, bit 4 = quad / 2 -- a half-warp then owns all 8 slots x 2 quads of ONE core-matrix column pair, so its 64-bit plane stores cover
     // 128 distinct bytes (16 bank pairs) -- with map 0 (k8 = lane / 4) a half-warp held slots 0-3 of two core matrices,
     // which sit on the same banks: every plane store took two wavefronts (ncu r2_dense: 13.9 M store bank conflicts
     // in 28.3 M store wavefronts, LSU data pipe 71 % busy).  Global side: a quarter-warp reads 4 rows x 32 B = 4 full
-    // sectors, as before (2 rows x 64 B).
+    // sectors, as before (2 rows x 64 B).  Measured 3 % SLOWER than map 0 (profiles/r2_experiments.txt): kept as a switch only.
     const int k8_l = lane_map == 2 ? ((lane >> 1) & 7) : (lane_map == 1 ? (lane & 7) : (lane >> 2));
     const int quad_l = lane_map == 2 ? ((lane & 1) | ((lane >> 4) << 1)) : (lane_map == 1 ? (lane >> 3) : (lane & 3));
     // with TC_ITEMS == 4 the four patches of a warp share their source slot (kk = warp / 2) and sit
@@ -270,8 +272,8 @@ dense_mm_t_tc_kernel(const float* __restrict__ W, int64_t k, int64_t m, const ui
 #pragma unroll
                 for (int i = 0; i < TC_ITEMS; ++i) wv[i] = __ldg(wrow + i * 4);
 #pragma unroll
-                for (int i = 0; i < B_CELLS; ++i)
-                    bw[i] = (__ldg(pc + (int64_t)rows[b_k[i]] * wpr + b_w[i]) >> b_sh[i]) & 0xffu;
+                for (int i = 0; i < B_CELLS; ++i)      // raw word: shifted where it is expanded, so nothing waits on this load here
+                    bw[i] = __ldg(pc + (int64_t)rows[b_k[i]] * wpr + b_w[i]);
                 return;
             }
             const uint32_t rid_a = rows[a_k];
@@ -292,7 +294,7 @@ dense_mm_t_tc_kernel(const float* __restrict__ W, int64_t k, int64_t m, const ui
                     bits = (__ldg(pc + (int64_t)rid * wpr + b_w[i]) >> b_sh[i]) & 0xffu;
                     if (b_c0[i] + 8 > n) bits &= (1u << (n - b_c0[i])) - 1u;
                 }
-                bw[i] = bits;
+                bw[i] = bits << b_sh[i];               // same form as the fast path (the consumer shifts back)
             }
         };
 
@@ -322,29 +324,37 @@ dense_mm_t_tc_kernel(const float* __restrict__ W, int64_t k, int64_t m, const ui
             // ---- B: 0/1 bf16 from the prefetched spike bits -----------------------------------------
 #pragma unroll
             for (int i = 0; i < B_CELLS; ++i) {
-                const uint32_t bits = cur_b[i];
+                const uint32_t bits = (cur_b[i] >> b_sh[i]) & 0xffu;
                 uint32_t v[4];
 #pragma unroll
                 for (int q = 0; q < 4; ++q)
                     v[q] = ((bits >> (2 * q)) & 1u ? 0x3f80u : 0u) | ((bits >> (2 * q + 1)) & 1u ? 0x3f800000u : 0u);
                 *reinterpret_cast<uint4*>(sB + b_soff[i]) = make_uint4(v[0], v[1], v[2], v[3]);
             }
-            // generic-proxy writes -> visible to the tensor core (async proxy)
+            // generic-proxy writes -> visible to the tensor core (async proxy); then the warp reports its part of the
+            // stage on the stage's mbarrier.  No CTA barrier: only the warp whose turn it is to issue the MMAs
+            // (round robin, step % 8) waits for the other seven -- the rest go straight on to the next k-block
+            // (ncu r2: 13 % of the samples sat at the per-k-block __syncthreads, with thread 0's MMA issue behind it)
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-            __syncthreads();
-            if (tid == 0) {
-                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                const uint32_t a0 = smem_u32(sA), b0 = smem_u32(sB);
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&full_bar[stage]);
+            if (warp == (n_issued & 7)) {
+                mbar_wait(&full_bar[stage], (n_issued / TC_STAGES) & 1);
+                if (lane == 0) {
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                    const uint32_t a0 = smem_u32(sA), b0 = smem_u32(sB);
 #pragma unroll
-                for (int ks = 0; ks < TC_BK / 16; ++ks) {
-                    const uint64_t bd = umma_desc(b0 + ks * 2 * TC_B_LBO, TC_B_LBO, TC_B_SBO);
+                    for (int ks = 0; ks < TC_BK / 16; ++ks) {
+                        const uint64_t bd = umma_desc(b0 + ks * 2 * TC_B_LBO, TC_B_LBO, TC_B_SBO);
 #pragma unroll
-                    for (int p = 0; p < 3; ++p) {
-                        const uint64_t ad = umma_desc(a0 + p * TC_A_PLANE + ks * 2 * TC_A_LBO, TC_A_LBO, TC_A_SBO);
-                        umma_bf16(tmem_d, ad, bd, tc_idesc(TC_BN), (n_issued > 0 || ks > 0 || p > 0) ? 1u : 0u);
+                        for (int p = 0; p < 3; ++p) {
+                            const uint64_t ad = umma_desc(a0 + p * TC_A_PLANE + ks * 2 * TC_A_LBO, TC_A_LBO, TC_A_SBO);
+                            umma_bf16(tmem_d, ad, bd, tc_idesc(TC_BN), (n_issued > 0 || ks > 0 || p > 0) ? 1u : 0u);
+                        }
                     }
+                    umma_commit(&empty_bar[stage]);     // arrives when these MMAs have finished reading smem
                 }
-                umma_commit(&empty_bar[stage]);     // arrives when these MMAs have finished reading smem
+                __syncwarp();
             }
             ++n_issued;
         };
@@ -361,8 +371,13 @@ dense_mm_t_tc_kernel(const float* __restrict__ W, int64_t k, int64_t m, const ui
 
     // ---- drain + epilogue ---------------------------------------------------------------------
     if (n_issued > 0) {
-        if (tid == 0) umma_commit(&done_bar);
-        mbar_wait(&done_bar, 0);
+        // the tensor pipe runs a CTA's MMAs in issue order and every step's commit covers the MMAs its issuing
+        // thread started: the last commit on each stage's barrier therefore covers everything
+#pragma unroll
+        for (int st = 0; st < TC_STAGES; ++st) {
+            const int uses = (n_issued - st + TC_STAGES - 1) / TC_STAGES;
+            if (uses > 0) mbar_wait(&empty_bar[st], (uses - 1) & 1);
+        }
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         // warp w reads TMEM lanes 32*(w%4)..+31 (its rows); 32-column chunks alternate between
         // the two warps that share a lane quadrant
@@ -411,7 +426,7 @@ int launch_dense_mm_t_tc(const float* W, int64_t k, int64_t m, const uint32_t* p
                          float* out, cudaStream_t s) {
     if (m == 0 || n == 0) return BE_B200_OK;
     const char* lm = getenv("BE_B200_TC_LANEMAP");
-    const int lane_map = lm ? atoi(lm) : 2;         // 2: conflict-free plane stores (see the kernel); 0 / 1: earlier maps (A/B)
+    const int lane_map = lm ? atoi(lm) : 0;         // 0: row-quad lanes (fastest measured); 1 / 2: alternative maps kept for A/B
     const char* pfe = getenv("BE_B200_TC_PREFETCH");
     const int pf_dist = pfe ? atoi(pfe) : 0;        // k-blocks of L2 prefetch distance; measured 8 % SLOWER at every distance 2..16, off
     // widest batch tile that the batch fills: W is read once per batch tile
