@@ -19,7 +19,7 @@ namespace be {
 // (n/8 bytes: 125 KB for 1 M neurons) into shared memory once per persistent CTA, where 32 random
 // 4-byte reads cost ~3-4 bank cycles, and runs 1024 threads per SM to keep the streams full.
 // ------------------------------------------------------------------------------------------
-template <typename T, bool HOMO, int PERM, bool VEC, int LPR, bool SMEM, typename Rows>
+template <typename T, bool HOMO, int PERM, bool VEC, int LPR, bool SMEM, typename Rows, int UQ = 0>
 __global__ void __launch_bounds__(SMEM ? 1024 : 256) gather_mv_kernel(Rows rows, const int32_t* __restrict__ indices,
                                                                       const T* __restrict__ weights,
                                                                       const void* __restrict__ perm,
@@ -127,7 +127,9 @@ __global__ void __launch_bounds__(SMEM ? 1024 : 256) gather_mv_kernel(Rows rows,
                     if (HOMO) ++cnt; else acc += weight_at<T, HOMO, PERM>(weights, perm, s + gl, w0);
                 }
                 // 4 independent 128-bit index loads per lane are issued before the first lookup
-                constexpr int U = (LPR <= 4) ? 8 : 4;   // narrow groups: more independent quads per lane
+                // narrow groups: more independent quads per lane.  UQ (launch-time choice, 4-lane groups only): just enough
+                // quads for the expected row -- 7 instead of 8 for 100-synapse rows, whose 8th slot is always masked
+                constexpr int U = UQ > 0 ? UQ : ((LPR <= 4) ? 8 : 4);
                 for (int64_t j0 = a + (int64_t)gl * 4; j0 < aend; j0 += (int64_t)LPR * 4 * U) {
                     int4 ix[U];
 #pragma unroll
@@ -338,16 +340,26 @@ static int launch_gather_mv(const Rows& rows, const ConnArgs& c, const Events& e
         size_t pend_bytes = defer_ok ? (bits_pad - (size_t)n_words) * 4 + (size_t)threads * 2 * 4 * 4 : 0;
         if (smem + pend_bytes > (227u << 10) - 1024) pend_bytes = 0;
         const int pend_off = pend_bytes ? (int)bits_pad : 0;
-#define BE_GAS(LPR)                                                                                           \
+#define BE_GAS2(LPR, UQ)                                                                                      \
         do {                                                                                                  \
-            BE_CUDA(cudaFuncSetAttribute(gather_mv_kernel<T, HOMO, PERM, true, LPR, true, Rows>,              \
+            BE_CUDA(cudaFuncSetAttribute(gather_mv_kernel<T, HOMO, PERM, true, LPR, true, Rows, UQ>,          \
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(227u << 10) - 1024));  \
-            gather_mv_kernel<T, HOMO, PERM, true, LPR, true, Rows><<<blocks, threads, smem + pend_bytes, s>>>(   \
+            gather_mv_kernel<T, HOMO, PERM, true, LPR, true, Rows, UQ><<<blocks, threads, smem + pend_bytes, s>>>( \
                 rows, c.indices, (const T*)c.weights, c.perm, evl.packed, n_words, n_rows, out, evl.n_active, evl.sel_thr, \
                 evl.raw_bool, evl.raw_n, pend_off);                                                           \
         } while (0)
-        switch (lpr) { case 4: BE_GAS(4); break; case 8: BE_GAS(8); break; case 16: BE_GAS(16); break; default: BE_GAS(32); }
+#define BE_GAS(LPR) BE_GAS2(LPR, 0)
+        // quads per lane of a 4-lane group: ceil(row / 16), at least 5 (rows that are longer simply take a second trip)
+        int uq = 8;
+        if (const char* e = getenv("BE_B200_GATHER_UQ")) uq = atoi(e);
+        else if (lpr == 4) uq = std::max(5, std::min(8, (int)((c.avg_row + 15.0) / 16.0)));
+        if (lpr == 4 && uq >= 5 && uq < 8) {
+            if (uq == 5) BE_GAS2(4, 5); else if (uq == 6) BE_GAS2(4, 6); else BE_GAS2(4, 7);
+        } else {
+            switch (lpr) { case 4: BE_GAS(4); break; case 8: BE_GAS(8); break; case 16: BE_GAS(16); break; default: BE_GAS(32); }
+        }
 #undef BE_GAS
+#undef BE_GAS2
     } else {
         int blocks = (int)std::min<int64_t>(ceil_div(n_rows, 256 / lpr), (int64_t)kNumSM * 16);
 #define BE_GA(VEC, LPR)                                                                      \

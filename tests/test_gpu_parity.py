@@ -400,6 +400,33 @@ def test_rate_selected_scatter_or_gather(G, homo, rate):
         np.testing.assert_array_equal(a, b)
 
 
+@pytest.mark.parametrize("rate", [0.01, 0.2, 0.7])
+@pytest.mark.parametrize("nnz", [100, 37, 520])
+def test_gather_shared_memory_path_deferred_weights(G, rate, nnz):
+    """csr @ spk (gather, transpose=False) on a matrix large enough for the persistent shared-memory kernel
+    (spike bits in shared memory, fp32 hit weights deferred through cp.async slots).  High rates overflow the four
+    slots a lane has per row (the rest is summed in place); ragged rows cover head / tail peels.  Checked against
+    the oracle (double accumulation) and for bit-reproducibility (the path is deterministic)."""
+    m, k = 120_000, 90_000
+    rng = np.random.default_rng(7 + nnz)
+    counts = rng.integers(max(nnz - 9, 0), nnz + 10, m)
+    counts[::97] = 0
+    indptr = np.zeros(m + 1, np.int32)
+    np.cumsum(counts, out=indptr[1:])
+    nse = int(indptr[-1])
+    indices = rng.integers(0, k, nse, dtype=np.int32)
+    data = rng.standard_normal(nse).astype(np.float32)
+    v = rng.random(k) < rate
+    ref = O.binary_csrmv(data, indices, indptr, v, shape=(m, k), transpose=False)
+    got = G.binary_csrmv(data, indices, indptr, v, shape=(m, k), transpose=False)
+    # fp32 accumulation of ~nnz * rate unit-scale terms against a double sum: eps x terms bounds the difference
+    np.testing.assert_allclose(got, ref, rtol=RTOL, atol=1e-6 + 1.2e-7 * (nnz * rate + 1))
+    np.testing.assert_array_equal(got, G.binary_csrmv(data, indices, indptr, v, shape=(m, k), transpose=False))
+    homo = G.binary_csrmv(np.float32(0.5), indices, indptr, v, shape=(m, k), transpose=False)
+    np.testing.assert_allclose(homo, O.binary_csrmv(np.float32(0.5), indices, indptr, v, shape=(m, k), transpose=False),
+                               rtol=RTOL, atol=ATOL)
+
+
 # ---- BASELINE.json sizes ---------------------------------------------------------------------
 def test_baseline_c2_cuba_400k_jitc_scalar(G):
     """configs[1]: JITCScalarR (320000, 400000) and (80000, 400000), prob 2e-4, seed 42, 0.24 % spikes.
