@@ -254,6 +254,9 @@ class FcnSharded(Workload):
                 self.launches_per_timestep = 4
             self.proj = bd.PostShardedProjection("csr", n_total, n_total, self.x, data=self.weights, indices=self.indices,
                                                  indptr=self.indptr)
+            if os.environ.get("BE_B200_SHARDED_FUSED") == "0" and self.proj._h is not None:     # A/B: three-kernel form
+                self.proj.set_option("fused", 0)
+                self.dominant_kernel = "scatter_mv_kernel"
             indptr_bytes = 8.0 * self.active_per_timestep
         del gpool
         # 8 B/event + packed spikes + indptr pair per active row (CSR) + the output vector
