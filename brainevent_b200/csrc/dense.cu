@@ -30,15 +30,33 @@ __global__ void __launch_bounds__(256) dense_mv_t_kernel(const T* __restrict__ W
     if (c0 >= cols) return;
     A acc[4] = {A(0), A(0), A(0), A(0)};
     const bool full = vec && (c0 + 4 <= cols);
-    for (int a = blockIdx.y; a < n_active; a += gridDim.y) {
-        const T* row = W + (int64_t)__ldg(ids + a) * cols + c0;
-        if (full) {
-            Vec4<T> v = load4(row);
+    // U active rows per trip: their ids first, then U independent 128-bit row loads, then the adds -- with one
+    // row per trip a thread had a single load in flight behind a dependent id load (65536 x 32768 at 1 %: 51 us for
+    // 86 MB, 1.7 TB/s)
+    constexpr int U = 8;
+    for (int a0 = blockIdx.y * U; a0 < n_active; a0 += gridDim.y * U) {
+        int rid[U];
 #pragma unroll
-            for (int q = 0; q < 4; ++q) acc[q] += v.v[q];
+        for (int u = 0; u < U; ++u) rid[u] = (a0 + u < n_active) ? __ldg(ids + a0 + u) : -1;
+        if (full) {
+            Vec4<T> v[U];
+#pragma unroll
+            for (int u = 0; u < U; ++u)
+                if (rid[u] >= 0) v[u] = load4(W + (int64_t)rid[u] * cols + c0);
+#pragma unroll
+            for (int u = 0; u < U; ++u)
+                if (rid[u] >= 0) {
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) acc[q] += v[u].v[q];
+                }
         } else {
 #pragma unroll
-            for (int q = 0; q < 4; ++q) if (c0 + q < cols) acc[q] += to_acc<T>(__ldg(row + q));
+            for (int u = 0; u < U; ++u)
+                if (rid[u] >= 0) {
+                    const T* row = W + (int64_t)rid[u] * cols + c0;
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) if (c0 + q < cols) acc[q] += to_acc<T>(__ldg(row + q));
+                }
         }
     }
 #pragma unroll
@@ -170,7 +188,7 @@ static int run_dense_mv(const T* W, int64_t rows, int64_t cols, const Events& ev
     if (transpose) {
         if (cols == 0) return BE_B200_OK;
         const int64_t col_blocks = ceil_div(ceil_div(cols, 4), 256);
-        int slices = (int)std::max<int64_t>(1, std::min<int64_t>(64, (2 * kNumSM) / col_blocks));
+        int slices = (int)std::max<int64_t>(1, std::min<int64_t>(64, (4 * kNumSM) / col_blocks));
         if (slices > 1) BE_CUDA(cudaMemsetAsync(out, 0, (size_t)cols * sizeof(T), s));
         const bool vec = (((uintptr_t)W & 15u) == 0) && ((cols * sizeof(T)) % 16 == 0);
         dim3 grid((unsigned)col_blocks, (unsigned)slices);
