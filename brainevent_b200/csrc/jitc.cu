@@ -48,6 +48,9 @@ __global__ void __launch_bounds__(256) jit_mv_gather_kernel(JitParams jp, const 
             // column j = cs + lane + 32 q  ->  word (cs+lane)/32 + q, bit (cs+lane)%32: invariant shift
             const int64_t b0 = cs + lane;
             const uint32_t* wp = packed + (b0 >> 5);
+            // opaque to the optimiser: it otherwise folds (b0 >> 5) + q into one 64-bit index and spends four
+            // instructions per walk step on the address instead of one IMAD.WIDE on this pointer
+            asm volatile("" : "+l"(wp));
             const uint32_t sh = (uint32_t)(b0 & 31);
             while (q < qmax) {
                 const uint32_t bit = (__ldg(wp + q) >> sh) & 1u;
