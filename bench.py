@@ -953,7 +953,8 @@ def e2e_leg(torch, dist, L, wl, world, device, K, T, numa_bound):
     host_spk = [torch.empty(n_in, dtype=torch.uint8).pin_memory() for _ in range(POOL)]
     for i in range(POOL):
         host_spk[i].copy_(wl.pool[i].to(torch.uint8))
-    host_out = [torch.empty(n_out, dtype=torch.float32).pin_memory() for _ in range(4)]
+    n_slots = int(os.environ.get("BE_B200_E2E_SLOTS", "8"))       # timesteps in flight at N > 1 (N = 2: 137 us with 4, 126 us with 8)
+    host_out = [torch.empty(n_out, dtype=torch.float32).pin_memory() for _ in range(max(4, n_slots))]
     Te = min(T, 50)
     sync_value = None
     lib = L.lib()
@@ -989,11 +990,11 @@ def e2e_leg(torch, dist, L, wl, world, device, K, T, numa_bound):
                  "be_b200_projection_apply_host)")
     else:
         from brainevent_b200 import dist as bd
-        pipe = bd.HostStepPipeline(wl.proj, n_in, slots=4)
+        pipe = bd.HostStepPipeline(wl.proj, n_in, slots=n_slots)
 
         def e2e_step():
             pipe.run(Te, host_spk, host_out)
-        entry = ("be_b200_sharded_run_host (C ABI, csrc/sharded.cu: one call per block of timesteps, 4 in flight, a CUDA "
+        entry = (f"be_b200_sharded_run_host (C ABI, csrc/sharded.cu: one call per block of timesteps, {n_slots} in flight, a CUDA "
                  "graph of the fused step per slot)" if pipe.native else
                  "HostStepPipeline.submit/wait over PostShardedProjection.step (Python-driven, NCCL exchange)")
     for _ in range(2):
