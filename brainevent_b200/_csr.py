@@ -116,7 +116,11 @@ def binary_csrmv(data, indices, indptr, v, *, shape, transpose=False, backend=No
     """y = A @ e(v) (or A^T @ e(v)); only active entries of v contribute (ref: _csr/binary.py:128)."""
     data, unitd = split_mantissa_unit(data)
     v, unitv = split_mantissa_unit(v)
-    res = binary_csrmv_p_call(data, indices, indptr, v, shape=shape, transpose=transpose, backend=backend)[0]
+    from . import _autograd
+    if _autograd.needs_grad(data, v):      # torch.autograd rule (ref: the primitive's jvp / transpose rules, :656-722)
+        res = _autograd.csrmv(data, as_tensor(indices), as_tensor(indptr), v, shape, transpose, backend)
+    else:
+        res = binary_csrmv_p_call(data, indices, indptr, v, shape=shape, transpose=transpose, backend=backend)[0]
     return maybe_decimal(res, unitd, unitv)
 
 

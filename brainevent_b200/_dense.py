@@ -63,7 +63,11 @@ def binary_densemv(weights, spikes, *, transpose, backend=None):
     """weights[m,k] @ spikes[k] (transpose=False) or spikes[k] @ weights[k,n] (transpose=True)."""
     weights, wunit = split_mantissa_unit(weights)
     spikes, sunit = split_mantissa_unit(spikes)
-    r = binary_densemv_p_call(weights, spikes, transpose=transpose, backend=backend)[0]
+    from . import _autograd
+    if _autograd.needs_grad(weights, spikes):
+        r = _autograd.densemv(weights, spikes, transpose, backend)
+    else:
+        r = binary_densemv_p_call(weights, spikes, transpose=transpose, backend=backend)[0]
     return maybe_decimal(r, wunit, sunit)
 
 

@@ -84,7 +84,11 @@ def binary_fcnmv(weights, indices, spikes, *, shape, transpose=False, backend=No
     """y = W @ s (gather) or W^T @ s (scatter, transpose=True); ref: _fcn/binary.py:43."""
     weights, w_unit = split_mantissa_unit(weights)
     spikes, v_unit = split_mantissa_unit(spikes)
-    r = binary_fcnmv_p_call(weights, indices, spikes, shape=shape, transpose=transpose, backend=backend)[0]
+    from . import _autograd
+    if _autograd.needs_grad(weights, spikes):
+        r = _autograd.fcnmv(weights, torch.as_tensor(indices), spikes, shape, transpose, backend)
+    else:
+        r = binary_fcnmv_p_call(weights, indices, spikes, shape=shape, transpose=transpose, backend=backend)[0]
     return maybe_decimal(r, v_unit, w_unit)
 
 
