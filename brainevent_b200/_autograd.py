@@ -162,3 +162,32 @@ def fcnmv(weights, indices, events, shape, transpose, backend):
 def densemv(weights, events, transpose, backend):
     ev = _raw(events)
     return _DenseMv.apply(weights, ev, events, bool(transpose), backend)
+
+
+class _LinearInParams(torch.autograd.Function):
+    """y = call(params) is linear in a few scalar parameters (JITC weight parameters: the scalar weight, (w_loc,
+    w_scale), (w_low, w_high); ref: the jvp rules of _jit_scalar / _jit_normal / _jit_uniform binary.py): the cotangent
+    of parameter i is <ct_y, call(e_i)>, one regenerating product with a unit parameter vector."""
+
+    @staticmethod
+    def forward(ctx, call, *params):
+        ctx.call = call
+        ctx.save_for_backward(*[p.detach() for p in params])
+        return call([p.detach() for p in params])
+
+    @staticmethod
+    def backward(ctx, g):
+        params = ctx.saved_tensors
+        grads = []
+        for i, p in enumerate(params):
+            if not ctx.needs_input_grad[1 + i]:
+                grads.append(None)
+                continue
+            unit = [torch.ones_like(q) if j == i else torch.zeros_like(q) for j, q in enumerate(params)]
+            y = ctx.call(unit)
+            grads.append((g.to(y.dtype) * y).sum().to(p.dtype).reshape(p.shape))
+        return (None, *grads)
+
+
+def linear_in_params(call, params):
+    return _LinearInParams.apply(call, *params)

@@ -137,7 +137,12 @@ def _public(prim, n_params, matmat, doc):
         dev = event_args(x).device
         seed = _initialize_seed(seed, dev)
         clen = _initialize_conn_length(prob, dev)
-        res = _jit_p_call(prim, vals, clen, x, seed, shape, transpose, corder, backend, matmat, **extra)[0]
+        call = lambda ps: _jit_p_call(prim, ps, clen, x, seed, shape, transpose, corder, backend, matmat, **extra)[0]
+        if torch.is_grad_enabled() and any(isinstance(v, torch.Tensor) and v.requires_grad for v in vals):
+            from . import _autograd           # the operator is linear in its weight parameters (ref: the primitives' jvp rules)
+            res = _autograd.linear_in_params(call, [as_tensor(v, device=dev) for v in vals])
+        else:
+            res = call(vals)
         return maybe_decimal(res, units[0], unx)
     op.__doc__ = doc
     return op

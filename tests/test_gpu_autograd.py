@@ -125,3 +125,33 @@ def test_grad_through_the_matrix_classes(be):
     y = be.BinaryArray(t(act)) @ be.FixedNumPerPre((wf, t(idx)), shape=(m, k))
     (y * t(g)).sum().backward()
     np.testing.assert_allclose(wf.grad.cpu().numpy(), (act[:, None] * g[idx]).astype(np.float32), rtol=1e-5, atol=1e-6)
+
+
+@pytest.mark.parametrize("family", ["scalar", "normal", "uniform"])
+@pytest.mark.parametrize("corder", [True, False])
+def test_jitc_parameter_grads(be, family, corder):
+    """JITC products are linear in their weight parameters: d<g, y>/dp_i = <g, y(e_i)>, checked against the oracle's
+    product with unit parameters."""
+    rng = np.random.default_rng(13)
+    shape, prob, seed = (900, 1100), 0.02, 77
+    act = rng.random(shape[0]) < 0.2
+    g = rng.standard_normal(shape[1]).astype(np.float32)
+    t = lambda a: torch.as_tensor(a, device="cuda")
+    if family == "scalar":
+        ps = [t(np.float32([0.8])).requires_grad_(True)]
+        y = be.binary_jitsmv(ps[0], prob, t(act), seed, shape=shape, transpose=True, corder=corder)
+        units = [O.binary_jitsmv(1.0, prob, act, seed, shape=shape, transpose=True, corder=corder)]
+    elif family == "normal":
+        ps = [t(np.float32([0.5])).requires_grad_(True), t(np.float32([0.2])).requires_grad_(True)]
+        y = be.binary_jitnmv(ps[0], ps[1], prob, t(act), seed, shape=shape, transpose=True, corder=corder)
+        units = [O.binary_jitnmv(1.0, 0.0, prob, act, seed, shape=shape, transpose=True, corder=corder),
+                 O.binary_jitnmv(0.0, 1.0, prob, act, seed, shape=shape, transpose=True, corder=corder)]
+    else:
+        ps = [t(np.float32([-0.3])).requires_grad_(True), t(np.float32([0.9])).requires_grad_(True)]
+        y = be.binary_jitumv(ps[0], ps[1], prob, t(act), seed, shape=shape, transpose=True, corder=corder)
+        units = [O.binary_jitumv(1.0, 0.0, prob, act, seed, shape=shape, transpose=True, corder=corder),
+                 O.binary_jitumv(0.0, 1.0, prob, act, seed, shape=shape, transpose=True, corder=corder)]
+    (y * t(g)).sum().backward()
+    for p, u in zip(ps, units):
+        expect = float(np.dot(g.astype(np.float64), np.asarray(u, np.float64)))
+        np.testing.assert_allclose(float(p.grad.item()), expect, rtol=2e-4, atol=2e-3)
