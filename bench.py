@@ -347,7 +347,7 @@ def parity_block(torch, dist, be, wl):
 
 class Coba(Workload):
     name = "coba_4000_csr"
-    dominant_kernel = "scatter_mv_kernel"
+    dominant_kernel = "scatter_mv_small_kernel"
     bytes_per_event = 4.0   # homogeneous weight: indices only
 
     def __init__(self, torch, be, device):
@@ -367,7 +367,7 @@ class Coba(Workload):
             ev += a * 80
         self.events_per_timestep = ev
         self.extra_bytes_per_timestep = 12.0 * act
-        self.launches_per_timestep = 4
+        self.launches_per_timestep = 2          # one single-cluster launch per projection (compaction + clear + scatter)
         self.profiled_kernels_per_timestep = 2
         self.config = {"workload": "COBA_2005: 4000-neuron E/I network, 80 synapses/neuron CSR, homogeneous weights, "
                                    "0.5% spikes/timestep, BinaryArray @ CSR (BASELINE configs[0])"}

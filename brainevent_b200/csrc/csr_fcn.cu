@@ -264,6 +264,78 @@ static int launch_scatter_mv(const Rows& rows, const ConnArgs& c, const Events& 
     return BE_B200_OK;
 }
 
+
+// ------------------------------------------------------------------------------------------
+// scatter, matvec, SMALL networks: ONE launch of ONE thread-block cluster (8 CTAs x 1024 threads).
+// A few-thousand-neuron projection (the reference's own examples: COBA / CUBA at 4 000 neurons) spends its time in
+// launch latency -- compaction kernel + scatter kernel, ~5 us for a few thousand reductions.  Here every CTA clears
+// its share of the output and compacts its share of the spike vector into shared memory, the cluster barrier
+// (hardware, release / acquire) orders the clear before any reduction, and every CTA then scatters the rows it found.
+// No workspace, no global id list, no second launch.
+// ------------------------------------------------------------------------------------------
+constexpr int kSmallCtas = 8, kSmallThreads = 1024;
+constexpr int64_t kSmallMaxSrc = (int64_t)kSmallCtas * 4096;     // sources (4096 list entries per CTA)
+constexpr int64_t kSmallMaxOut = 1 << 18;                        // outputs cleared inside the kernel
+
+template <typename T, bool HOMO, int PERM, int VEC, int KIND, typename Rows>
+__global__ void __cluster_dims__(kSmallCtas, 1, 1) __launch_bounds__(kSmallThreads)
+scatter_mv_small_kernel(Rows rows, const int32_t* __restrict__ indices, const T* __restrict__ weights,
+                        const void* __restrict__ perm, const void* __restrict__ spikes, int64_t n_src,
+                        T* __restrict__ out, int64_t n_out) {
+    using A = typename Acc<T>::type;
+    __shared__ int s_list[4096];
+    __shared__ int s_n;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const A w0 = HOMO ? to_acc<T>(__ldg(weights)) : A(0);
+    if (tid == 0) s_n = 0;
+    for (int64_t i = (int64_t)blockIdx.x * kSmallThreads + tid; i < n_out; i += (int64_t)kSmallCtas * kSmallThreads) out[i] = T(0);
+    __syncthreads();
+    const int64_t per = (n_src + kSmallCtas - 1) / kSmallCtas;
+    const int64_t lo = (int64_t)blockIdx.x * per, hi = min(n_src, lo + per);
+    for (int64_t base = lo; base < hi; base += kSmallThreads) {
+        const int64_t i = base + tid;
+        bool on = false;
+        if (i < hi) {
+            if (KIND == BE_B200_SPK_BOOL) on = __ldg((const uint8_t*)spikes + i) != 0;
+            else if (KIND == BE_B200_SPK_F32) on = __ldg((const float*)spikes + i) > 0.0f;
+            else on = (__ldg((const uint32_t*)spikes + (i >> 5)) >> (i & 31)) & 1u;
+        }
+        const uint32_t bal = __ballot_sync(0xffffffffu, on);
+        int pos = 0;
+        if (lane == 0 && bal) pos = atomicAdd(&s_n, __popc(bal));
+        pos = __shfl_sync(0xffffffffu, pos, 0);
+        if (on) s_list[pos + __popc(bal & ((1u << lane) - 1u))] = (int)i;
+    }
+    __threadfence();        // the cleared outputs are visible device-wide before any CTA of the cluster reduces into them
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+    const int n = s_n;
+    for (int a = warp; a < n; a += kSmallThreads / 32) {
+        int64_t s, e;
+        rows.get(s_list[a], s, e);
+        scatter_segment<T, HOMO, PERM, VEC, 32>(s, e, lane, indices, weights, perm, w0, out);
+    }
+}
+
+template <typename T, bool HOMO, int PERM, typename Rows>
+static int launch_scatter_mv_small(const Rows& rows, const ConnArgs& c, const void* spikes, int spk_kind, int64_t n_src,
+                                   T* out, int64_t n_out, cudaStream_t s) {
+    const int vec = vec_mode(rows, c);
+#define BE_SS(VEC, KIND)                                                                                   \
+    scatter_mv_small_kernel<T, HOMO, PERM, VEC, KIND, Rows><<<kSmallCtas, kSmallThreads, 0, s>>>(          \
+        rows, c.indices, (const T*)c.weights, c.perm, spikes, n_src, out, n_out)
+#define BE_SS_K(VEC)                                                                                       \
+    do { if (spk_kind == BE_B200_SPK_BOOL) BE_SS(VEC, BE_B200_SPK_BOOL);                                   \
+         else if (spk_kind == BE_B200_SPK_F32) BE_SS(VEC, BE_B200_SPK_F32); else BE_SS(VEC, BE_B200_SPK_PACKED); } while (0)
+    {
+        ProfileScope prof(s);
+        if (vec == 2) BE_SS_K(2); else if (vec == 1) BE_SS_K(1); else BE_SS_K(0);
+    }
+#undef BE_SS_K
+#undef BE_SS
+    BE_LAUNCH_CHECK("scatter_mv_small_kernel");
+    return BE_B200_OK;
+}
+
 constexpr size_t kL2TileBytesDefault = 48u << 20;   // output tile kept L2-resident per scatter pass (L2 = 126 MB)
 static size_t l2_tile_bytes() {
     if (const char* e = getenv("BE_B200_SPMM_TILE_MB")) { const long v = atol(e); if (v >= 1 && v <= 4096) return (size_t)v << 20; }   // A/B switch
@@ -318,6 +390,11 @@ static int launch_scatter_mm_bm(const Rows& rows, const ConnArgs& c, const Event
     return BE_B200_OK;
 }
 
+static bool small_path_enabled() {            // BE_B200_SMALL_SCATTER=0: always the two-kernel path (A/B)
+    const char* e = getenv("BE_B200_SMALL_SCATTER");
+    return !(e && e[0] == '0');
+}
+
 // One entry for all four shapes.  n == 0 means matvec.
 template <typename T, typename Rows>
 static int run_conn(const Rows& rows, const RowsDesc& rd, const ConnArgs& c, const void* spikes, const void* aux,
@@ -329,6 +406,19 @@ static int run_conn(const Rows& rows, const RowsDesc& rd, const ConnArgs& c, con
     int rc;
     const bool mm = n_batch > 0;
     const int64_t out_elems = n_out * (mm ? n_batch : 1);
+    // small networks: one single-cluster launch does compaction, output clear and scatter (latency, not bandwidth)
+    if (scatter && !mm && n_src > 0 && n_src <= kSmallMaxSrc && n_out > 0 && n_out <= kSmallMaxOut &&
+        (spk_kind == BE_B200_SPK_BOOL || spk_kind == BE_B200_SPK_F32 || spk_kind == BE_B200_SPK_PACKED) &&
+        (double)n_src * c.avg_row <= 4.0e6 && small_path_enabled()) {
+#define BE_RUN_SMALL(HOMO, PERM) return launch_scatter_mv_small<T, HOMO, PERM, Rows>(rows, c, spikes, spk_kind, n_src, out, n_out, s)
+        if (c.homo) BE_RUN_SMALL(true, 0);
+        if constexpr (!std::is_same<Rows, FcnRows>::value) {
+            if (c.perm_kind == 1) BE_RUN_SMALL(false, 1);
+            if (c.perm_kind == 2) BE_RUN_SMALL(false, 2);
+        }
+        BE_RUN_SMALL(false, 0);
+#undef BE_RUN_SMALL
+    }
     ev.defer_pack_ok = !mm && !scatter;     // the matvec gather can pack small bool vectors itself
     if (mm) rc = prepare_events_2d(spikes, aux, spk_kind, n_src, n_batch, scatter, workspace, workspace_bytes, s, &ev);
     else rc = prepare_events_1d(spikes, aux, spk_kind, n_src, scatter, !scatter, workspace, workspace_bytes, s, &ev,
