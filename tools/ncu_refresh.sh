@@ -26,3 +26,4 @@ python bench.py --steps 2 --warmup 3 --no-extra --no-cpu --no-e2e > gpurun_out/$
 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file gpurun_out/${P}_fcn_launches.csv \
     python bench.py --steps 2 --warmup 3 --no-extra --no-cpu --no-e2e > /dev/null 2>&1
 wc -l gpurun_out/${P}_fcn_launches.csv
+# (later in round 2 the same `cap` was run for: coba -> scatter_mv_small, jitc_1m_gather / cuba_jitc_gather -> jit_mv_gather)
