@@ -427,6 +427,34 @@ def test_gather_shared_memory_path_deferred_weights(G, rate, nnz):
                                rtol=RTOL, atol=ATOL)
 
 
+@pytest.mark.parametrize("n_src,n_out", [(32768, 4000), (32769, 4000), (5000, 262144), (5000, 262145), (1, 7), (4097, 33)])
+@pytest.mark.parametrize("kind", ["bool", "float", "packed"])
+def test_small_network_scatter_boundaries(G, n_src, n_out, kind):
+    """Either side of the single-launch small-network scatter's limits (<= 32768 sources, <= 2^18 outputs): one
+    thread-block cluster does output clear + compaction + scatter there, the two-kernel path beyond -- same result.
+    Ragged rows incl. one heavy and one empty row; bool / float / bit-packed events; CSR hetero, CSR homo, ELL."""
+    import brainevent_b200 as be
+    c = cases.csr_case(n_src + n_out, n_src, n_out, 6, 0.05, ragged=True)
+    v = cases.spikes(3 + n_src, n_src, 0.05, float_spikes=(kind == "float"))
+    ref = O.binary_csrmv(c["data"], c["indices"], c["indptr"], v, shape=c["shape"], transpose=True)
+    t = lambda x: torch.as_tensor(x, device="cuda")
+    ev = be.BitPackedBinary(t(v)) if kind == "packed" else t(v)
+    got = be.binary_csrmv(t(c["data"]), t(c["indices"]), t(c["indptr"]), ev, shape=c["shape"], transpose=True)
+    np.testing.assert_allclose(got.cpu().numpy(), ref, rtol=RTOL, atol=2e-5)
+    h = np.float32([0.75])
+    got = be.binary_csrmv(t(h), t(c["indices"]), t(c["indptr"]), ev, shape=c["shape"], transpose=True)
+    np.testing.assert_allclose(got.cpu().numpy(),
+                               O.binary_csrmv(h, c["indices"], c["indptr"], v, shape=c["shape"], transpose=True),
+                               rtol=RTOL, atol=2e-5)
+    rng = np.random.default_rng(n_src)
+    n_conn = 5
+    idx = rng.integers(0, n_out, (n_src, n_conn)).astype(np.int32)
+    w = rng.standard_normal((n_src, n_conn)).astype(np.float32)
+    got = be.binary_fcnmv(t(w), t(idx), ev, shape=(n_src, n_out), transpose=True)
+    np.testing.assert_allclose(got.cpu().numpy(), O.binary_fcnmv(w, idx, v, shape=(n_src, n_out), transpose=True),
+                               rtol=RTOL, atol=2e-5)
+
+
 # ---- BASELINE.json sizes ---------------------------------------------------------------------
 def test_baseline_c2_cuba_400k_jitc_scalar(G):
     """configs[1]: JITCScalarR (320000, 400000) and (80000, 400000), prob 2e-4, seed 42, 0.24 % spikes.
