@@ -433,7 +433,13 @@ int launch_dense_mm_t_tc(const float* W, int64_t k, int64_t m, const uint32_t* p
     const int bn = n > 128 ? 256 : (n > 64 ? 128 : 64);
     const int total_kb = (int)ceil_div(k, TC_BK);
     const int64_t tiles = ceil_div(m, TC_BM) * ceil_div(n, bn);
-    int split_k = (int)std::max<int64_t>(1, std::min<int64_t>({(int64_t)total_kb, (6 * kNumSM) / std::max<int64_t>(tiles, 1), (int64_t)32}));
+    // split K so that the grid is ONE wave of resident CTAs (3 per SM at batch tile 64, 2 above): CTAs of a call all take
+    // the same time, so 768 CTAs on 444 slots ran as two waves with the second 73 % full -- 384 CTAs (split 3) are 3 %
+    // faster at batch 64 and 256 instead of 768 CTAs 11 % faster at batch 256 (profiles/r2_experiments.txt); fewer
+    // splits also mean fewer RED epilogues
+    const int64_t slots = (int64_t)(bn == 64 ? 3 : 2) * kNumSM;
+    int split_k = (int)std::max<int64_t>(1, std::min<int64_t>({(int64_t)total_kb, slots / std::max<int64_t>(tiles, 1), (int64_t)32}));
+    if (const char* e = getenv("BE_B200_TC_SPLITK")) split_k = std::max(1, std::min(atoi(e), std::max(total_kb, 1)));   // A/B switch
     const int kb_per_split = (int)ceil_div(std::max(total_kb, 1), split_k);
     split_k = (int)ceil_div(std::max(total_kb, 1), kb_per_split);
     if (split_k > 1) BE_CUDA(cudaMemsetAsync(out, 0, (size_t)(m * n) * sizeof(float), s));
