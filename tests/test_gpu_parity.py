@@ -455,6 +455,19 @@ def test_small_network_scatter_boundaries(G, n_src, n_out, kind):
                                rtol=RTOL, atol=2e-5)
 
 
+def test_small_network_scatter_all_active(G):
+    """every source fires at the largest size the single-launch path takes: each CTA's shared-memory row list is
+    filled to its last slot (8 x 4096)"""
+    import brainevent_b200 as be
+    n_src, n_out = 32768, 1000
+    c = cases.csr_case(5, n_src, n_out, 3, 1.0)
+    v = np.ones(n_src, bool)
+    t = lambda x: torch.as_tensor(x, device="cuda")
+    got = be.binary_csrmv(t(c["data"]), t(c["indices"]), t(c["indptr"]), t(v), shape=c["shape"], transpose=True)
+    ref = O.binary_csrmv(c["data"], c["indices"], c["indptr"], v, shape=c["shape"], transpose=True)
+    np.testing.assert_allclose(got.cpu().numpy(), ref, rtol=1e-4, atol=2e-4)     # ~100 terms per output, atomic order
+
+
 # ---- BASELINE.json sizes ---------------------------------------------------------------------
 def test_baseline_c2_cuba_400k_jitc_scalar(G):
     """configs[1]: JITCScalarR (320000, 400000) and (80000, 400000), prob 2e-4, seed 42, 0.24 % spikes.
